@@ -1,0 +1,140 @@
+// tg_common.cuh — shared helpers for the topicgcn sm_100a kernels (error plumbing, Philox, vector ld/st).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/topicgcn.h"
+
+namespace tg {
+
+// ---- error plumbing -------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define TG_CUDA(call)                                                          \
+    do {                                                                       \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess) return tg::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define TG_REQUIRE(cond, code, ...)   \
+    do {                              \
+        if (!(cond)) {                \
+            tg::set_error(__VA_ARGS__); \
+            return (code);            \
+        }                             \
+    } while (0)
+
+#define TG_LAUNCH_CHECK() TG_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs
+
+// ---- plan (opaque in the C header) ------------------------------------------------------------------
+}  // namespace tg
+
+struct tg_plan {
+    int64_t n_rows = 0, n_cols = 0, nnz = 0;
+    int32_t hub_threshold = 0, segment_nnz = 0;
+    int32_t n_hub = 0, n_seg = 0;
+    int64_t hub_nnz = 0;
+    int32_t max_row_nnz = 0;
+    // device tables (owned)
+    int32_t* hub_rows = nullptr;     // [n_hub]   row id of each split row
+    int32_t* hub_seg_ptr = nullptr;  // [n_hub+1] first segment of each split row
+    int32_t* seg_hub = nullptr;      // [n_seg]   hub slot a segment belongs to
+    int32_t* seg_begin = nullptr;    // [n_seg]   first stored entry of the segment
+    int32_t* seg_end = nullptr;      // [n_seg]   one past the last stored entry
+    uint32_t* tickets = nullptr;     // [n_hub]   arrival counters (integer; reset by the last arriver)
+};
+
+namespace tg {
+
+// ---- Philox4x32-10 (Salmon et al., SC'11) — counter-based RNG for the dropout keep mask -------------
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                           uint32_t c3, uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+// Keep-mask definition shared by every kernel (and restated in oracle/gcn_oracle.py):
+//   element (row, col):  q = col / 4 (float4 chunk), slot = q % 32, j = q / 64, half = (q / 32) % 2
+//   r = philox(counter = (row_lo, row_hi, slot | j << 8, offset_lo), key = (seed_lo ^ offset_hi, seed_hi))
+//   u16 #(half*4 + col%4) of the 128 random bits;  keep  <=>  u16 < keep_threshold(p)
+__host__ __device__ __forceinline__ uint32_t dropout_keep_threshold(float p) {
+    float t = (1.0f - p) * 65536.0f + 0.5f;
+    if (t < 0.f) t = 0.f;
+    if (t > 65536.f) t = 65536.f;
+    return (uint32_t)t;
+}
+
+__host__ __device__ __forceinline__ Philox4 dropout_philox(int64_t row, uint32_t slot, uint32_t j,
+                                                            uint64_t seed, uint64_t offset) {
+    return philox4x32_10((uint32_t)(uint64_t)row, (uint32_t)((uint64_t)row >> 32), slot | (j << 8),
+                         (uint32_t)offset, (uint32_t)seed ^ (uint32_t)(offset >> 32),
+                         (uint32_t)(seed >> 32));
+}
+
+// the four u16 lanes that belong to chunk-half `half` (0/1) of a Philox result
+__host__ __device__ __forceinline__ void dropout_u16x4(const Philox4& r, int half, uint32_t u[4]) {
+    const uint32_t a = half ? r.z : r.x, b = half ? r.w : r.y;
+    u[0] = a & 0xFFFFu; u[1] = a >> 16; u[2] = b & 0xFFFFu; u[3] = b >> 16;
+}
+
+// ---- vector helpers ----------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float4 ldg_f4(const float* p) {  // read-only path, 128-bit
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float4 ldg_f4_stream(const float* p) {  // streamed once: do not keep in L1
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_f4(float* p, const float4& v) {
+    *reinterpret_cast<float4*>(p) = v;
+}
+__device__ __forceinline__ void st_f4_stream(float* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void fma4(float4& acc, float a, const float4& b) {
+    acc.x = fmaf(a, b.x, acc.x);
+    acc.y = fmaf(a, b.y, acc.y);
+    acc.z = fmaf(a, b.z, acc.z);
+    acc.w = fmaf(a, b.w, acc.w);
+}
+__device__ __forceinline__ void add4(float4& acc, const float4& b) {
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+}
+#endif
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace tg
