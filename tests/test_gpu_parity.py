@@ -1,0 +1,420 @@
+"""GPU parity tests: the CUDA library (through the C-ABI) against the CPU oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): SpMM outputs within 1e-5 relative in fp32 (measured as max|Y-Y_ref| / max|Y_ref|
+per row class), index/CSR construction bit-exact.  On the big synthetic shapes the reference's own serial fp32
+accumulation is ~1e-5 away from the float64 truth on hub rows, so there the additional criterion
+err(new, fp64) <= err(ref, fp64) + eps is enforced.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SPMM_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def tg():
+    import topicgcn_b200 as tg
+    tg._native.lib()
+    return tg
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def golden_adj(g):
+    n = int(g["n_docs"] + g["n_topics"])
+    return O.Coo(g["adj_rows"], g["adj_cols"], g["adj_vals"], (n, n))
+
+
+def to_csr(tg, coo: O.Coo, **kw):
+    return tg.DeviceCSR.from_coo(torch.tensor(coo.rows, device=dev()), torch.tensor(coo.cols, device=dev()),
+                                 torch.tensor(coo.vals, device=dev()), coo.shape[0], coo.shape[1], **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CSR construction: bit-exact
+# ---------------------------------------------------------------------------------------------------------------
+def test_csr_from_sorted_coo_bit_exact(tg, r8_golden):
+    coo = golden_adj(r8_golden)
+    csr = to_csr(tg, coo)
+    rp, ci, v = O.csr_from_coo(coo)
+    assert csr.coo_flags & 1  # fast path: the reference layout is already sorted
+    assert np.array_equal(csr.rowptr.cpu().numpy(), rp)
+    assert np.array_equal(csr.colidx.cpu().numpy(), ci)
+    assert np.array_equal(csr.vals.cpu().numpy().view(np.uint32), v.view(np.uint32))
+    assert csr.is_symmetric
+
+
+def test_csr_from_unsorted_coo_with_duplicates(tg):
+    rng = np.random.default_rng(3)
+    n, m, nnz = 211, 157, 5000
+    coo = O.Coo(rng.integers(0, n, nnz), rng.integers(0, m, nnz), rng.normal(size=nnz).astype(np.float32), (n, m))
+    csr = to_csr(tg, coo)
+    rp, ci, v = O.csr_from_coo(coo)
+    assert csr.coo_flags & 2
+    assert np.array_equal(csr.rowptr.cpu().numpy(), rp)
+    assert np.array_equal(csr.colidx.cpu().numpy(), ci)
+    assert np.array_equal(csr.vals.cpu().numpy().view(np.uint32), v.view(np.uint32))  # duplicates summed in input order
+    # same as torch's own coalesce()
+    t = torch.sparse_coo_tensor(torch.tensor(np.stack([coo.rows, coo.cols])), torch.tensor(coo.vals), (n, m)).coalesce()
+    assert np.array_equal(ci, t.indices()[1].numpy())
+    # transpose round trip
+    tt = csr.transpose()
+    assert not csr.is_symmetric
+    rp2, ci2, v2 = O.csr_from_coo(O.Coo(ci.astype(np.int64), np.repeat(np.arange(n), np.diff(rp)), v, (m, n)))
+    assert np.array_equal(tt.rowptr.cpu().numpy(), rp2) and np.array_equal(tt.colidx.cpu().numpy(), ci2)
+    assert np.array_equal(tt.vals.cpu().numpy().view(np.uint32), v2.view(np.uint32))
+
+
+def test_csr_edge_cases(tg):
+    # empty matrix, empty rows at both ends, single entry
+    e = tg.DeviceCSR.from_coo(torch.zeros(0, dtype=torch.int64, device=dev()), torch.zeros(0, dtype=torch.int64, device=dev()),
+                              torch.zeros(0, device=dev()), 5, 7)
+    assert e.nnz == 0 and e.rowptr.cpu().tolist() == [0] * 6
+    y = tg.spmm(e, torch.ones(7, 8, device=dev()))
+    assert y.shape == (5, 8) and float(y.abs().max()) == 0.0
+    coo = O.Coo([3], [1], [2.5], (6, 4))
+    c = to_csr(tg, coo)
+    assert c.rowptr.cpu().tolist() == [0, 0, 0, 0, 1, 1, 1]
+    B = torch.arange(12, dtype=torch.float32, device=dev()).reshape(4, 3)
+    y = tg.spmm(c, B).cpu().numpy()
+    assert np.array_equal(y, O.spmm(coo, B.cpu().numpy()))
+    with pytest.raises(tg.TopicGCNError):
+        tg.DeviceCSR.from_coo(torch.tensor([9], device=dev()), torch.tensor([0], device=dev()), torch.ones(1, device=dev()), 5, 5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SpMM
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F", [1, 2, 3, 8, 20, 23, 52, 64, 100, 200, 256, 300, 512])
+def test_spmm_small_golden_shapes(tg, small_golden, F):
+    coo = golden_adj(small_golden)
+    rng = np.random.default_rng(F)
+    B = rng.normal(size=(coo.shape[1], F)).astype(np.float32)
+    ref = O.spmm(coo, B)
+    for kw in ({}, {"hub_threshold": 16, "segment_nnz": 8}):  # second plan forces the split-row path on a tiny graph
+        csr = to_csr(tg, coo, **kw)
+        y = tg.spmm(csr, torch.tensor(B, device=dev())).cpu().numpy()
+        assert rel_err(y, ref) <= SPMM_RTOL, (F, kw)
+        bias = rng.normal(size=F).astype(np.float32)
+        yb = tg.spmm(csr, torch.tensor(B, device=dev()), torch.tensor(bias, device=dev())).cpu().numpy()
+        assert rel_err(yb, ref + bias) <= SPMM_RTOL
+
+
+def test_spmm_matches_reference_golden(tg, small_golden):
+    g = small_golden
+    y = tg.spmm(to_csr(tg, golden_adj(g)), torch.tensor(g["spmm_B"], device=dev())).cpu().numpy()
+    assert rel_err(y, g["spmm_Y"]) <= SPMM_RTOL  # golden = th.spmm of the real reference stack
+
+
+@pytest.mark.parametrize("F", [8, 200])
+def test_spmm_r8_graph(tg, r8_golden, F):
+    g = r8_golden
+    coo = golden_adj(g)
+    nd = int(g["n_docs"])
+    B = np.random.default_rng(1).uniform(size=(coo.shape[1], F)).astype(np.float32)
+    ref, ref64 = O.spmm(coo, B), O.spmm_f64(coo, B)
+    for kw in ({}, {"hub_threshold": 256, "segment_nnz": 128}):
+        csr = to_csr(tg, coo, **kw)
+        y = tg.spmm(csr, torch.tensor(B, device=dev())).cpu().numpy()
+        assert rel_err(y[:nd], ref[:nd]) <= SPMM_RTOL       # document rows
+        assert rel_err(y[nd:], ref[nd:]) <= SPMM_RTOL       # topic (hub) rows, 191..1807 entries
+        assert rel_err(y, ref64) <= rel_err(ref, ref64) + 2e-7
+
+
+def test_spmm_deterministic_and_split_rows(tg):
+    from topicgcn_b200 import graphgen
+    g, h, c = graphgen.make_config("c3_1m_docs_256_topics", device="cuda:0", scale=0.1)
+    csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n)
+    assert csr.n_hub_rows == g.n_hubs and csr.n_segments > csr.n_hub_rows
+    B = torch.rand(g.n, 256, device=dev())
+    y1 = tg.spmm(csr, B).clone()
+    for _ in range(3):
+        y2 = tg.spmm(csr, B)
+        assert torch.equal(y1, y2)  # bitwise run-to-run reproducible (fixed-order reduction, no float atomics)
+    coo = O.Coo(g.rows.cpu().numpy(), g.cols.cpu().numpy(), g.vals.cpu().numpy(), (g.n, g.n))
+    ref, ref64 = O.spmm(coo, B.cpu().numpy()), O.spmm_f64(coo, B.cpu().numpy())
+    y = y1.cpu().numpy()
+    nd = g.n_docs
+    assert rel_err(y[:nd], ref[:nd]) <= SPMM_RTOL
+    # hub rows (~3e3 entries): the reference's serial fp32 sum carries its own error; require being at least as
+    # close to the float64 truth as the reference and within 2x its error of the reference itself
+    e_ref = rel_err(ref[nd:], ref64[nd:])
+    assert rel_err(y[nd:], ref64[nd:]) <= e_ref + 2e-7
+    assert rel_err(y[nd:], ref[nd:]) <= max(SPMM_RTOL, 2 * e_ref)
+
+
+def test_spmm_textgcn_skew(tg):
+    """C5: power-law word rows (median ~200, max ~1.5e4 entries) - every row class of the plan in one graph."""
+    from topicgcn_b200 import graphgen
+    g, h, c = graphgen.make_config("c5_textgcn_r8_shape", device="cuda:0")
+    csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n)
+    assert 0 < csr.n_hub_rows < g.n_hubs
+    B = torch.randn(g.n, 200, device=dev())
+    y = tg.spmm(csr, B).cpu().numpy()
+    coo = O.Coo(g.rows.cpu().numpy(), g.cols.cpu().numpy(), g.vals.cpu().numpy(), (g.n, g.n))
+    ref, ref64 = O.spmm(coo, B.cpu().numpy()), O.spmm_f64(coo, B.cpu().numpy())
+    assert rel_err(y, ref64) <= rel_err(ref, ref64) + 2e-7
+    assert rel_err(y, ref) <= SPMM_RTOL
+
+
+def test_spmm_full_size_properties(tg):
+    """C3 at full size (1M docs x 256 topics): size-independent properties instead of the (slow) oracle."""
+    from topicgcn_b200 import graphgen
+    g, h, c = graphgen.make_config("c3_1m_docs_256_topics", device="cuda:0")
+    csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n)
+    F = 64
+    X = torch.randn(g.n, F, device=dev())
+    Y = torch.randn(g.n, F, device=dev())
+    AX, AY = tg.spmm(csr, X), tg.spmm(csr, Y)
+    # linearity
+    lin = tg.spmm(csr, 2.0 * X - 0.5 * Y)
+    assert float((lin - (2.0 * AX - 0.5 * AY)).abs().max() / lin.abs().max()) < 1e-5
+    # adjoint identity <Y, A X> = <A^T Y, X> in float64
+    ATY = tg.spmm(csr.transpose(), Y)
+    lhs = float((Y.double() * AX.double()).sum())
+    rhs = float((ATY.double() * X.double()).sum())
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0) + 1e-3
+    # A * 1 = row sums (float64 index_add of the stored values)
+    ones = torch.ones(g.n, 4, device=dev())
+    rs = torch.zeros(g.n, dtype=torch.float64, device=dev()).index_add_(0, g.rows, g.vals.double())
+    got = tg.spmm(csr, ones)[:, 0].double()
+    assert float(((got - rs).abs() / rs.abs().clamp_min(1e-12)).max()) < 1e-5
+    # idempotent re-run
+    assert torch.equal(AX, tg.spmm(csr, X))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused epilogues
+# ---------------------------------------------------------------------------------------------------------------
+def test_philox_keep_mask_bit_exact(tg):
+    from topicgcn_b200 import ops
+    for (n, f, p, seed, off) in [(257, 200, 0.5, 1234, 3), (64, 256, 0.2, 7, 1), (33, 20, 0.5, 2**40 + 5, 2**33 + 1),
+                                 (17, 23, 0.7, 1, 0), (5, 520, 0.5, 99, 12)]:
+        got = ops.dropout_keep_mask(n, f, p, seed, off, dev()).cpu().numpy()
+        assert np.array_equal(got, O.philox_keep_mask(n, f, p, seed, off)), (n, f, p)
+
+
+@pytest.mark.parametrize("plan_kw", [{}, {"hub_threshold": 16, "segment_nnz": 8}])
+def test_gc1_fused_forward(tg, small_golden, plan_kw):
+    from topicgcn_b200 import ops
+    g = small_golden
+    coo = golden_adj(g)
+    csr = to_csr(tg, coo, **plan_kw)
+    n, H = coo.shape[0], int(g["nhid"])
+    W1, b1 = g["fl_gc1.weight"], g["fl_gc1.bias"]
+    Z1 = O.spmm(coo, W1) + b1
+    # eval mode
+    h_eval = ops.gc1_forward(csr, torch.tensor(W1, device=dev()), torch.tensor(b1, device=dev()), 0.5, False).cpu().numpy()
+    assert rel_err(h_eval, np.maximum(Z1, 0)) <= SPMM_RTOL
+    # explicit mask (the one torch's bernoulli_ drew for the reference run)
+    mask = g["fl_keep_mask"]
+    h_tr = ops.gc1_forward(csr, torch.tensor(W1, device=dev()), torch.tensor(b1, device=dev()), 0.5, True,
+                           keep_mask=torch.tensor(mask, device=dev())).cpu().numpy()
+    assert rel_err(h_tr, np.maximum(Z1, 0) * mask * 2.0) <= SPMM_RTOL
+    # Philox mode: the fused kernel applies exactly the mask tg_dropout_keep_mask reports
+    h_ph = ops.gc1_forward(csr, torch.tensor(W1, device=dev()), torch.tensor(b1, device=dev()), 0.5, True,
+                           seed=42, offset=9).cpu().numpy()
+    pm = O.philox_keep_mask(n, H, 0.5, 42, 9)
+    assert rel_err(h_ph, np.maximum(Z1, 0) * pm * 2.0) <= SPMM_RTOL
+    assert np.array_equal(h_ph != 0, (np.maximum(Z1, 0) * pm) != 0)
+
+
+@pytest.mark.parametrize("plan_kw", [{}, {"hub_threshold": 16, "segment_nnz": 8}])
+@pytest.mark.parametrize("C", [5, 8, 20, 23])
+def test_gc2_loss_fused_forward(tg, small_golden, plan_kw, C):
+    from topicgcn_b200 import ops
+    g = small_golden
+    coo = golden_adj(g)
+    csr = to_csr(tg, coo, **plan_kw)
+    n = coo.shape[0]
+    rng = np.random.default_rng(C)
+    S2 = rng.normal(size=(n, C)).astype(np.float32)
+    b2 = rng.normal(size=C).astype(np.float32)
+    target = rng.integers(0, C, size=int(g["n_docs"]))
+    index = g["index"]
+    logits_ref = O.spmm(coo, S2) + b2
+    loss_ref, dz_ref = O.masked_cross_entropy(logits_ref, target, index)
+    row_label = ops.make_row_label(n, torch.tensor(target, device=dev()), torch.tensor(index, device=dev()))
+    loss, logits, dz = ops.gc2_loss_forward(csr, torch.tensor(S2, device=dev()), torch.tensor(b2, device=dev()),
+                                            row_label, 1.0 / index.size)
+    assert rel_err(logits.cpu().numpy(), logits_ref) <= SPMM_RTOL
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    assert rel_err(dz.cpu().numpy(), dz_ref) <= 2e-5
+    # stand-alone loss on given logits
+    loss2, dz2 = ops.masked_ce(torch.tensor(logits_ref, device=dev()), row_label, 1.0 / index.size)
+    assert abs(float(loss2) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    assert rel_err(dz2.cpu().numpy(), dz_ref) <= 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dense products / reductions
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,h,c", [(1, 1, 1), (700, 200, 8), (1500, 256, 20), (513, 200, 23), (300, 64, 52), (2049, 37, 5)])
+def test_dense_nn(tg, n, h, c):
+    from topicgcn_b200 import ops
+    rng = np.random.default_rng(n + h + c)
+    A = rng.normal(size=(n, h)).astype(np.float32)
+    W = rng.normal(size=(h, c)).astype(np.float32)
+    got = ops.dense_nn(torch.tensor(A, device=dev()), torch.tensor(W, device=dev())).cpu().numpy()
+    ref = A.astype(np.float64) @ W.astype(np.float64)
+    assert rel_err(got, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("n,h,c", [(1, 8, 2), (700, 200, 8), (5000, 256, 20), (513, 200, 23), (300, 64, 52), (40000, 256, 20)])
+def test_hidden_backward(tg, n, h, c):
+    from topicgcn_b200 import ops
+    rng = np.random.default_rng(n + h + c)
+    H1 = np.maximum(rng.normal(size=(n, h)), 0).astype(np.float32) * 2.0
+    dS2 = rng.normal(size=(n, c)).astype(np.float32)
+    W2 = rng.normal(size=(h, c)).astype(np.float32)
+    dZ1, dW2, db1 = ops.hidden_backward(torch.tensor(H1, device=dev()), torch.tensor(dS2, device=dev()),
+                                        torch.tensor(W2, device=dev()), 2.0)
+    dH1 = dS2.astype(np.float64) @ W2.astype(np.float64).T
+    dZ1_ref = np.where(H1 > 0, dH1 * 2.0, 0.0)
+    assert rel_err(dZ1.cpu().numpy(), dZ1_ref) <= 1e-5
+    assert rel_err(dW2.cpu().numpy(), H1.astype(np.float64).T @ dS2.astype(np.float64)) <= 2e-5
+    assert rel_err(db1.cpu().numpy(), dZ1_ref.sum(axis=0)) <= 2e-5
+    # deterministic
+    dZ1b, dW2b, db1b = ops.hidden_backward(torch.tensor(H1, device=dev()), torch.tensor(dS2, device=dev()),
+                                           torch.tensor(W2, device=dev()), 2.0)
+    assert torch.equal(dW2, dW2b) and torch.equal(db1, db1b) and torch.equal(dZ1, dZ1b)
+
+
+@pytest.mark.parametrize("n,c", [(1, 1), (1000, 8), (100000, 20), (777, 23), (5000, 300)])
+def test_colsum_and_reduce(tg, n, c):
+    from topicgcn_b200 import ops
+    X = np.random.default_rng(n).normal(size=(n, c)).astype(np.float32)
+    got = ops.colsum(torch.tensor(X, device=dev())).cpu().numpy()
+    ref = X.astype(np.float64).sum(axis=0)
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(X).sum(axis=0).max()
+    s = float(ops.reduce_sum(torch.tensor(X[:, 0].copy(), device=dev())))
+    assert abs(s - ref[0]) <= 1e-5 * np.abs(X[:, 0]).sum()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the modules (drop-in API) against the real reference's outputs
+# ---------------------------------------------------------------------------------------------------------------
+def _load_params(model, g, prefix):
+    sd = {k: torch.tensor(g[f"{prefix}_{k}"]) for k in ("gc1.weight", "gc1.bias", "gc2.weight", "gc2.bias")}
+    model.load_state_dict(sd)  # same keys/shapes as the reference module
+    return model.to(dev())
+
+
+def _sparse(rows, cols, vals, shape):
+    return torch.sparse_coo_tensor(torch.tensor(np.stack([rows, cols])), torch.tensor(vals), shape,
+                                   check_invariants=False).to(dev())
+
+
+@pytest.mark.parametrize("prefix", ["fl", "sf"])
+@pytest.mark.parametrize("fused_loss", [False, True])
+def test_gcn_module_against_reference_golden(tg, small_golden, prefix, fused_loss):
+    g = small_golden
+    n = int(g["n_docs"] + g["n_topics"])
+    adj = _sparse(g["adj_rows"], g["adj_cols"], g["adj_vals"], (n, n))
+    if prefix == "fl":
+        idx = np.arange(n)
+        x = _sparse(idx, idx, np.ones(n, dtype=np.float32), (n, n))  # the reference's featureless input: sparse identity
+        nfeat = n
+    else:
+        x = _sparse(g["sf_x_rows"], g["sf_x_cols"], g["sf_x_vals"], (n, 24))
+        nfeat = 24
+    model = _load_params(tg.GCN(nfeat, int(g["nhid"]), int(g["nclass"]), float(g["p"])), g, prefix)
+    target = torch.tensor(g["target"], device=dev())
+    index = torch.tensor(g["index"], device=dev())
+    model.eval()
+    with torch.no_grad():
+        assert rel_err(model.forward(x, adj).cpu().numpy(), g[f"{prefix}_eval_logits"]) <= SPMM_RTOL
+    model.train()
+    model.set_next_dropout_mask(torch.tensor(g[f"{prefix}_keep_mask"], device=dev()))
+    if fused_loss:
+        loss, logits = model.loss(x, adj, target, index, return_logits=True)
+    else:
+        logits = model.forward(x, adj)
+        loss = torch.nn.CrossEntropyLoss()(logits[index], target[index])  # exactly the reference call site
+    loss.backward()
+    assert rel_err(logits.detach().cpu().numpy(), g[f"{prefix}_train_logits"]) <= SPMM_RTOL
+    assert abs(float(loss) - float(g[f"{prefix}_train_loss"])) <= 1e-5
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), g[f"{prefix}_grad_{k}"]) <= 2e-5, k
+
+
+def test_graph_convolution_module(tg, small_golden):
+    g = small_golden
+    n = int(g["n_docs"] + g["n_topics"])
+    adj = _sparse(g["adj_rows"], g["adj_cols"], g["adj_vals"], (n, n))
+    x = _sparse(g["sf_x_rows"], g["sf_x_cols"], g["sf_x_vals"], (n, 24))
+    gc = tg.GraphConvolution(24, 8)
+    gc.load_state_dict({"weight": torch.tensor(g["gc_weight"]), "bias": torch.tensor(g["gc_bias"])})
+    gc = gc.to(dev())
+    out = gc(x, adj)
+    assert rel_err(out.detach().cpu().numpy(), g["gc_out"]) <= SPMM_RTOL
+    out.sum().backward()
+    assert gc.weight.grad is not None and gc.bias.grad is not None
+    assert repr(gc) == "GraphConvolution (24 -> 8)"
+
+
+def test_masked_cross_entropy_dropin(tg, small_golden):
+    g = small_golden
+    logits = torch.tensor(g["fl_train_logits"], device=dev(), requires_grad=True)
+    target = torch.tensor(g["target"], device=dev())
+    index = torch.tensor(g["index"], device=dev())
+    loss = tg.masked_cross_entropy(logits, target, index)
+    loss.backward()
+    l2 = torch.tensor(g["fl_train_logits"], device=dev(), requires_grad=True)
+    ref = torch.nn.CrossEntropyLoss()(l2[index], target[index])
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-6
+    assert rel_err(logits.grad.cpu().numpy(), l2.grad.cpu().numpy()) <= 1e-5
+
+
+def test_r8_seed0_step_against_reference(tg, r8_golden):
+    """Real R8 TopicGCN graph (config 1), featureless, seed 0: same init, same split, same dropout mask."""
+    from tests.golden.make_golden_shared import mask_seed, train_val_split
+    g = r8_golden
+    n, nd = int(g["n_docs"] + g["n_topics"]), int(g["n_docs"])
+    adj = _sparse(g["adj_rows"].astype(np.int64), g["adj_cols"].astype(np.int64), g["adj_vals"], (n, n))
+    torch.manual_seed(0)
+    model = tg.GCN(n, int(g["nhid"]), int(g["nclass"]), 0.5).to(dev())  # same RNG order as the reference ctor
+    x = tg.Featureless(n)
+    train_lst, _ = train_val_split(g["train_all"], 0)
+    target = torch.tensor(g["target"].astype(np.int64), device=dev())
+    index = torch.tensor(train_lst, device=dev())
+    model.eval()
+    with torch.no_grad():
+        assert rel_err(model.forward(x, adj).cpu().numpy(), g["s0_eval_logits"]) <= SPMM_RTOL
+    model.train()
+    torch.manual_seed(mask_seed(0, 0))
+    mask = torch.empty(n, int(g["nhid"])).bernoulli_(0.5).to(torch.uint8)
+    model.set_next_dropout_mask(mask.to(dev()))
+    loss, logits = model.loss(x, adj, target, index, return_logits=True)
+    loss.backward()
+    assert abs(float(loss) - float(g["s0_train_loss"])) <= 1e-5
+    assert rel_err(logits.cpu().numpy()[::97], g["s0_train_logits_rows"]) <= SPMM_RTOL
+    assert rel_err(model.gc2.weight.grad.cpu().numpy(), g["s0_grad_gc2.weight"]) <= 2e-5
+    assert rel_err(model.gc1.bias.grad.cpu().numpy(), g["s0_grad_gc1.bias"]) <= 2e-5
+    assert rel_err(model.gc2.bias.grad.cpu().numpy(), g["s0_grad_gc2.bias"]) <= 2e-5
+    gw1 = model.gc1.weight.grad.cpu().numpy()
+    assert rel_err(gw1[nd:], g["s0_grad_gc1.weight_topics"]) <= 2e-5
+    assert rel_err(gw1[::97], g["s0_grad_gc1.weight_rows"]) <= 2e-5
+
+
+def test_cpu_inputs_fail_loudly(tg, small_golden):
+    g = small_golden
+    n = int(g["n_docs"] + g["n_topics"])
+    adj_cpu = torch.sparse_coo_tensor(torch.tensor(np.stack([g["adj_rows"], g["adj_cols"]])), torch.tensor(g["adj_vals"]), (n, n))
+    model = tg.GCN(n, 16, 5, 0.5)
+    with pytest.raises(tg.TopicGCNError):
+        model.forward(tg.Featureless(n), adj_cpu)
