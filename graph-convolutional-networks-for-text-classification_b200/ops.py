@@ -19,6 +19,41 @@ from .csr import DeviceCSR
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# instrumentation: how many of OUR kernels were launched, and an optional per-kernel CUDA-event hook (bench.py)
+# ---------------------------------------------------------------------------------------------------------------
+class Stats:
+    launches = 0  # kernels of libtopicgcn.so launched through this module since the last reset
+
+
+_kernel_hook = None
+
+
+def set_kernel_hook(hook) -> None:
+    """hook.start(tag, info) -> token / hook.stop(token) are called around every C-ABI compute call (bench.py records
+    CUDA events on the launching stream with it).  None disables."""
+    global _kernel_hook
+    _kernel_hook = hook
+
+
+class _call:
+    """Context around one C-ABI call: counts its kernel launches and feeds the optional event hook."""
+
+    def __init__(self, tag: str, launches: int, **info):
+        self.tag, self.launches, self.info, self.tok = tag, launches, info, None
+
+    def __enter__(self):
+        Stats.launches += self.launches
+        if _kernel_hook is not None:
+            self.tok = _kernel_hook.start(self.tag, self.info)
+        return self
+
+    def __exit__(self, *exc):
+        if _kernel_hook is not None and self.tok is not None:
+            _kernel_hook.stop(self.tok)
+        return False
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # tensor plumbing
 # ---------------------------------------------------------------------------------------------------------------
 def _dense2d(t: torch.Tensor, what: str) -> torch.Tensor:
@@ -63,7 +98,7 @@ def spmm(csr: DeviceCSR, B: torch.Tensor, bias: Optional[torch.Tensor] = None,
     if out is None:
         out = torch.empty((csr.n_rows, F), dtype=torch.float32, device=B.device)
     ws, ws_bytes = csr.workspace(F)
-    with torch.cuda.device(B.device):
+    with torch.cuda.device(B.device), _call("spmm", 1, n_feat=F, csr=csr):
         N.check(N.lib().tg_spmm_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(B), _ld(B),
                                     N.ptr(out), _ld(out), F, N.ptr(bias), ws, ws_bytes, _stream()), "tg_spmm_f32")
     return out
@@ -85,7 +120,7 @@ def gc1_forward(csr: DeviceCSR, S: torch.Tensor, bias: Optional[torch.Tensor], p
     if out is None:
         out = torch.empty((csr.n_rows, F), dtype=torch.float32, device=S.device)
     ws, ws_bytes = csr.workspace(F)
-    with torch.cuda.device(S.device):
+    with torch.cuda.device(S.device), _call("gc1_fwd", 1, n_feat=F, csr=csr):
         N.check(N.lib().tg_gc1_fwd_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(S), _ld(S),
                                        N.ptr(bias), N.ptr(out), _ld(out), F, float(p), int(bool(training)),
                                        N.ptr(keep_mask), int(seed) & (2**64 - 1), int(offset) & (2**64 - 1), ws,
@@ -96,7 +131,7 @@ def gc1_forward(csr: DeviceCSR, S: torch.Tensor, bias: Optional[torch.Tensor], p
 def dropout_keep_mask(n_rows: int, n_feat: int, p: float, seed: int, offset: int, device) -> torch.Tensor:
     """The Philox keep mask tg_gc1_fwd_f32 uses for (seed, offset): tg_dropout_keep_mask."""
     out = torch.empty((n_rows, n_feat), dtype=torch.uint8, device=device)
-    with torch.cuda.device(out.device):
+    with torch.cuda.device(out.device), _call("keep_mask", 1):
         N.check(N.lib().tg_dropout_keep_mask(N.ptr(out), n_rows, n_feat, float(p), int(seed) & (2**64 - 1),
                                              int(offset) & (2**64 - 1), _stream()), "tg_dropout_keep_mask")
     return out
@@ -108,7 +143,7 @@ def reduce_sum(x: torch.Tensor) -> torch.Tensor:
     n = int(x.numel())
     scratch = torch.empty(int(N.lib().tg_reduce_scratch_floats(n)), dtype=torch.float32, device=x.device)
     out = torch.empty((), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _call("reduce_sum", 2):
         N.check(N.lib().tg_reduce_sum_f32(N.ptr(x), n, N.ptr(scratch), N.ptr(out), _stream()), "tg_reduce_sum_f32")
     return out
 
@@ -134,7 +169,7 @@ def gc2_loss_forward(csr: DeviceCSR, S2: torch.Tensor, bias: Optional[torch.Tens
     dZ2 = torch.empty((csr.n_rows, Cc), dtype=torch.float32, device=dev) if want_grad else None
     row_loss = torch.empty(csr.n_rows, dtype=torch.float32, device=dev)
     ws, ws_bytes = csr.workspace(Cc)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _call("gc2_loss_fwd", 1, n_feat=Cc, csr=csr):
         N.check(N.lib().tg_gc2_loss_fwd_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(S2),
                                             _ld(S2), N.ptr(bias), N.ptr(row_label), float(inv_count), N.ptr(logits),
                                             Cc, N.ptr(dZ2), Cc, N.ptr(row_loss), Cc, ws, ws_bytes, _stream()),
@@ -148,7 +183,7 @@ def masked_ce(logits: torch.Tensor, row_label: torch.Tensor, inv_count: float, w
     n, Cc = int(logits.shape[0]), int(logits.shape[1])
     dZ = torch.empty((n, Cc), dtype=torch.float32, device=logits.device) if want_grad else None
     row_loss = torch.empty(n, dtype=torch.float32, device=logits.device)
-    with torch.cuda.device(logits.device):
+    with torch.cuda.device(logits.device), _call("masked_ce", 1):
         N.check(N.lib().tg_masked_ce_f32(N.ptr(logits), _ld(logits), N.ptr(row_label), float(inv_count), N.ptr(dZ), Cc,
                                          N.ptr(row_loss), n, Cc, _stream()), "tg_masked_ce_f32")
     return reduce_sum(row_loss), dZ
@@ -162,7 +197,7 @@ def dense_nn(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
     if W.shape[0] != h:
         raise N.TopicGCNError("inner dimensions differ")
     out = torch.empty((n, c), dtype=torch.float32, device=A.device)
-    with torch.cuda.device(A.device):
+    with torch.cuda.device(A.device), _call("dense_nn", (c + 31) // 32, n=n, h=h, c=c):
         N.check(N.lib().tg_dense_nn_f32(N.ptr(A), _ld(A), N.ptr(W), _ld(W), N.ptr(out), c, n, h, c, _stream()),
                 "tg_dense_nn_f32")
     return out
@@ -174,7 +209,7 @@ def colsum(X: torch.Tensor) -> torch.Tensor:
     n, c = int(X.shape[0]), int(X.shape[1])
     scratch = torch.empty(int(N.lib().tg_colsum_scratch_floats(n, c)), dtype=torch.float32, device=X.device)
     out = torch.empty(c, dtype=torch.float32, device=X.device)
-    with torch.cuda.device(X.device):
+    with torch.cuda.device(X.device), _call("colsum", 2):
         N.check(N.lib().tg_colsum_f32(N.ptr(X), _ld(X), n, c, N.ptr(scratch), N.ptr(out), _stream()), "tg_colsum_f32")
     return out
 
@@ -185,7 +220,7 @@ def relu_dropout_backward(H: torch.Tensor, dH: torch.Tensor, scale: float) -> to
     dH = _dense2d(dH, "dH")
     n, f = int(H.shape[0]), int(H.shape[1])
     dZ = torch.empty((n, f), dtype=torch.float32, device=H.device)
-    with torch.cuda.device(H.device):
+    with torch.cuda.device(H.device), _call("relu_dropout_bwd", 1):
         N.check(N.lib().tg_relu_dropout_bwd_f32(N.ptr(H), _ld(H), N.ptr(dH), _ld(dH), float(scale), N.ptr(dZ), f, n, f,
                                                 _stream()), "tg_relu_dropout_bwd_f32")
     return dZ
@@ -213,7 +248,7 @@ def hidden_backward(H1: torch.Tensor, dS2: torch.Tensor, W2: torch.Tensor, scale
     dW2 = torch.empty((h, c), dtype=torch.float32, device=dev)
     db1 = torch.empty(h, dtype=torch.float32, device=dev)
     scratch = torch.empty(int(N.lib().tg_hidden_bwd_scratch_floats(n, h, c)), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _call("hidden_bwd", 2, n=n, h=h, c=c):
         N.check(N.lib().tg_hidden_bwd_f32(N.ptr(H1), _ld(H1), N.ptr(dS2), _ld(dS2), N.ptr(W2), _ld(W2), float(scale),
                                           N.ptr(dZ1), h, N.ptr(dW2), N.ptr(db1), N.ptr(scratch), n, h, c, _stream()),
                 "tg_hidden_bwd_f32")
@@ -227,21 +262,16 @@ class SpMMFunction(torch.autograd.Function):
     """Y = A @ B (+ bias).  A is constant (the reference never differentiates adj or X)."""
 
     @staticmethod
-    def forward(ctx, B, bias, csr: DeviceCSR, post=None):
-        ctx.csr, ctx.has_bias, ctx.post = csr, bias is not None, post
-        Y = spmm(csr, B, bias)
-        if post is not None:
-            post(Y)
-        return Y
+    def forward(ctx, B, bias, csr: DeviceCSR):
+        ctx.csr, ctx.has_bias = csr, bias is not None
+        return spmm(csr, B, bias)
 
     @staticmethod
     def backward(ctx, dY):
         dY = dY.contiguous()
         dB = spmm(ctx.csr.transpose(), dY) if ctx.needs_input_grad[0] else None
-        if dB is not None and ctx.post is not None:
-            ctx.post(dB)
         db = colsum(dY) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
-        return dB, db, None, None
+        return dB, db, None
 
 
 def _dropout_scale(p: float, training: bool) -> float:
@@ -254,27 +284,15 @@ class GCNCoreFunction(torch.autograd.Function):
     forward : tg_gc1_fwd_f32 -> tg_dense_nn_f32 -> tg_spmm_f32(+b2)
     backward: tg_colsum_f32 (db2) -> tg_spmm_f32 on A^T (dS2) -> tg_hidden_bwd_f32 (dZ1, dW2, db1)
               -> tg_spmm_f32 on A^T (dS1)
-    `post` (optional) is called on every SpMM output; the document-sharded multi-GPU mode uses it to all-reduce the
-    replicated topic rows (shard.py).
     """
 
     @staticmethod
-    def forward(ctx, S1, b1, W2, b2, csr: DeviceCSR, p: float, training: bool, keep_mask, seed: int, offset: int,
-                post=None, param_post=None):
-        H1 = gc1_forward(csr, S1, b1, p, training, keep_mask, seed, offset) if post is None else None
-        if post is not None:
-            # sharded: the topic rows of A @ S1 must be summed across ranks BEFORE bias/relu/dropout
-            Z1 = spmm(csr, S1)
-            post(Z1)
-            H1 = _bias_relu_dropout_identity(Z1, b1, p, training, keep_mask, seed, offset)
+    def forward(ctx, S1, b1, W2, b2, csr: DeviceCSR, p: float, training: bool, keep_mask, seed: int, offset: int):
+        H1 = gc1_forward(csr, S1, b1, p, training, keep_mask, seed, offset)
         S2 = dense_nn(H1, W2)
-        logits = spmm(csr, S2, None if post is not None else b2)
-        if post is not None:
-            post(logits)
-            if b2 is not None:
-                logits += b2
+        logits = spmm(csr, S2, b2)
         ctx.save_for_backward(H1, W2)
-        ctx.csr, ctx.scale, ctx.post, ctx.param_post = csr, _dropout_scale(p, training), post, param_post
+        ctx.csr, ctx.scale = csr, _dropout_scale(p, training)
         ctx.has_b1, ctx.has_b2 = b1 is not None, b2 is not None
         return logits
 
@@ -285,36 +303,26 @@ class GCNCoreFunction(torch.autograd.Function):
         csr_t = ctx.csr.transpose()
         db2 = colsum(dlogits) if ctx.has_b2 else None
         dS2 = spmm(csr_t, dlogits)
-        if ctx.post is not None:
-            ctx.post(dS2)
         dZ1, dW2, db1 = hidden_backward(H1, dS2, W2, ctx.scale)
         dS1 = spmm(csr_t, dZ1) if ctx.needs_input_grad[0] else None
-        if dS1 is not None and ctx.post is not None:
-            ctx.post(dS1)
-        if ctx.param_post is not None:
-            db1, dW2, db2 = ctx.param_post(db1, dW2, db2)
-        return dS1, (db1 if ctx.has_b1 else None), dW2, db2, None, None, None, None, None, None, None, None
+        return dS1, (db1 if ctx.has_b1 else None), dW2, db2, None, None, None, None, None, None
 
 
-class _IdentityCSRCache:
-    cache: dict = {}
-
-
-def _identity_csr(n: int, device) -> DeviceCSR:
+def identity_csr(n: int, device) -> DeviceCSR:
+    """CSR of the n x n identity (cached): lets the fused layer-1 epilogue run on an already aggregated operand."""
     key = (n, str(device))
-    hit = _IdentityCSRCache.cache.get(key)
+    hit = _identity_cache.get(key)
     if hit is None:
         rowptr = torch.arange(n + 1, dtype=torch.int32, device=device)
         colidx = torch.arange(n, dtype=torch.int32, device=device)
         vals = torch.ones(n, dtype=torch.float32, device=device)
         hit = DeviceCSR(rowptr, colidx, vals, n, n, symmetric=True)
-        _IdentityCSRCache.cache = {key: hit}
+        _identity_cache.clear()
+        _identity_cache[key] = hit
     return hit
 
 
-def _bias_relu_dropout_identity(Z1, b1, p, training, keep_mask, seed, offset):
-    """bias + relu + dropout on an already aggregated Z1 (sharded mode): the fused layer-1 kernel with A = I."""
-    return gc1_forward(_identity_csr(int(Z1.shape[0]), Z1.device), Z1, b1, p, training, keep_mask, seed, offset, out=Z1)
+_identity_cache: dict = {}
 
 
 class GCNLossFunction(torch.autograd.Function):

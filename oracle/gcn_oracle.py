@@ -79,7 +79,12 @@ class Coo:
         return int(self.rows.size)
 
     def transpose(self) -> "Coo":
-        return Coo(self.cols, self.rows, self.vals, (self.shape[1], self.shape[0]))
+        """`sparse.t()`: swaps the index rows, storage order unchanged; memoised."""
+        t = getattr(self, "_t", None)
+        if t is None:
+            t = Coo(self.cols, self.rows, self.vals, (self.shape[1], self.shape[0]))
+            self._t = t
+        return t
 
 
 def csr_from_coo(coo: Coo):
@@ -96,10 +101,40 @@ def csr_from_coo(coo: Coo):
 # ---------------------------------------------------------------------------------------------------------------
 # the sparse x dense product (layer.py:102/106 -> ATen)
 # ---------------------------------------------------------------------------------------------------------------
+_THREADS = 1
+
+
+def set_threads(n: int) -> None:
+    """n > 1: `spmm` runs the row-parallel CSR form of the same loop on n OpenMP threads (bit-identical results for
+    any input: rows are gathered with a stable sort).  Used by the CPU-baseline legs of bench.py; the default (1) is the reference's serial
+    storage-order loop."""
+    global _THREADS
+    _THREADS = max(1, int(n))
+
+
+def _row_sorted_csr(coo: "Coo"):
+    hit = getattr(coo, "_csr_cache", None)
+    if hit is None:
+        # a STABLE sort by row keeps, inside every row, the storage order of its entries: the row-parallel loop
+        # then performs exactly the additions of the serial storage-order loop, row by row
+        cols, vals = coo.cols, coo.vals
+        if coo.nnz > 1 and not bool(np.all(coo.rows[1:] >= coo.rows[:-1])):
+            order = np.argsort(coo.rows, kind="stable")
+            cols, vals = cols[order], vals[order]
+        rowptr = np.zeros(coo.shape[0] + 1, dtype=np.int32)
+        np.cumsum(np.bincount(coo.rows, minlength=coo.shape[0]), out=rowptr[1:])
+        hit = (rowptr, cols.astype(np.int32), np.ascontiguousarray(vals))
+        coo._csr_cache = hit
+    return hit
+
+
 def spmm(coo: Coo, B: np.ndarray) -> np.ndarray:
     """th.spmm(sparse_coo, dense) on CPU: serial fp32 axpy per stored entry, storage order."""
     B = np.ascontiguousarray(B, dtype=np.float32)
     F = B.shape[1]
+    if _THREADS > 1:
+        csr = _row_sorted_csr(coo)
+        return spmm_csr(csr[0], csr[1], csr[2], B, _THREADS)
     Y = np.empty((coo.shape[0], F), dtype=np.float32)
     _c().oracle_spmm_coo_f32(_ptr(coo.rows), _ptr(coo.cols), _ptr(coo.vals), C.c_int64(coo.nnz), _ptr(B),
                              C.c_int64(F), C.c_int64(F), _ptr(Y), C.c_int64(F), C.c_int64(coo.shape[0]))
