@@ -49,7 +49,7 @@ def _declare(lib) -> None:
     sig("tg_csr_from_coo", C.c_int, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, C.POINTER(_i64),
         C.POINTER(C.c_uint32), _p)
     sig("tg_csr_transpose", C.c_int, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, C.POINTER(_i32), _p)
-    sig("tg_plan_create", C.c_int, _p, _i64, _i64, _i64, _i32, _i32, C.POINTER(_p), _p)
+    sig("tg_plan_create", C.c_int, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, C.POINTER(_p), _p)
     sig("tg_plan_destroy", None, _p)
     sig("tg_plan_info", C.c_int, _p, C.POINTER(_i64))
     sig("tg_plan_workspace_bytes", _sz, _p, _i32)

@@ -26,7 +26,8 @@ class DeviceCSR:
     """int32 CSR on the GPU + its SpMM plan.  `transpose()` returns the CSR used by the backward pass."""
 
     def __init__(self, rowptr: torch.Tensor, colidx: torch.Tensor, vals: torch.Tensor, n_rows: int, n_cols: int,
-                 *, hub_threshold: int = 0, segment_nnz: int = 0, symmetric: Optional[bool] = None):
+                 *, hub_threshold: int = 0, segment_nnz: int = 0, symmetric: Optional[bool] = None,
+                 streaming: bool = True):
         for t, name, dt in ((rowptr, "rowptr", torch.int32), (colidx, "colidx", torch.int32), (vals, "vals", torch.float32)):
             _require_cuda(t, name)
             if t.dtype != dt or not t.is_contiguous():
@@ -42,14 +43,18 @@ class DeviceCSR:
         self._transposed: Optional["DeviceCSR"] = None
         self._workspace: Optional[torch.Tensor] = None
         self._plan = C.c_void_p()
+        self._streaming_requested = bool(streaming)
         with torch.cuda.device(self.device):
-            N.check(N.lib().tg_plan_create(N.ptr(rowptr), self.n_rows, self.n_cols, self.nnz, self._hub_threshold,
-                                           self._segment_nnz, C.byref(self._plan), N.current_stream_ptr()),
-                    "tg_plan_create")
-        info = (C.c_int64 * 6)()
+            # colidx/vals = NULL -> no column-chunk streaming layout (gather kernel only)
+            N.check(N.lib().tg_plan_create(N.ptr(rowptr), N.ptr(colidx) if streaming else 0,
+                                           N.ptr(vals) if streaming else 0, self.n_rows, self.n_cols, self.nnz,
+                                           self._hub_threshold, self._segment_nnz, C.byref(self._plan),
+                                           N.current_stream_ptr()), "tg_plan_create")
+        info = (C.c_int64 * 8)()
         N.check(N.lib().tg_plan_info(self._plan, info), "tg_plan_info")
         self.n_hub_rows, self.n_segments, self.hub_nnz, self.max_row_nnz = (int(info[i]) for i in range(4))
         self.hub_threshold, self.segment_nnz = int(info[4]), int(info[5])
+        self.streaming, self.chunk_rows = bool(info[6]), int(info[7])
 
     def __del__(self):
         try:
@@ -122,7 +127,7 @@ class DeviceCSR:
             self._symmetric = False
             self._transposed = DeviceCSR(t_rowptr, t_colidx, t_vals, self.n_cols, self.n_rows,
                                          hub_threshold=self._hub_threshold, segment_nnz=self._segment_nnz,
-                                         symmetric=False)
+                                         symmetric=False, streaming=self._streaming_requested)
             self._transposed._transposed = self
         return self._transposed
 

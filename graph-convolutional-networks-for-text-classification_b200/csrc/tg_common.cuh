@@ -49,6 +49,18 @@ struct tg_plan {
     int32_t* seg_begin = nullptr;    // [n_seg]   first stored entry of the segment
     int32_t* seg_end = nullptr;      // [n_seg]   one past the last stored entry
     uint32_t* tickets = nullptr;     // [n_hub]   arrival counters (integer; reset by the last arriver)
+
+    // ---- column-chunk streaming sub-plan (tg_stream.cu); present when the hub set is compact -------------------
+    bool stream_ok = false;
+    int32_t chunk_rows = 0;          // T: nodes per column chunk
+    int32_t n_chunks = 0;
+    int32_t cap_doc = 0, cap_hub = 0;  // staged entry windows (entries per chunk held in shared memory)
+    int32_t* colidx2 = nullptr;      // [nnz]  column ids with hub columns rewritten to (HUB_BIT | hub slot)
+    int32_t* hcol = nullptr;         // [hub_nnz] chunk-major copy of the hub rows' entries: column LOCAL to its chunk
+    float* hval = nullptr;           // [hub_nnz]
+    int32_t* htab = nullptr;         // [n_chunks][n_hub+1] offsets into hcol/hval: segment (chunk, hub slot)
+    int4* cdesc = nullptr;           // [n_chunks] {first CSR entry of the chunk's rows, one past the last, htab[c][0], htab[c][n_hub]}
+    uint8_t* row_is_hub = nullptr;   // [n_rows]
 };
 
 namespace tg {

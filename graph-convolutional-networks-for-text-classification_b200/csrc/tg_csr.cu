@@ -8,7 +8,7 @@
 #include <cub/cub.cuh>
 #include <vector>
 
-#include "tg_common.cuh"
+#include "tg_stream.cuh"
 
 namespace tg {
 
@@ -258,8 +258,8 @@ int tg_csr_transpose(const int32_t* rowptr, const int32_t* colidx, const float* 
 }
 
 // ---- skew plan -----------------------------------------------------------------------------------------
-int tg_plan_create(const int32_t* rowptr, int64_t n_rows, int64_t n_cols, int64_t nnz, int32_t hub_threshold,
-                   int32_t segment_nnz, tg_plan** plan_out, void* stream) {
+int tg_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* vals, int64_t n_rows, int64_t n_cols,
+                   int64_t nnz, int32_t hub_threshold, int32_t segment_nnz, tg_plan** plan_out, void* stream) {
     using namespace tg;
     cudaStream_t st = as_stream(stream);
     TG_REQUIRE(rowptr && plan_out, TG_ERR_INVALID_ARG, "null pointer");
@@ -321,28 +321,38 @@ int tg_plan_create(const int32_t* rowptr, int64_t n_rows, int64_t n_cols, int64_
         tg_plan_destroy(pl);
         return cuda_fail(e, "plan upload", __FILE__, __LINE__);
     }
+    // optional streaming sub-plan (square matrices with a compact hub set: the document-topic-topic graphs)
+    const int rc = stream_plan_build(pl, rowptr, colidx, vals, h_ptr.data(), st);
+    if (rc != TG_OK) {
+        tg_plan_destroy(pl);
+        return rc;
+    }
     *plan_out = pl;
     return TG_OK;
 }
 
 void tg_plan_destroy(tg_plan* pl) {
     if (!pl) return;
+    tg::stream_plan_free(pl);
     cudaFree(pl->hub_rows); cudaFree(pl->hub_seg_ptr); cudaFree(pl->seg_hub);
     cudaFree(pl->seg_begin); cudaFree(pl->seg_end); cudaFree(pl->tickets);
     delete pl;
 }
 
-int tg_plan_info(const tg_plan* pl, int64_t info[6]) {
+int tg_plan_info(const tg_plan* pl, int64_t info[8]) {
     TG_REQUIRE(pl && info, TG_ERR_INVALID_ARG, "null pointer");
     info[0] = pl->n_hub; info[1] = pl->n_seg; info[2] = pl->hub_nnz;
     info[3] = pl->max_row_nnz; info[4] = pl->hub_threshold; info[5] = pl->segment_nnz;
+    info[6] = pl->stream_ok ? 1 : 0; info[7] = pl->stream_ok ? pl->chunk_rows : 0;
     return TG_OK;
 }
 
 size_t tg_plan_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
     if (!pl || n_feat <= 0) return 0;
     const size_t ld = (size_t)((n_feat + 3) / 4) * 4;
-    return (size_t)pl->n_seg * ld * sizeof(float) + 16;
+    const size_t v1 = (size_t)pl->n_seg * ld * sizeof(float) + 16;
+    const size_t v2 = tg::stream_workspace_bytes(pl, n_feat);
+    return v1 > v2 ? v1 : v2;
 }
 
 }  // extern "C"

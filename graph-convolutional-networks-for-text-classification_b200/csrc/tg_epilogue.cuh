@@ -1,0 +1,232 @@
+// tg_epilogue.cuh — register tiles and the fused epilogues shared by the SpMM kernels (tg_spmm.cu, tg_stream.cu).
+//
+//   EpiStore : Y = dropout(relu(acc + bias))            reference layer.py:109-110, :182, :185
+//   EpiLoss  : logits = acc + bias; log-softmax; masked cross-entropy and its gradient   trainer.py:358-359
+#pragma once
+#include "tg_common.cuh"
+
+namespace tg {
+
+// ---- VEC-generic register tiles ----------------------------------------------------------------------------
+template <int VEC>
+struct Chunk {
+    float v[VEC];
+};
+
+template <int VEC>
+__device__ __forceinline__ Chunk<VEC> chunk_zero() {
+    Chunk<VEC> c;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) c.v[k] = 0.f;
+    return c;
+}
+
+template <int VEC>
+__device__ __forceinline__ Chunk<VEC> chunk_ldg(const float* p);
+template <>
+__device__ __forceinline__ Chunk<4> chunk_ldg<4>(const float* p) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    Chunk<4> c;
+    c.v[0] = t.x; c.v[1] = t.y; c.v[2] = t.z; c.v[3] = t.w;
+    return c;
+}
+template <>
+__device__ __forceinline__ Chunk<1> chunk_ldg<1>(const float* p) {
+    Chunk<1> c;
+    c.v[0] = __ldg(p);
+    return c;
+}
+
+// partial rows are written by other SMs in this launch: read them at L2 (.cg), never through L1
+template <int VEC>
+__device__ __forceinline__ Chunk<VEC> chunk_ldcg(const float* p);
+template <>
+__device__ __forceinline__ Chunk<4> chunk_ldcg<4>(const float* p) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+    Chunk<4> c;
+    c.v[0] = t.x; c.v[1] = t.y; c.v[2] = t.z; c.v[3] = t.w;
+    return c;
+}
+template <>
+__device__ __forceinline__ Chunk<1> chunk_ldcg<1>(const float* p) {
+    Chunk<1> c;
+    c.v[0] = __ldcg(p);
+    return c;
+}
+
+template <int VEC>
+__device__ __forceinline__ void chunk_st(float* p, const Chunk<VEC>& c);
+template <>
+__device__ __forceinline__ void chunk_st<4>(float* p, const Chunk<4>& c) {
+    *reinterpret_cast<float4*>(p) = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
+}
+template <>
+__device__ __forceinline__ void chunk_st<1>(float* p, const Chunk<1>& c) {
+    *p = c.v[0];
+}
+
+template <int G>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+    if (G == 32) return 0xffffffffu;
+    return ((1u << G) - 1u) << ((lane / G) * G);
+}
+
+
+// ---- epilogues ------------------------------------------------------------------------------------------------
+// Elementwise: Y = dropout(relu(acc + bias))   (each stage optional)
+struct EpiStore {
+    float* Y;
+    int64_t ldy;
+    const float* bias;
+    int relu;
+    int drop_mode;  // 0 none, 1 Philox counter RNG, 2 explicit keep mask
+    const uint8_t* keep_mask;
+    uint32_t keep_thr;
+    float scale;
+    uint64_t seed, offset;
+    int32_t n_feat;
+
+    template <int VEC, int G, int CPL>
+    __device__ __forceinline__ void apply(int64_t row, int gl, unsigned gmask, int n_chunks,
+                                          Chunk<VEC> (&acc)[CPL]) const {
+        Philox4 rnd = Philox4{0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int chunk = gl + i * G;
+            if (chunk >= n_chunks) continue;
+            const int col0 = chunk * VEC;
+            Chunk<VEC> y = acc[i];
+            if (bias) {
+                const Chunk<VEC> bb = chunk_ldg<VEC>(bias + col0);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) y.v[k] += bb.v[k];
+            }
+            if (relu) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) y.v[k] = fmaxf(y.v[k], 0.f);
+            }
+            if (drop_mode == 1) {
+                if (VEC == 4) {
+                    // chunk q = gl + i*G: slot = q % 32, half = (q / 32) % 2, j = q / 64 (see tg_common.cuh)
+                    const int q = chunk;
+                    if (G < 32 || (i & 1) == 0) rnd = dropout_philox(row, (uint32_t)(q & 31), (uint32_t)(q >> 6), seed, offset);
+                    uint32_t u[4];
+                    dropout_u16x4(rnd, (q >> 5) & 1, u);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) y.v[k] = (u[k] < keep_thr) ? y.v[k] * scale : 0.f;
+                } else {
+                    const int q = col0 >> 2;
+                    const Philox4 r1 = dropout_philox(row, (uint32_t)(q & 31), (uint32_t)(q >> 6), seed, offset);
+                    uint32_t u[4];
+                    dropout_u16x4(r1, (q >> 5) & 1, u);
+                    y.v[0] = (u[col0 & 3] < keep_thr) ? y.v[0] * scale : 0.f;
+                }
+            } else if (drop_mode == 2) {
+                const uint8_t* mp = keep_mask + row * (int64_t)n_feat + col0;
+                if (VEC == 4) {
+                    const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(mp));
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) y.v[k] = ((m >> (8 * k)) & 0xffu) ? y.v[k] * scale : 0.f;
+                } else {
+                    y.v[0] = __ldg(mp) ? y.v[0] * scale : 0.f;
+                }
+            }
+            chunk_st<VEC>(Y + row * ldy + col0, y);
+        }
+    }
+};
+
+// Row-wise: logits = acc + bias; log-softmax; masked cross-entropy and its gradient.
+struct EpiLoss {
+    const float* bias;
+    const int32_t* row_label;
+    float inv_count;
+    float* logits;  // optional
+    int64_t ldl;
+    float* dZ;  // optional
+    int64_t ldd;
+    float* row_loss;
+    int32_t n_class;
+
+    template <int VEC, int G, int CPL>
+    __device__ __forceinline__ void apply(int64_t row, int gl, unsigned gmask, int n_chunks,
+                                          Chunk<VEC> (&acc)[CPL]) const {
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int chunk = gl + i * G;
+            if (chunk >= n_chunks) continue;
+            const int col0 = chunk * VEC;
+            if (bias) {
+                const Chunk<VEC> bb = chunk_ldg<VEC>(bias + col0);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc[i].v[k] += bb.v[k];
+            }
+            if (logits) chunk_st<VEC>(logits + row * ldl + col0, acc[i]);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) m = fmaxf(m, acc[i].v[k]);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, o, G));
+        float se = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int chunk = gl + i * G;
+            if (chunk >= n_chunks) continue;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) se += expf(acc[i].v[k] - m);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) se += __shfl_xor_sync(gmask, se, o, G);
+        const float lse = m + logf(se);
+        const int y = __ldg(row_label + row);
+        // z_y lives in chunk y/VEC, owned by lane (y/VEC) % G, register (y/VEC) / G
+        float zy = 0.f;
+        if (y >= 0) {
+            const int ychunk = y / VEC, yk = y % VEC;
+            float mine = 0.f;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i)
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    if (gl + i * G == ychunk && k == yk) mine = acc[i].v[k];
+            zy = __shfl_sync(gmask, mine, ychunk % G, G);
+        }
+        if (gl == 0) row_loss[row] = (y >= 0) ? (lse - zy) * inv_count : 0.f;
+        if (dZ) {
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int chunk = gl + i * G;
+                if (chunk >= n_chunks) continue;
+                const int col0 = chunk * VEC;
+                Chunk<VEC> g;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    const float sm = expf(acc[i].v[k] - lse);
+                    g.v[k] = (y >= 0) ? (sm - ((col0 + k) == y ? 1.f : 0.f)) * inv_count : 0.f;
+                }
+                chunk_st<VEC>(dZ + row * ldd + col0, g);
+            }
+        }
+    }
+};
+
+
+// shape dispatch: G lanes per row and CPL chunks per lane so that G*CPL >= n_chunks
+#define TG_SHAPE_SWITCH(VEC, nc, LAUNCH)                                   \
+    do {                                                                   \
+        if ((nc) <= 2) return LAUNCH(VEC, 2, 1);                           \
+        if ((nc) <= 4) return LAUNCH(VEC, 4, 1);                           \
+        if ((nc) <= 8) return LAUNCH(VEC, 8, 1);                           \
+        if ((nc) <= 16) return LAUNCH(VEC, 16, 1);                         \
+        if ((nc) <= 32) return LAUNCH(VEC, 32, 1);                         \
+        if ((nc) <= 64) return LAUNCH(VEC, 32, 2);                         \
+        if ((nc) <= 96) return LAUNCH(VEC, 32, 3);                         \
+        if ((nc) <= 128) return LAUNCH(VEC, 32, 4);                        \
+        if ((nc) <= 192) return LAUNCH(VEC, 32, 6);                        \
+        if ((nc) <= 256) return LAUNCH(VEC, 32, 8);                        \
+    } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace tg

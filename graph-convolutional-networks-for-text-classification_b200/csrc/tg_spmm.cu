@@ -15,7 +15,8 @@
 //     partials in segment order and applies the epilogue.  The order of every floating-point addition is
 //     fixed by the plan, so results are bitwise reproducible run to run.
 // Hub segments occupy the first blocks of the grid so the long work starts first.
-#include "tg_common.cuh"
+#include "tg_epilogue.cuh"
+#include "tg_stream.cuh"
 
 namespace tg {
 
@@ -45,70 +46,6 @@ struct SpmmArgs {
     int32_t n_seg;
     int32_t n_hub_blocks;
 };
-
-// ---- VEC-generic register tiles ----------------------------------------------------------------------------
-template <int VEC>
-struct Chunk {
-    float v[VEC];
-};
-
-template <int VEC>
-__device__ __forceinline__ Chunk<VEC> chunk_zero() {
-    Chunk<VEC> c;
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) c.v[k] = 0.f;
-    return c;
-}
-
-template <int VEC>
-__device__ __forceinline__ Chunk<VEC> chunk_ldg(const float* p);
-template <>
-__device__ __forceinline__ Chunk<4> chunk_ldg<4>(const float* p) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-    Chunk<4> c;
-    c.v[0] = t.x; c.v[1] = t.y; c.v[2] = t.z; c.v[3] = t.w;
-    return c;
-}
-template <>
-__device__ __forceinline__ Chunk<1> chunk_ldg<1>(const float* p) {
-    Chunk<1> c;
-    c.v[0] = __ldg(p);
-    return c;
-}
-
-// partial rows are written by other SMs in this launch: read them at L2 (.cg), never through L1
-template <int VEC>
-__device__ __forceinline__ Chunk<VEC> chunk_ldcg(const float* p);
-template <>
-__device__ __forceinline__ Chunk<4> chunk_ldcg<4>(const float* p) {
-    const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
-    Chunk<4> c;
-    c.v[0] = t.x; c.v[1] = t.y; c.v[2] = t.z; c.v[3] = t.w;
-    return c;
-}
-template <>
-__device__ __forceinline__ Chunk<1> chunk_ldcg<1>(const float* p) {
-    Chunk<1> c;
-    c.v[0] = __ldcg(p);
-    return c;
-}
-
-template <int VEC>
-__device__ __forceinline__ void chunk_st(float* p, const Chunk<VEC>& c);
-template <>
-__device__ __forceinline__ void chunk_st<4>(float* p, const Chunk<4>& c) {
-    *reinterpret_cast<float4*>(p) = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
-}
-template <>
-__device__ __forceinline__ void chunk_st<1>(float* p, const Chunk<1>& c) {
-    *p = c.v[0];
-}
-
-template <int G>
-__device__ __forceinline__ unsigned group_mask(int lane) {
-    if (G == 32) return 0xffffffffu;
-    return ((1u << G) - 1u) << ((lane / G) * G);
-}
 
 // ---- the gather/accumulate core: acc += sum_{p in [s,e)} vals[p] * B[colidx[p], my chunks] -------------------
 template <int VEC, int G, int CPL>
@@ -152,145 +89,6 @@ __device__ __forceinline__ void accumulate_range(const SpmmArgs& a, int s, int e
         }
     }
 }
-
-// ---- epilogues ------------------------------------------------------------------------------------------------
-// Elementwise: Y = dropout(relu(acc + bias))   (each stage optional)
-struct EpiStore {
-    float* Y;
-    int64_t ldy;
-    const float* bias;
-    int relu;
-    int drop_mode;  // 0 none, 1 Philox counter RNG, 2 explicit keep mask
-    const uint8_t* keep_mask;
-    uint32_t keep_thr;
-    float scale;
-    uint64_t seed, offset;
-    int32_t n_feat;
-
-    template <int VEC, int G, int CPL>
-    __device__ __forceinline__ void apply(int64_t row, int gl, unsigned gmask, int n_chunks,
-                                          Chunk<VEC> (&acc)[CPL]) const {
-        Philox4 rnd = Philox4{0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-            const int chunk = gl + i * G;
-            if (chunk >= n_chunks) continue;
-            const int col0 = chunk * VEC;
-            Chunk<VEC> y = acc[i];
-            if (bias) {
-                const Chunk<VEC> bb = chunk_ldg<VEC>(bias + col0);
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) y.v[k] += bb.v[k];
-            }
-            if (relu) {
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) y.v[k] = fmaxf(y.v[k], 0.f);
-            }
-            if (drop_mode == 1) {
-                if (VEC == 4) {
-                    // chunk q = gl + i*G: slot = q % 32, half = (q / 32) % 2, j = q / 64 (see tg_common.cuh)
-                    const int q = chunk;
-                    if (G < 32 || (i & 1) == 0) rnd = dropout_philox(row, (uint32_t)(q & 31), (uint32_t)(q >> 6), seed, offset);
-                    uint32_t u[4];
-                    dropout_u16x4(rnd, (q >> 5) & 1, u);
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) y.v[k] = (u[k] < keep_thr) ? y.v[k] * scale : 0.f;
-                } else {
-                    const int q = col0 >> 2;
-                    const Philox4 r1 = dropout_philox(row, (uint32_t)(q & 31), (uint32_t)(q >> 6), seed, offset);
-                    uint32_t u[4];
-                    dropout_u16x4(r1, (q >> 5) & 1, u);
-                    y.v[0] = (u[col0 & 3] < keep_thr) ? y.v[0] * scale : 0.f;
-                }
-            } else if (drop_mode == 2) {
-                const uint8_t* mp = keep_mask + row * (int64_t)n_feat + col0;
-                if (VEC == 4) {
-                    const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(mp));
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) y.v[k] = ((m >> (8 * k)) & 0xffu) ? y.v[k] * scale : 0.f;
-                } else {
-                    y.v[0] = __ldg(mp) ? y.v[0] * scale : 0.f;
-                }
-            }
-            chunk_st<VEC>(Y + row * ldy + col0, y);
-        }
-    }
-};
-
-// Row-wise: logits = acc + bias; log-softmax; masked cross-entropy and its gradient.
-struct EpiLoss {
-    const float* bias;
-    const int32_t* row_label;
-    float inv_count;
-    float* logits;  // optional
-    int64_t ldl;
-    float* dZ;  // optional
-    int64_t ldd;
-    float* row_loss;
-    int32_t n_class;
-
-    template <int VEC, int G, int CPL>
-    __device__ __forceinline__ void apply(int64_t row, int gl, unsigned gmask, int n_chunks,
-                                          Chunk<VEC> (&acc)[CPL]) const {
-        float m = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-            const int chunk = gl + i * G;
-            if (chunk >= n_chunks) continue;
-            const int col0 = chunk * VEC;
-            if (bias) {
-                const Chunk<VEC> bb = chunk_ldg<VEC>(bias + col0);
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) acc[i].v[k] += bb.v[k];
-            }
-            if (logits) chunk_st<VEC>(logits + row * ldl + col0, acc[i]);
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) m = fmaxf(m, acc[i].v[k]);
-        }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, o, G));
-        float se = 0.f;
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-            const int chunk = gl + i * G;
-            if (chunk >= n_chunks) continue;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) se += expf(acc[i].v[k] - m);
-        }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) se += __shfl_xor_sync(gmask, se, o, G);
-        const float lse = m + logf(se);
-        const int y = __ldg(row_label + row);
-        // z_y lives in chunk y/VEC, owned by lane (y/VEC) % G, register (y/VEC) / G
-        float zy = 0.f;
-        if (y >= 0) {
-            const int ychunk = y / VEC, yk = y % VEC;
-            float mine = 0.f;
-#pragma unroll
-            for (int i = 0; i < CPL; ++i)
-#pragma unroll
-                for (int k = 0; k < VEC; ++k)
-                    if (gl + i * G == ychunk && k == yk) mine = acc[i].v[k];
-            zy = __shfl_sync(gmask, mine, ychunk % G, G);
-        }
-        if (gl == 0) row_loss[row] = (y >= 0) ? (lse - zy) * inv_count : 0.f;
-        if (dZ) {
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                const int chunk = gl + i * G;
-                if (chunk >= n_chunks) continue;
-                const int col0 = chunk * VEC;
-                Chunk<VEC> g;
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) {
-                    const float sm = expf(acc[i].v[k] - lse);
-                    g.v[k] = (y >= 0) ? (sm - ((col0 + k) == y ? 1.f : 0.f)) * inv_count : 0.f;
-                }
-                chunk_st<VEC>(dZ + row * ldd + col0, g);
-            }
-        }
-    }
-};
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
 template <int VEC, int G, int CPL, class Epi>
@@ -388,21 +186,6 @@ static int launch_cfg(SpmmArgs a, const Epi& epi, cudaStream_t st) {
     return TG_OK;
 }
 
-// shape dispatch: G lanes per row and CPL chunks per lane so that G*CPL >= n_chunks
-#define TG_SHAPE_SWITCH(VEC, nc, LAUNCH)                                   \
-    do {                                                                   \
-        if ((nc) <= 2) return LAUNCH(VEC, 2, 1);                           \
-        if ((nc) <= 4) return LAUNCH(VEC, 4, 1);                           \
-        if ((nc) <= 8) return LAUNCH(VEC, 8, 1);                           \
-        if ((nc) <= 16) return LAUNCH(VEC, 16, 1);                         \
-        if ((nc) <= 32) return LAUNCH(VEC, 32, 1);                         \
-        if ((nc) <= 64) return LAUNCH(VEC, 32, 2);                         \
-        if ((nc) <= 96) return LAUNCH(VEC, 32, 3);                         \
-        if ((nc) <= 128) return LAUNCH(VEC, 32, 4);                        \
-        if ((nc) <= 192) return LAUNCH(VEC, 32, 6);                        \
-        if ((nc) <= 256) return LAUNCH(VEC, 32, 8);                        \
-    } while (0)
-
 template <int VEC, class Epi>
 static int launch_vec(SpmmArgs a, const Epi& epi, cudaStream_t st) {
 #define TG_LAUNCH_SPMM(V, G, C) launch_cfg<V, G, C>(a, epi, st)
@@ -452,7 +235,14 @@ static int rowwise_loss_vec(const float* Z, int64_t ldz, int64_t n_rows, int n_c
     return TG_ERR_UNSUPPORTED;
 }
 
-static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int stream_dispatch(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st) {
+    return stream_spmm_store(pl, c, epi, st);
+}
+static inline int stream_dispatch(const tg_plan* pl, const StreamCall& c, const EpiLoss& epi, cudaStream_t st) {
+    return stream_spmm_loss(pl, c, epi, st);
+}
+template <class Epi> struct EpiTraits { static constexpr bool whole_row = false; };
+template <> struct EpiTraits<EpiLoss> { static constexpr bool whole_row = true; };
 
 template <class Epi>
 static int run_spmm(const tg_plan* pl, const int32_t* rowptr, const int32_t* colidx, const float* vals,
@@ -463,8 +253,13 @@ static int run_spmm(const tg_plan* pl, const int32_t* rowptr, const int32_t* col
     TG_REQUIRE(n_feat > 0, TG_ERR_INVALID_ARG, "n_feat must be positive");
     TG_REQUIRE(ldb >= n_feat, TG_ERR_INVALID_ARG, "ldb < n_feat");
     const size_t need = tg_plan_workspace_bytes(pl, n_feat);
-    TG_REQUIRE(pl->n_seg == 0 || (workspace && workspace_bytes >= need), TG_ERR_WORKSPACE,
+    TG_REQUIRE((pl->n_seg == 0 && !pl->stream_ok) || (workspace && workspace_bytes >= need), TG_ERR_WORKSPACE,
                "workspace %zu B < required %zu B", workspace_bytes, need);
+    {
+        // column-chunk streaming kernel (tg_stream.cu) when the plan carries the sub-plan and the operands qualify
+        StreamCall sc{rowptr, vals, B, ldb, n_feat, workspace, workspace_bytes};
+        if (stream_applicable(pl, sc, out_vec4_ok, EpiTraits<Epi>::whole_row)) return stream_dispatch(pl, sc, epi, st);
+    }
     SpmmArgs a;
     a.rowptr = rowptr; a.colidx = colidx; a.vals = vals; a.B = B; a.ldb = ldb;
     a.n_rows = pl->n_rows; a.n_feat = n_feat; a.hub_threshold = pl->hub_threshold;

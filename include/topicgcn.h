@@ -73,15 +73,22 @@ int tg_csr_transpose(const int32_t* rowptr, const int32_t* colidx, const float* 
  * SpMM plan: row classification for the doc/topic skew (short rows -> one lane group per row, hub rows
  * with more than `hub_threshold` stored entries -> split into `segment_nnz` segments reduced in fixed
  * order).  Opaque; owns a few small device tables.
- * ---------------------------------------------------------------------------------------------- */
+ */
 typedef struct tg_plan tg_plan;
-
-int tg_plan_create(const int32_t* rowptr, int64_t n_rows, int64_t n_cols, int64_t nnz,
-                   int32_t hub_threshold /*<=0: default*/, int32_t segment_nnz /*<=0: default*/,
-                   tg_plan** plan_out, void* stream);
+/*
+ * When the matrix is square and its hub set is compact (<= 512 hub rows holding >= 1/8 of the entries: the
+ * document-topic-topic graphs), the plan also carries the "column-chunk streaming" layout (tg_stream.cu): a
+ * chunk-major copy of the hub rows' entries and an (index, value) interleaved copy of all entries.  The plan
+ * therefore SNAPSHOTS the values: rebuild it when `vals` change.  colidx/vals may be NULL (no streaming layout).
+ * Environment knobs read at creation: TG_STREAM=0 disables it, TG_STREAM_CHUNK={128,256,512} nodes per chunk.
+ * ---------------------------------------------------------------------------------------------- */
+int tg_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* vals, int64_t n_rows,
+                   int64_t n_cols, int64_t nnz, int32_t hub_threshold /*<=0: default*/,
+                   int32_t segment_nnz /*<=0: default*/, tg_plan** plan_out, void* stream);
 void tg_plan_destroy(tg_plan* plan);
-/* info: [0]=n_hub_rows [1]=n_segments [2]=hub_nnz [3]=max_row_nnz [4]=hub_threshold [5]=segment_nnz */
-int tg_plan_info(const tg_plan* plan, int64_t info_host[6]);
+/* info: [0]=n_hub_rows [1]=n_segments [2]=hub_nnz [3]=max_row_nnz [4]=hub_threshold [5]=segment_nnz
+ *       [6]=streaming layout present (0/1) [7]=nodes per chunk */
+int tg_plan_info(const tg_plan* plan, int64_t info_host[8]);
 /* bytes of scratch a tg_spmm* / tg_gc* call with `n_feat` columns needs (partials of split hub rows) */
 size_t tg_plan_workspace_bytes(const tg_plan* plan, int32_t n_feat);
 

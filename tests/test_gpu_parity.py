@@ -104,8 +104,11 @@ def test_spmm_small_golden_shapes(tg, small_golden, F):
     rng = np.random.default_rng(F)
     B = rng.normal(size=(coo.shape[1], F)).astype(np.float32)
     ref = O.spmm(coo, B)
-    for kw in ({}, {"hub_threshold": 16, "segment_nnz": 8}):  # second plan forces the split-row path on a tiny graph
+    # plans: default; split rows + column-chunk streaming forced on a tiny graph; the same without streaming
+    for kw in ({}, {"hub_threshold": 16, "segment_nnz": 8}, {"hub_threshold": 16, "segment_nnz": 8, "streaming": False}):
         csr = to_csr(tg, coo, **kw)
+        if "streaming" not in kw and kw:
+            assert csr.streaming
         y = tg.spmm(csr, torch.tensor(B, device=dev())).cpu().numpy()
         assert rel_err(y, ref) <= SPMM_RTOL, (F, kw)
         bias = rng.normal(size=F).astype(np.float32)
@@ -126,7 +129,7 @@ def test_spmm_r8_graph(tg, r8_golden, F):
     nd = int(g["n_docs"])
     B = np.random.default_rng(1).uniform(size=(coo.shape[1], F)).astype(np.float32)
     ref, ref64 = O.spmm(coo, B), O.spmm_f64(coo, B)
-    for kw in ({}, {"hub_threshold": 256, "segment_nnz": 128}):
+    for kw in ({}, {"hub_threshold": 256, "segment_nnz": 128}, {"hub_threshold": 256, "segment_nnz": 128, "streaming": False}):
         csr = to_csr(tg, coo, **kw)
         y = tg.spmm(csr, torch.tensor(B, device=dev())).cpu().numpy()
         assert rel_err(y[:nd], ref[:nd]) <= SPMM_RTOL       # document rows
@@ -134,11 +137,12 @@ def test_spmm_r8_graph(tg, r8_golden, F):
         assert rel_err(y, ref64) <= rel_err(ref, ref64) + 2e-7
 
 
-def test_spmm_deterministic_and_split_rows(tg):
+@pytest.mark.parametrize("streaming", [True, False])
+def test_spmm_deterministic_and_split_rows(tg, streaming):
     from topicgcn_b200 import graphgen
     g, h, c = graphgen.make_config("c3_1m_docs_256_topics", device="cuda:0", scale=0.1)
-    csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n)
-    assert csr.n_hub_rows == g.n_hubs and csr.n_segments > csr.n_hub_rows
+    csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n, streaming=streaming)
+    assert csr.n_hub_rows == g.n_hubs and csr.n_segments > csr.n_hub_rows and csr.streaming == streaming
     B = torch.rand(g.n, 256, device=dev())
     y1 = tg.spmm(csr, B).clone()
     for _ in range(3):
@@ -175,6 +179,7 @@ def test_spmm_full_size_properties(tg):
     from topicgcn_b200 import graphgen
     g, h, c = graphgen.make_config("c3_1m_docs_256_topics", device="cuda:0")
     csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n)
+    assert csr.streaming
     F = 64
     X = torch.randn(g.n, F, device=dev())
     Y = torch.randn(g.n, F, device=dev())
@@ -194,6 +199,10 @@ def test_spmm_full_size_properties(tg):
     assert float(((got - rs).abs() / rs.abs().clamp_min(1e-12)).max()) < 1e-5
     # idempotent re-run
     assert torch.equal(AX, tg.spmm(csr, X))
+    # the gather kernel (no streaming layout) agrees with the streaming kernel
+    csr_g = tg.DeviceCSR(csr.rowptr, csr.colidx, csr.vals, g.n, g.n, streaming=False)
+    AXg = tg.spmm(csr_g, X)
+    assert float((AXg - AX).abs().max() / AX.abs().max()) < 1e-5
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -207,7 +216,10 @@ def test_philox_keep_mask_bit_exact(tg):
         assert np.array_equal(got, O.philox_keep_mask(n, f, p, seed, off)), (n, f, p)
 
 
-@pytest.mark.parametrize("plan_kw", [{}, {"hub_threshold": 16, "segment_nnz": 8}])
+PLAN_VARIANTS = [{}, {"hub_threshold": 16, "segment_nnz": 8}, {"hub_threshold": 16, "segment_nnz": 8, "streaming": False}]
+
+
+@pytest.mark.parametrize("plan_kw", PLAN_VARIANTS)
 def test_gc1_fused_forward(tg, small_golden, plan_kw):
     from topicgcn_b200 import ops
     g = small_golden
@@ -232,8 +244,8 @@ def test_gc1_fused_forward(tg, small_golden, plan_kw):
     assert np.array_equal(h_ph != 0, (np.maximum(Z1, 0) * pm) != 0)
 
 
-@pytest.mark.parametrize("plan_kw", [{}, {"hub_threshold": 16, "segment_nnz": 8}])
-@pytest.mark.parametrize("C", [5, 8, 20, 23])
+@pytest.mark.parametrize("plan_kw", PLAN_VARIANTS)
+@pytest.mark.parametrize("C", [5, 8, 20, 23, 40])
 def test_gc2_loss_fused_forward(tg, small_golden, plan_kw, C):
     from topicgcn_b200 import ops
     g = small_golden
