@@ -55,12 +55,12 @@ struct tg_plan {
     int32_t chunk_rows = 0;          // T: nodes per column chunk
     int32_t n_chunks = 0;
     int32_t cap_doc = 0, cap_hub = 0;  // staged entry windows (entries per chunk held in shared memory)
-    int32_t* colidx2 = nullptr;      // [nnz]  column ids with hub columns rewritten to (HUB_BIT | hub slot)
+    int32_t* colidx2 = nullptr;      // [nnz] int2 {hub slot or column id, value bits}; per row: non-hub columns first
     int32_t* hcol = nullptr;         // [hub_nnz] chunk-major copy of the hub rows' entries: column LOCAL to its chunk
     float* hval = nullptr;           // [hub_nnz]
     int32_t* htab = nullptr;         // [n_chunks][n_hub+1] offsets into hcol/hval: segment (chunk, hub slot)
     int4* cdesc = nullptr;           // [n_chunks] {first CSR entry of the chunk's rows, one past the last, htab[c][0], htab[c][n_hub]}
-    uint8_t* row_is_hub = nullptr;   // [n_rows]
+    int32_t* rsplit = nullptr;       // [n_rows] first hub-column entry of each row in colidx2 (rows are reordered: others | hubs)
 };
 
 namespace tg {
@@ -93,9 +93,10 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
 }
 
 // Keep-mask definition shared by every kernel (and restated in oracle/gcn_oracle.py):
-//   element (row, col):  q = col / 4 (float4 chunk), slot = q % 32, j = q / 64, half = (q / 32) % 2
-//   r = philox(counter = (row_lo, row_hi, slot | j << 8, offset_lo), key = (seed_lo ^ offset_hi, seed_hi))
+//   element (row, col):  q = col / 4 (float4 chunk), blk = q / 16 (64-column block), lane8 = q % 8, half = (q / 8) % 2
+//   r = philox(counter = (row_lo, row_hi, lane8 | blk << 8, offset_lo), key = (seed_lo ^ offset_hi, seed_hi))
 //   u16 #(half*4 + col%4) of the 128 random bits;  keep  <=>  u16 < keep_threshold(p)
+// One Philox call therefore serves the two float4 chunks (q, q + 8) a lane of the streaming kernel owns.
 __host__ __device__ __forceinline__ uint32_t dropout_keep_threshold(float p) {
     float t = (1.0f - p) * 65536.0f + 0.5f;
     if (t < 0.f) t = 0.f;
@@ -103,9 +104,9 @@ __host__ __device__ __forceinline__ uint32_t dropout_keep_threshold(float p) {
     return (uint32_t)t;
 }
 
-__host__ __device__ __forceinline__ Philox4 dropout_philox(int64_t row, uint32_t slot, uint32_t j,
+__host__ __device__ __forceinline__ Philox4 dropout_philox(int64_t row, uint32_t lane8, uint32_t blk,
                                                             uint64_t seed, uint64_t offset) {
-    return philox4x32_10((uint32_t)(uint64_t)row, (uint32_t)((uint64_t)row >> 32), slot | (j << 8),
+    return philox4x32_10((uint32_t)(uint64_t)row, (uint32_t)((uint64_t)row >> 32), lane8 | (blk << 8),
                          (uint32_t)offset, (uint32_t)seed ^ (uint32_t)(offset >> 32),
                          (uint32_t)(seed >> 32));
 }

@@ -107,18 +107,20 @@ struct EpiStore {
             }
             if (drop_mode == 1) {
                 if (VEC == 4) {
-                    // chunk q = gl + i*G: slot = q % 32, half = (q / 32) % 2, j = q / 64 (see tg_common.cuh)
+                    // chunk q: Philox call (q % 8, q / 16), half (q / 8) % 2 (see tg_common.cuh); with G == 8 the
+                    // chunks (q, q + 8) of consecutive i share one call
                     const int q = chunk;
-                    if (G < 32 || (i & 1) == 0) rnd = dropout_philox(row, (uint32_t)(q & 31), (uint32_t)(q >> 6), seed, offset);
+                    const bool reuse = (G == 8) && (i & 1);
+                    if (!reuse) rnd = dropout_philox(row, (uint32_t)(q & 7), (uint32_t)(q >> 4), seed, offset);
                     uint32_t u[4];
-                    dropout_u16x4(rnd, (q >> 5) & 1, u);
+                    dropout_u16x4(rnd, (q >> 3) & 1, u);
 #pragma unroll
                     for (int k = 0; k < VEC; ++k) y.v[k] = (u[k] < keep_thr) ? y.v[k] * scale : 0.f;
                 } else {
                     const int q = col0 >> 2;
-                    const Philox4 r1 = dropout_philox(row, (uint32_t)(q & 31), (uint32_t)(q >> 6), seed, offset);
+                    const Philox4 r1 = dropout_philox(row, (uint32_t)(q & 7), (uint32_t)(q >> 4), seed, offset);
                     uint32_t u[4];
-                    dropout_u16x4(r1, (q >> 5) & 1, u);
+                    dropout_u16x4(r1, (q >> 3) & 1, u);
                     y.v[0] = (u[col0 & 3] < keep_thr) ? y.v[0] * scale : 0.f;
                 }
             } else if (drop_mode == 2) {

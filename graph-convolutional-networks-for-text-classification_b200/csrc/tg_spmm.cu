@@ -286,9 +286,9 @@ __global__ void keep_mask_kernel(uint8_t* __restrict__ out, int64_t n_rows, int3
     const int64_t row = idx / n_feat;
     const int col = (int)(idx % n_feat);
     const int q = col >> 2;
-    const Philox4 r = dropout_philox(row, (uint32_t)(q & 31), (uint32_t)(q >> 6), seed, offset);
+    const Philox4 r = dropout_philox(row, (uint32_t)(q & 7), (uint32_t)(q >> 4), seed, offset);
     uint32_t u[4];
-    dropout_u16x4(r, (q >> 5) & 1, u);
+    dropout_u16x4(r, (q >> 3) & 1, u);
     out[idx] = (u[col & 3] < thr) ? 1 : 0;
 }
 

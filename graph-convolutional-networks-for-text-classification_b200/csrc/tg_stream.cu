@@ -27,15 +27,18 @@
 namespace tg {
 
 constexpr int kSThreads = 512;
+constexpr int kGW = 8;                    // lanes per row group: a quarter warp reads one 128-byte line of a row slice
+constexpr int kNG = kSThreads / kGW;      // row groups per CTA
 constexpr int kMaxHubStream = 512;
 constexpr size_t kSmemBudget = 227 * 1024;
 
 struct StreamArgs {
     const int32_t* __restrict__ rowptr;
-    const int2* __restrict__ dent;    // [nnz]     {col2, val bits} of every stored entry (hub columns -> kHubBit | slot)
-    const int2* __restrict__ hent;    // [hub_nnz] {col local to chunk, val bits}, chunk-major / hub-minor
-    const int32_t* __restrict__ htab; // [n_chunks][Kh+1]
-    const int4* __restrict__ cdesc;   // [n_chunks]
+    const int32_t* __restrict__ rsplit;  // [n] first hub-column entry of every row (entries are reordered: others | hubs)
+    const int2* __restrict__ dent;       // [nnz]     {hub slot or column id, val bits}, per row: non-hub columns first
+    const int2* __restrict__ hent;       // [hub_nnz] {column local to chunk, val bits}, chunk-major / hub-minor
+    const int32_t* __restrict__ htab;    // [n_chunks][Kh+1]
+    const int4* __restrict__ cdesc;      // [n_chunks]
     const int32_t* __restrict__ hub_rows;
     const float* __restrict__ B;
     int64_t ldb;
@@ -69,6 +72,7 @@ __device__ __forceinline__ void cp_async_wait() {
 struct StageView {
     float* Bs;       // [T][FT]
     int32_t* rp;     // [T+1]
+    int32_t* rs;     // [T]
     int2* dent;      // [cap_doc]
     int2* hent;      // [cap_hub]
     int32_t* htab;   // [Kh+1]
@@ -77,8 +81,8 @@ struct StageView {
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 __host__ __device__ inline size_t stage_bytes(int T, int FT, int cap_doc, int cap_hub, int Kh) {
-    return align16((size_t)T * FT * 4) + align16((size_t)(T + 1) * 4) + align16((size_t)cap_doc * 8) +
-           align16((size_t)cap_hub * 8) + align16((size_t)(Kh + 1) * 4);
+    return align16((size_t)T * FT * 4) + align16((size_t)(T + 1) * 4) + align16((size_t)T * 4) +
+           align16((size_t)cap_doc * 8) + align16((size_t)cap_hub * 8) + align16((size_t)(Kh + 1) * 4);
 }
 
 __device__ __forceinline__ StageView stage_view(unsigned char* base, int T, int FT, int cap_doc, int cap_hub) {
@@ -87,6 +91,8 @@ __device__ __forceinline__ StageView stage_view(unsigned char* base, int T, int 
     base += align16((size_t)T * FT * 4);
     v.rp = reinterpret_cast<int32_t*>(base);
     base += align16((size_t)(T + 1) * 4);
+    v.rs = reinterpret_cast<int32_t*>(base);
+    base += align16((size_t)T * 4);
     v.dent = reinterpret_cast<int2*>(base);
     base += align16((size_t)cap_doc * 8);
     v.hent = reinterpret_cast<int2*>(base);
@@ -95,20 +101,34 @@ __device__ __forceinline__ StageView stage_view(unsigned char* base, int T, int 
     return v;
 }
 
+// acc[i] += v * row[gl*4 + i*32 .. +4)   — `row` is a shared-memory row slice of FT = 32*CPL floats
+template <int CPL>
+__device__ __forceinline__ void fma_row_smem(Chunk<4> (&acc)[CPL], float v, const float* row, int gl) {
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+        const float4 b = *reinterpret_cast<const float4*>(row + gl * 4 + i * 32);
+        acc[i].v[0] = fmaf(v, b.x, acc[i].v[0]);
+        acc[i].v[1] = fmaf(v, b.y, acc[i].v[1]);
+        acc[i].v[2] = fmaf(v, b.z, acc[i].v[2]);
+        acc[i].v[3] = fmaf(v, b.w, acc[i].v[3]);
+    }
+}
+
 // ---- the streaming kernel ----------------------------------------------------------------------------------------------
-template <int GW, int KPG, class Epi>
+// CTA = 64 row groups of 8 lanes; a lane owns CPL float4 chunks (q0 + 8*i) of the CTA's 32*CPL-column slice.
+template <int CPL, int KPG, class Epi>
 __global__ void __launch_bounds__(kSThreads, 1) stream_spmm_kernel(const StreamArgs a, const Epi epi) {
-    constexpr int FT = GW * 4;
-    constexpr int NG = kSThreads / GW;
+    constexpr int FT = 32 * CPL;
+    constexpr int QS = 8 * CPL;  // float4 chunks per slice
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int gl = lane & (GW - 1);
-    const int grp = tid / GW;
-    const unsigned gmask = group_mask<GW>(lane);
+    const int gl = lane & (kGW - 1);
+    const int grp = tid / kGW;
+    const unsigned gmask = group_mask<kGW>(lane);
     const int slice = blockIdx.x % a.n_slices;
     const int cg = blockIdx.x / a.n_slices;
-    const int q_abs = slice * GW + gl;  // this lane's float4 column within the full row
+    const int q0 = slice * QS + gl;  // this lane's first float4 column within the full row (the others are q0 + 8*i)
     const int c_begin = (int)((int64_t)cg * a.n_chunks / a.n_groups);
     const int c_end = (int)((int64_t)(cg + 1) * a.n_chunks / a.n_groups);
 
@@ -121,44 +141,50 @@ __global__ void __launch_bounds__(kSThreads, 1) stream_spmm_kernel(const StreamA
 
     auto issue_stage = [&](const StageView& sv, int c, const int4 d) {
         const int64_t c0 = (int64_t)c * a.T;
-        // chunk rows of B, this CTA's column slice
-        for (int idx = tid; idx < a.T * GW; idx += kSThreads) {
-            const int r = idx / GW, q = idx % GW;
+        // chunk rows of B, this CTA's column slice: QS 16-byte pieces per row
+        for (int idx = tid; idx < a.T * QS; idx += kSThreads) {
+            const int r = idx / QS, q = idx % QS;
             const int64_t row = c0 + r;
-            const bool ok = row < a.n && (slice * GW + q) < a.n_chunks4;
-            const float* src = ok ? a.B + row * a.ldb + (int64_t)(slice * GW + q) * 4 : a.B;
+            const bool ok = row < a.n && (slice * QS + q) < a.n_chunks4;
+            const float* src = ok ? a.B + row * a.ldb + (int64_t)(slice * QS + q) * 4 : a.B;
             cp_async16(sv.Bs + r * FT + q * 4, src, ok);
         }
         for (int idx = tid; idx <= a.T; idx += kSThreads) {
             const bool ok = c0 + idx <= a.n;
             cp_async4(sv.rp + idx, ok ? a.rowptr + c0 + idx : a.rowptr, ok);
         }
+        for (int idx = tid; idx < a.T; idx += kSThreads) {
+            const bool ok = c0 + idx < a.n;
+            cp_async4(sv.rs + idx, ok ? a.rsplit + c0 + idx : a.rsplit, ok);
+        }
         // entry windows start at an even entry so that every copy is one aligned 16-byte pair
         const int64_t d0 = d.x & ~1, h0 = d.z & ~1;
         for (int idx = tid; idx < a.cap_doc / 2; idx += kSThreads) {
             const int64_t p = d0 + 2 * idx;
-            const bool ok = p < d.y && p + 2 <= ((a.nnz + 1) & ~(int64_t)1);
+            const bool ok = p < d.y;
             cp_async16(sv.dent + 2 * idx, ok ? a.dent + p : a.dent, ok);
         }
         for (int idx = tid; idx < a.cap_hub / 2; idx += kSThreads) {
             const int64_t p = h0 + 2 * idx;
-            const bool ok = p < d.w && p + 2 <= ((a.hub_nnz + 1) & ~(int64_t)1);
+            const bool ok = p < d.w;
             cp_async16(sv.hent + 2 * idx, ok ? a.hent + p : a.hent, ok);
         }
         for (int idx = tid; idx <= a.Kh; idx += kSThreads)
             cp_async4(sv.htab + idx, a.htab + (int64_t)c * (a.Kh + 1) + idx, true);
     };
 
-    float4 hacc[KPG];
+    Chunk<4> hacc[KPG][CPL];
 #pragma unroll
-    for (int kk = 0; kk < KPG; ++kk) hacc[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kk = 0; kk < KPG; ++kk)
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) hacc[kk][i] = chunk_zero<4>();
 
     if (c_begin < c_end) {
         // prologue: hub rows of B (slice) + first stage
-        for (int idx = tid; idx < a.Kh * GW; idx += kSThreads) {
-            const int k = idx / GW, q = idx % GW;
-            const bool ok = (slice * GW + q) < a.n_chunks4;
-            const float* src = ok ? a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb + (int64_t)(slice * GW + q) * 4 : a.B;
+        for (int idx = tid; idx < a.Kh * QS; idx += kSThreads) {
+            const int k = idx / QS, q = idx % QS;
+            const bool ok = (slice * QS + q) < a.n_chunks4;
+            const float* src = ok ? a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb + (int64_t)(slice * QS + q) * 4 : a.B;
             cp_async16(BH + k * FT + q * 4, src, ok);
         }
         int4 d_cur = __ldg(a.cdesc + c_begin);
@@ -178,91 +204,103 @@ __global__ void __launch_bounds__(kSThreads, 1) stream_spmm_kernel(const StreamA
             __syncthreads();
             const int4 d_new = (c + 2 < c_end) ? __ldg(a.cdesc + c + 2) : make_int4(0, 0, 0, 0);
             const StageView sv = stage_at(buf);
-            const int64_t c0 = (int64_t)c * a.T;
-            const int64_t dwin0 = d_cur.x & ~1, hwin0 = d_cur.z & ~1;
+            const int c0 = c * a.T;
+            const int dwin0 = d_cur.x & ~1, hwin0 = d_cur.z & ~1;
+            const int dwin_end = dwin0 + a.cap_doc, hwin_end = hwin0 + a.cap_hub;
 
             // ---- (i) short rows of this chunk --------------------------------------------------------------------
-            for (int lr = grp; lr < a.T; lr += NG) {
-                const int64_t row = c0 + lr;
+            for (int lr = grp; lr < a.T; lr += kNG) {
+                const int64_t row = (int64_t)c0 + lr;
                 if (row >= a.n) break;
                 const int s = sv.rp[lr], e = sv.rp[lr + 1];
                 if (e - s > a.hub_threshold) continue;  // hub rows are produced by (ii)
-                Chunk<4> acc[1];
-                acc[0] = chunk_zero<4>();
-                for (int base = s; base < e; base += GW) {
-                    const int p = base + gl;
-                    int2 ent = make_int2(0, 0);
-                    if (p < e) ent = (p - dwin0 < a.cap_doc) ? sv.dent[p - dwin0] : __ldg(a.dent + p);
-                    const int cnt = min(GW, e - base);
-                    for (int j = 0; j < cnt; j += 4) {
-                        float4 b[4];
-                        float vj[4];
+                const int m = sv.rs[lr];
+                Chunk<4> acc[CPL];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int cj = __shfl_sync(gmask, ent.x, j + u, GW);
-                            vj[u] = __int_as_float(__shfl_sync(gmask, ent.y, j + u, GW));
-                            b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (j + u < cnt) {
-                                if (cj < 0) {
-                                    b[u] = *reinterpret_cast<const float4*>(BH + (cj & 0x7fffffff) * FT + gl * 4);
-                                } else if ((unsigned)(cj - (int)c0) < (unsigned)a.T) {
-                                    b[u] = *reinterpret_cast<const float4*>(sv.Bs + (cj - (int)c0) * FT + gl * 4);
-                                } else if (q_abs < a.n_chunks4) {
-                                    b[u] = __ldg(reinterpret_cast<const float4*>(a.B + (int64_t)cj * a.ldb + (int64_t)q_abs * 4));
+                for (int i = 0; i < CPL; ++i) acc[i] = chunk_zero<4>();
+                if (e <= dwin_end) {
+                    // fast path: every entry of the row sits in the staged window (group-uniform broadcast reads)
+                    const int2* ent = sv.dent - dwin0;
+                    for (int p = s; p < m; ++p) {  // non-hub columns (the self loop): staged chunk or L2
+                        const int2 en = ent[p];
+                        const float v = __int_as_float(en.y);
+                        const unsigned lc = (unsigned)(en.x - c0);
+                        if (lc < (unsigned)a.T) {
+                            fma_row_smem<CPL>(acc, v, sv.Bs + lc * FT, gl);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < CPL; ++i)
+                                if (q0 + 8 * i < a.n_chunks4) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.B + (int64_t)en.x * a.ldb + (int64_t)(q0 + 8 * i) * 4));
+                                    acc[i].v[0] = fmaf(v, b.x, acc[i].v[0]); acc[i].v[1] = fmaf(v, b.y, acc[i].v[1]);
+                                    acc[i].v[2] = fmaf(v, b.z, acc[i].v[2]); acc[i].v[3] = fmaf(v, b.w, acc[i].v[3]);
                                 }
-                            }
                         }
+                    }
+#pragma unroll 4
+                    for (int p = m; p < e; ++p) {  // hub columns: resident hub rows of B
+                        const int2 en = ent[p];
+                        fma_row_smem<CPL>(acc, __int_as_float(en.y), BH + en.x * FT, gl);
+                    }
+                } else {
+                    // slow path (rows whose entries overflow the staged window): entries from L2
+                    for (int p = s; p < e; ++p) {
+                        const int2 en = (p < dwin_end) ? sv.dent[p - dwin0] : __ldg(a.dent + p);
+                        const float v = __int_as_float(en.y);
+                        if (p >= m) {
+                            fma_row_smem<CPL>(acc, v, BH + en.x * FT, gl);
+                        } else if ((unsigned)(en.x - c0) < (unsigned)a.T) {
+                            fma_row_smem<CPL>(acc, v, sv.Bs + (en.x - c0) * FT, gl);
+                        } else {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            acc[0].v[0] = fmaf(vj[u], b[u].x, acc[0].v[0]);
-                            acc[0].v[1] = fmaf(vj[u], b[u].y, acc[0].v[1]);
-                            acc[0].v[2] = fmaf(vj[u], b[u].z, acc[0].v[2]);
-                            acc[0].v[3] = fmaf(vj[u], b[u].w, acc[0].v[3]);
+                            for (int i = 0; i < CPL; ++i)
+                                if (q0 + 8 * i < a.n_chunks4) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.B + (int64_t)en.x * a.ldb + (int64_t)(q0 + 8 * i) * 4));
+                                    acc[i].v[0] = fmaf(v, b.x, acc[i].v[0]); acc[i].v[1] = fmaf(v, b.y, acc[i].v[1]);
+                                    acc[i].v[2] = fmaf(v, b.z, acc[i].v[2]); acc[i].v[3] = fmaf(v, b.w, acc[i].v[3]);
+                                }
                         }
                     }
                 }
-                epi.template apply<4, GW, 1>(row, q_abs, gmask, a.n_chunks4, acc);
+                epi.template apply<4, kGW, CPL>(row, q0, gmask, a.n_chunks4, acc);
             }
 
             // ---- (ii) hub rows: accumulate the chunk's contribution in registers ----------------------------------
 #pragma unroll
             for (int kk = 0; kk < KPG; ++kk) {
-                const int k = grp + NG * kk;
+                const int k = grp + kNG * kk;
                 if (k < a.Kh) {
-                    const int q0 = sv.htab[k], q1 = sv.htab[k + 1];
-                    for (int base = q0; base < q1; base += GW) {
-                        const int q = base + gl;
-                        int2 ent = make_int2(0, 0);
-                        if (q < q1) ent = (q - hwin0 < a.cap_hub) ? sv.hent[q - hwin0] : __ldg(a.hent + q);
-                        const int cnt = min(GW, q1 - base);
-                        for (int j = 0; j < cnt; j += 4) {
-                            float4 b[4];
-                            float vj[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int lc = __shfl_sync(gmask, ent.x, j + u, GW);
-                                vj[u] = __int_as_float(__shfl_sync(gmask, ent.y, j + u, GW));
-                                b[u] = (j + u < cnt) ? *reinterpret_cast<const float4*>(sv.Bs + lc * FT + gl * 4)
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) fma4(hacc[kk], vj[u], b[u]);
+                    const int h0 = sv.htab[k], h1 = sv.htab[k + 1];
+                    if (h1 <= hwin_end) {
+                        const int2* ent = sv.hent - hwin0;
+#pragma unroll 4
+                        for (int q = h0; q < h1; ++q) {
+                            const int2 en = ent[q];
+                            fma_row_smem<CPL>(hacc[kk], __int_as_float(en.y), sv.Bs + en.x * FT, gl);
+                        }
+                    } else {
+                        for (int q = h0; q < h1; ++q) {
+                            const int2 en = (q < hwin_end) ? sv.hent[q - hwin0] : __ldg(a.hent + q);
+                            fma_row_smem<CPL>(hacc[kk], __int_as_float(en.y), sv.Bs + en.x * FT, gl);
                         }
                     }
                 }
             }
-            __syncthreads();  // everyone is done with stage[buf] before it is refilled two iterations later
+            __syncthreads();  // everyone is done with this stage before it is refilled two iterations later
             d_cur = d_next;
             d_next = d_new;
         }
     }
 
     // per-CTA hub partials (zeros when the CTA had no chunk)
-    if (q_abs < a.n_chunks4) {
 #pragma unroll
-        for (int kk = 0; kk < KPG; ++kk) {
-            const int k = grp + NG * kk;
-            if (k < a.Kh) st_f4(a.partials + ((int64_t)cg * a.Kh + k) * a.ldp + (int64_t)q_abs * 4, hacc[kk]);
+    for (int kk = 0; kk < KPG; ++kk) {
+        const int k = grp + kNG * kk;
+        if (k < a.Kh) {
+#pragma unroll
+            for (int i = 0; i < CPL; ++i)
+                if (q0 + 8 * i < a.n_chunks4)
+                    chunk_st<4>(a.partials + ((int64_t)cg * a.Kh + k) * a.ldp + (int64_t)(q0 + 8 * i) * 4, hacc[kk][i]);
         }
     }
 }
@@ -323,20 +361,18 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-static size_t stream_smem_bytes(const tg_plan* pl, int GW) {
-    const int FT = GW * 4;
+static size_t stream_smem_bytes(const tg_plan* pl, int CPL) {
+    const int FT = 32 * CPL;
     return align16((size_t)pl->n_hub * FT * 4) + 2 * stage_bytes(pl->chunk_rows, FT, pl->cap_doc, pl->cap_hub, pl->n_hub);
 }
 
-static int pick_gw(const tg_plan* pl, int n_feat, bool whole_row) {
-    const int pref = env_int("TG_STREAM_GW", 8);
-    const int order[2] = {pref == 16 ? 16 : 8, pref == 16 ? 8 : 16};
-    for (int i = 0; i < 2; ++i) {
-        const int GW = order[i];
-        if (whole_row && n_feat > GW * 4) continue;
-        if (stream_smem_bytes(pl, GW) > kSmemBudget) continue;
-        if ((kSThreads / GW) * 8 < pl->n_hub) continue;
-        return GW;
+// chunks per lane: 2 (64-column slices) when the row is wide enough and the hub rows fit, else 1 (32-column slices)
+static int pick_cpl(const tg_plan* pl, int n_feat, bool whole_row) {
+    const int pref = env_int("TG_STREAM_CPL", 2);
+    for (int CPL = (n_feat > 32 && pref >= 2) ? 2 : 1; CPL >= 1; --CPL) {
+        if (whole_row && n_feat > 32 * CPL) continue;
+        if (stream_smem_bytes(pl, CPL) > kSmemBudget) continue;
+        return CPL;
     }
     return 0;
 }
@@ -345,7 +381,7 @@ bool stream_applicable(const tg_plan* pl, const StreamCall& c, bool out_vec4_ok,
     if (!pl || !pl->stream_ok) return false;
     if (!(c.n_feat % 4 == 0 && c.ldb % 4 == 0 && aligned16(c.B) && out_vec4_ok)) return false;
     if (c.n_feat > 1024) return false;
-    return pick_gw(pl, c.n_feat, whole_row) != 0;
+    return pick_cpl(pl, c.n_feat, whole_row) != 0;
 }
 
 size_t stream_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
@@ -354,11 +390,11 @@ size_t stream_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
     return (size_t)kNumSM * pl->n_hub * ld * sizeof(float) + 16;
 }
 
-template <int GW, int KPG, class Epi>
+template <int CPL, int KPG, class Epi>
 static int launch_stream(const tg_plan* pl, const StreamCall& c, StreamArgs a, const Epi& epi, cudaStream_t st) {
-    const size_t smem = stream_smem_bytes(pl, GW);
-    TG_CUDA(cudaFuncSetAttribute(stream_spmm_kernel<GW, KPG, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    a.n_slices = (int)ceil_div64(a.n_chunks4, GW);
+    const size_t smem = stream_smem_bytes(pl, CPL);
+    TG_CUDA(cudaFuncSetAttribute(stream_spmm_kernel<CPL, KPG, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a.n_slices = (int)ceil_div64(a.n_chunks4, 8 * CPL);
     int groups = kNumSM / a.n_slices;
     if (groups < 1) groups = 1;
     if (groups > a.n_chunks) groups = a.n_chunks;
@@ -366,17 +402,17 @@ static int launch_stream(const tg_plan* pl, const StreamCall& c, StreamArgs a, c
     const size_t need = (size_t)groups * pl->n_hub * a.ldp * sizeof(float);
     TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
                c.workspace_bytes, need + 16);
-    stream_spmm_kernel<GW, KPG, Epi><<<(unsigned)(groups * a.n_slices), kSThreads, smem, st>>>(a, epi);
+    stream_spmm_kernel<CPL, KPG, Epi><<<(unsigned)(groups * a.n_slices), kSThreads, smem, st>>>(a, epi);
     TG_LAUNCH_CHECK();
     return finish_dispatch(a.partials, a.ldp, groups, pl->n_hub, pl->hub_rows, a.n_chunks4, epi, st);
 }
 
 template <class Epi>
 static int run_stream(const tg_plan* pl, const StreamCall& c, const Epi& epi, bool whole_row, cudaStream_t st) {
-    const int GW = pick_gw(pl, c.n_feat, whole_row);
-    TG_REQUIRE(GW != 0, TG_ERR_UNSUPPORTED, "streaming kernel not applicable");
+    const int CPL = pick_cpl(pl, c.n_feat, whole_row);
+    TG_REQUIRE(CPL != 0, TG_ERR_UNSUPPORTED, "streaming kernel not applicable");
     StreamArgs a;
-    a.rowptr = c.rowptr; a.dent = reinterpret_cast<const int2*>(pl->colidx2);
+    a.rowptr = c.rowptr; a.rsplit = pl->rsplit; a.dent = reinterpret_cast<const int2*>(pl->colidx2);
     a.hent = reinterpret_cast<const int2*>(pl->hcol); a.htab = pl->htab; a.cdesc = pl->cdesc;
     a.hub_rows = pl->hub_rows; a.B = c.B; a.ldb = c.ldb; a.n = pl->n_rows; a.nnz = pl->nnz; a.hub_nnz = pl->hub_nnz;
     a.n_chunks4 = c.n_feat / 4; a.T = pl->chunk_rows; a.n_chunks = pl->n_chunks; a.Kh = pl->n_hub;
@@ -384,19 +420,18 @@ static int run_stream(const tg_plan* pl, const StreamCall& c, const Epi& epi, bo
     a.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(c.workspace) + 15u) & ~(uintptr_t)15u);
     a.ldp = (int64_t)((c.n_feat + 3) / 4) * 4;
     a.n_slices = a.n_groups = 0;
-    const int NG = kSThreads / GW;
-    const int kpg = (int)ceil_div64(pl->n_hub, NG);
-#define TG_STREAM_CASE(GWv)                                                         \
-    if (GW == GWv) {                                                                \
-        if (kpg <= 1) return launch_stream<GWv, 1>(pl, c, a, epi, st);              \
-        if (kpg <= 2) return launch_stream<GWv, 2>(pl, c, a, epi, st);              \
-        if (kpg <= 4) return launch_stream<GWv, 4>(pl, c, a, epi, st);              \
-        return launch_stream<GWv, 8>(pl, c, a, epi, st);                            \
+    const int kpg = (int)ceil_div64(pl->n_hub, kNG);
+#define TG_STREAM_CASE(CPLv)                                                        \
+    if (CPL == CPLv) {                                                              \
+        if (kpg <= 1) return launch_stream<CPLv, 1>(pl, c, a, epi, st);             \
+        if (kpg <= 2) return launch_stream<CPLv, 2>(pl, c, a, epi, st);             \
+        if (kpg <= 4) return launch_stream<CPLv, 4>(pl, c, a, epi, st);             \
+        return launch_stream<CPLv, 8>(pl, c, a, epi, st);                           \
     }
-    TG_STREAM_CASE(8)
-    TG_STREAM_CASE(16)
+    TG_STREAM_CASE(1)
+    TG_STREAM_CASE(2)
 #undef TG_STREAM_CASE
-    set_error("unsupported lane-group width %d", GW);
+    set_error("unsupported chunks-per-lane %d", CPL);
     return TG_ERR_UNSUPPORTED;
 }
 
@@ -408,13 +443,30 @@ int stream_spmm_loss(const tg_plan* pl, const StreamCall& c, const EpiLoss& epi,
 }
 
 // ---- plan build ------------------------------------------------------------------------------------------------------------
-__global__ void remap_cols_kernel(const int32_t* __restrict__ colidx, const float* __restrict__ vals, int64_t nnz,
-                                  const int32_t* __restrict__ slot_of, int2* __restrict__ dent) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nnz) return;
-    const int c = colidx[p];
-    const int s = slot_of[c];
-    dent[p] = make_int2(s >= 0 ? (kHubBit | s) : c, __float_as_int(vals[p]));
+// one thread per row: stable partition of the row's entries into (non-hub columns | hub columns); hub columns are
+// rewritten to their hub slot.  Within each part the ascending column order of the CSR is kept, so a document row of a
+// document-topic graph (self loop, then topics) is summed in exactly the reference's storage order.
+__global__ void reorder_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                    const float* __restrict__ vals, int64_t n, const int32_t* __restrict__ slot_of,
+                                    int32_t hub_threshold, int2* __restrict__ dent, int32_t* __restrict__ rsplit) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int s = rowptr[r], e = rowptr[r + 1];
+    if (e - s > hub_threshold) {  // hub rows are not read through this copy
+        rsplit[r] = e;
+        return;
+    }
+    int w = s;
+    for (int p = s; p < e; ++p) {
+        const int c = colidx[p];
+        if (slot_of[c] < 0) dent[w++] = make_int2(c, __float_as_int(vals[p]));
+    }
+    rsplit[r] = w;
+    for (int p = s; p < e; ++p) {
+        const int c = colidx[p];
+        const int sl = slot_of[c];
+        if (sl >= 0) dent[w++] = make_int2(sl, __float_as_int(vals[p]));
+    }
 }
 
 // one block per hub row: key = chunk * Kh + slot for each of its entries, in storage (column) order
@@ -468,8 +520,9 @@ __global__ void chunk_desc_kernel(const int32_t* __restrict__ rowptr, const int3
 
 void stream_plan_free(tg_plan* pl) {
     if (!pl) return;
-    cudaFree(pl->colidx2); cudaFree(pl->hcol); cudaFree(pl->htab); cudaFree(pl->cdesc);
+    cudaFree(pl->colidx2); cudaFree(pl->hcol); cudaFree(pl->htab); cudaFree(pl->cdesc); cudaFree(pl->rsplit);
     pl->colidx2 = nullptr; pl->hcol = nullptr; pl->hval = nullptr; pl->htab = nullptr; pl->cdesc = nullptr;
+    pl->rsplit = nullptr;
     pl->stream_ok = false;
 }
 
@@ -481,8 +534,8 @@ int stream_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         return TG_OK;
     const int64_t n = pl->n_rows;
     const int Kh = pl->n_hub;
-    int T = env_int("TG_STREAM_CHUNK", 256);
-    if (T != 128 && T != 256 && T != 512) T = 256;
+    int T = env_int("TG_STREAM_CHUNK", 128);
+    if (T < 32 || T > 1024 || (T % 32) != 0) T = 128;
     const int n_chunks = (int)ceil_div64(n, T);
     if ((uint64_t)n_chunks * (uint64_t)Kh >= 0xFFFFFFFFull) return TG_OK;
     // only worth it when the hub rows carry a real share of the entries
@@ -521,8 +574,9 @@ int stream_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     // +2 entries of padding so that the kernel's aligned 16-byte pair copies never leave the allocation
     TG_TRY(cudaMalloc((void**)&pl->colidx2, ((size_t)pl->nnz + 2) * sizeof(int2)));
     TG_TRY(cudaMemsetAsync(pl->colidx2, 0, ((size_t)pl->nnz + 2) * sizeof(int2), st));
-    remap_cols_kernel<<<(unsigned)ceil_div64(pl->nnz, 256), 256, 0, st>>>(colidx, vals, pl->nnz, d_slot,
-                                                                          reinterpret_cast<int2*>(pl->colidx2));
+    TG_TRY(cudaMalloc((void**)&pl->rsplit, (size_t)n * sizeof(int32_t)));
+    reorder_rows_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(rowptr, colidx, vals, n, d_slot, pl->hub_threshold,
+                                                                      reinterpret_cast<int2*>(pl->colidx2), pl->rsplit);
     TG_TRY(cudaGetLastError());
     TG_TRY(cudaMalloc((void**)&keys_a, (size_t)hub_nnz * sizeof(uint32_t)));
     TG_TRY(cudaMalloc((void**)&keys_b, (size_t)hub_nnz * sizeof(uint32_t)));
@@ -554,10 +608,13 @@ int stream_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     cudaFree(d_slot); cudaFree(d_ofs); cudaFree(keys_a); cudaFree(keys_b); cudaFree(src_a); cudaFree(src_b); cudaFree(tmp);
     pl->chunk_rows = T;
     pl->n_chunks = n_chunks;
-    pl->cap_doc = pl->cap_hub = 12 * T;
+    // staged entry windows: average occupancy of a chunk plus slack (rows beyond the window take the L2 path)
+    const int64_t avg_doc = ceil_div64(pl->nnz - hub_nnz, n_chunks), avg_hub = ceil_div64(hub_nnz, n_chunks);
+    pl->cap_doc = (int32_t)(((avg_doc + avg_doc / 4 + 64) + 1) & ~(int64_t)1);
+    pl->cap_hub = (int32_t)(((avg_hub + avg_hub / 4 + 64) + 1) & ~(int64_t)1);
     pl->stream_ok = true;
     // the kernel must fit at least the narrow configuration
-    if (stream_smem_bytes(pl, 8) > kSmemBudget) stream_plan_free(pl);
+    if (stream_smem_bytes(pl, 1) > kSmemBudget) stream_plan_free(pl);
     return TG_OK;
 }
 

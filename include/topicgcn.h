@@ -80,7 +80,7 @@ typedef struct tg_plan tg_plan;
  * document-topic-topic graphs), the plan also carries the "column-chunk streaming" layout (tg_stream.cu): a
  * chunk-major copy of the hub rows' entries and an (index, value) interleaved copy of all entries.  The plan
  * therefore SNAPSHOTS the values: rebuild it when `vals` change.  colidx/vals may be NULL (no streaming layout).
- * Environment knobs read at creation: TG_STREAM=0 disables it, TG_STREAM_CHUNK={128,256,512} nodes per chunk.
+ * Environment knobs read at creation: TG_STREAM=0 disables it, TG_STREAM_CHUNK=nodes per chunk (multiple of 32, default 128).
  * ---------------------------------------------------------------------------------------------- */
 int tg_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* vals, int64_t n_rows,
                    int64_t n_cols, int64_t nnz, int32_t hub_threshold /*<=0: default*/,

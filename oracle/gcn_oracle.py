@@ -231,7 +231,7 @@ def philox_keep_mask(n_rows: int, n_feat: int, p: float, seed: int, offset: int)
     row = np.repeat(np.arange(n_rows, dtype=np.uint64), n_feat)
     col = np.tile(np.arange(n_feat, dtype=np.uint64), n_rows)
     q = col >> np.uint64(2)
-    slot, j, half = q & np.uint64(31), q >> np.uint64(6), (q >> np.uint64(5)) & np.uint64(1)
+    slot, j, half = q & np.uint64(7), q >> np.uint64(4), (q >> np.uint64(3)) & np.uint64(1)
     seed, offset = int(seed) & (2**64 - 1), int(offset) & (2**64 - 1)
     k0 = (seed & 0xFFFFFFFF) ^ (offset >> 32)
     k1 = seed >> 32
