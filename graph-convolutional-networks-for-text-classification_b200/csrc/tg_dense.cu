@@ -16,86 +16,96 @@ namespace tg {
 
 // ------------------------------------------------------------------------------------------------------------
 // C[n x c] = A[n x h] * W[h x c]     (c <= 32 per pass, wider c loops column blocks on the host side)
-// Block = 128 threads, 512 rows; thread t owns rows {t, t+128, t+256, t+384} and all CP columns.
-// A is staged [512 x 32] with row stride 33 (conflict-free both for the float4->scalar stores and the
-// per-row reads), W chunk [32 x CP] is read by every lane at the same address (broadcast).
+// Thread t owns RT rows {t, t + 256, ...} of the block and all CP = 4*NC4 columns: RT*CP accumulators in registers.
+// Each thread streams its own rows with 128-bit loads (8 k-steps per 128-byte line, the line is consumed while it
+// is L1 resident), the next k-block's loads are issued before the current block's FMAs (register double buffer);
+// W (<= 32 KB) is staged once per CTA in shared memory and read at a warp-uniform address (broadcast).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kNnThreads = 128;
-constexpr int kNnRT = 4;
+constexpr int kNnThreads = 256;
+constexpr int kNnRT = 2;
 constexpr int kNnRows = kNnThreads * kNnRT;
-constexpr int kNnKC = 32;
-constexpr int kNnAStride = kNnKC + 1;
 
-template <int NC4>
+template <int NC4, bool VEC_A>
 __global__ void __launch_bounds__(kNnThreads) dense_nn_kernel(const float* __restrict__ A, int64_t lda,
                                                               const float* __restrict__ W, int64_t ldw,
                                                               float* __restrict__ C, int64_t ldc, int64_t n,
                                                               int h, int c) {
     constexpr int CP = NC4 * 4;
-    extern __shared__ float smem[];
-    float* As = smem;                         // [kNnRows][kNnAStride]
-    float* Ws = smem + kNnRows * kNnAStride;  // [kNnKC][CP]
+    extern __shared__ __align__(16) float Ws[];  // [h4][CP], h4 = h rounded up to 4, zero padded
     const int t = threadIdx.x;
-    const int64_t row0 = (int64_t)blockIdx.x * kNnRows;
-
+    const int h4 = (h + 3) & ~3;
+    for (int idx = t; idx < h4 * CP; idx += kNnThreads) {
+        const int kk = idx / CP, j = idx % CP;
+        Ws[idx] = (kk < h && j < c) ? __ldg(W + (int64_t)kk * ldw + j) : 0.f;
+    }
+    __syncthreads();
+    const int64_t row0 = (int64_t)blockIdx.x * kNnRows + t;
+    const float* ap[kNnRT];
+    bool live[kNnRT];
+#pragma unroll
+    for (int r = 0; r < kNnRT; ++r) {
+        const int64_t row = row0 + (int64_t)r * kNnThreads;
+        live[r] = row < n;
+        ap[r] = A + (live[r] ? row : 0) * lda;
+    }
     float acc[kNnRT][CP];
 #pragma unroll
     for (int r = 0; r < kNnRT; ++r)
 #pragma unroll
         for (int j = 0; j < CP; ++j) acc[r][j] = 0.f;
 
-    const bool a_vec = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0);
-    for (int k0 = 0; k0 < h; k0 += kNnKC) {
-        __syncthreads();
-        // stage A[row0 .. row0+512) x [k0, k0+32): 8 lanes per row, one float4 each
-        for (int idx = t; idx < kNnRows * (kNnKC / 4); idx += kNnThreads) {
-            const int r = idx >> 3, q = idx & 7;
-            const int64_t row = row0 + r;
-            const int k = k0 + q * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < n) {
-                const float* src = A + row * lda + k;
-                if (a_vec && k + 3 < h) {
-                    v = ldg_f4_stream(src);
-                } else {
-                    if (k + 0 < h) v.x = __ldg(src + 0);
-                    if (k + 1 < h) v.y = __ldg(src + 1);
-                    if (k + 2 < h) v.z = __ldg(src + 2);
-                    if (k + 3 < h) v.w = __ldg(src + 3);
-                }
-            }
-            float* dst = As + r * kNnAStride + q * 4;
-            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-        }
-        for (int idx = t; idx < kNnKC * CP; idx += kNnThreads) {
-            const int kk = idx / CP, j = idx % CP;
-            Ws[idx] = (k0 + kk < h && j < c) ? __ldg(W + (int64_t)(k0 + kk) * ldw + j) : 0.f;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int kk = 0; kk < kNnKC; ++kk) {
-            float a[kNnRT];
+    auto load4 = [&](int r, int k) -> float4 {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!live[r]) return v;
+        if (VEC_A && k + 3 < h) return __ldg(reinterpret_cast<const float4*>(ap[r] + k));
+        if (k + 0 < h) v.x = __ldg(ap[r] + k + 0);
+        if (k + 1 < h) v.y = __ldg(ap[r] + k + 1);
+        if (k + 2 < h) v.z = __ldg(ap[r] + k + 2);
+        if (k + 3 < h) v.w = __ldg(ap[r] + k + 3);
+        return v;
+    };
+    constexpr int KB = 2;  // float4 k-steps per register buffer
+    float4 cur[kNnRT][KB], nxt[kNnRT][KB];
 #pragma unroll
-            for (int r = 0; r < kNnRT; ++r) a[r] = As[(t + r * kNnThreads) * kNnAStride + kk];
+    for (int r = 0; r < kNnRT; ++r)
 #pragma unroll
-            for (int q = 0; q < NC4; ++q) {
-                const float4 w = *reinterpret_cast<const float4*>(Ws + kk * CP + q * 4);
+        for (int u = 0; u < KB; ++u) cur[r][u] = load4(r, u * 4);
+    for (int k0 = 0; k0 < h4; k0 += 4 * KB) {
 #pragma unroll
-                for (int r = 0; r < kNnRT; ++r) {
-                    acc[r][q * 4 + 0] = fmaf(a[r], w.x, acc[r][q * 4 + 0]);
-                    acc[r][q * 4 + 1] = fmaf(a[r], w.y, acc[r][q * 4 + 1]);
-                    acc[r][q * 4 + 2] = fmaf(a[r], w.z, acc[r][q * 4 + 2]);
-                    acc[r][q * 4 + 3] = fmaf(a[r], w.w, acc[r][q * 4 + 3]);
+        for (int r = 0; r < kNnRT; ++r)
+#pragma unroll
+            for (int u = 0; u < KB; ++u) nxt[r][u] = load4(r, k0 + 4 * KB + u * 4);
+#pragma unroll
+        for (int u = 0; u < KB; ++u) {
+            const int kb = k0 + u * 4;
+            if (kb < h4) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                    for (int q = 0; q < NC4; ++q) {
+                        const float4 w = *reinterpret_cast<const float4*>(Ws + (kb + kk) * CP + q * 4);
+#pragma unroll
+                        for (int r = 0; r < kNnRT; ++r) {
+                            const float av = kk == 0 ? cur[r][u].x : kk == 1 ? cur[r][u].y : kk == 2 ? cur[r][u].z : cur[r][u].w;
+                            acc[r][q * 4 + 0] = fmaf(av, w.x, acc[r][q * 4 + 0]);
+                            acc[r][q * 4 + 1] = fmaf(av, w.y, acc[r][q * 4 + 1]);
+                            acc[r][q * 4 + 2] = fmaf(av, w.z, acc[r][q * 4 + 2]);
+                            acc[r][q * 4 + 3] = fmaf(av, w.w, acc[r][q * 4 + 3]);
+                        }
+                    }
                 }
             }
         }
+#pragma unroll
+        for (int r = 0; r < kNnRT; ++r)
+#pragma unroll
+            for (int u = 0; u < KB; ++u) cur[r][u] = nxt[r][u];
     }
     const bool c_vec = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0) && (c % 4 == 0);
 #pragma unroll
     for (int r = 0; r < kNnRT; ++r) {
-        const int64_t row = row0 + t + r * kNnThreads;
-        if (row >= n) continue;
-        float* dst = C + row * ldc;
+        if (!live[r]) continue;
+        float* dst = C + (row0 + (int64_t)r * kNnThreads) * ldc;
         if (c_vec) {
 #pragma unroll
             for (int q = 0; q < NC4; ++q)
@@ -111,9 +121,18 @@ __global__ void __launch_bounds__(kNnThreads) dense_nn_kernel(const float* __res
 template <int NC4>
 static int launch_dense_nn(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
                            int64_t n, int h, int c, cudaStream_t st) {
-    const size_t smem = (size_t)(kNnRows * kNnAStride + kNnKC * NC4 * 4) * sizeof(float);
-    TG_CUDA(cudaFuncSetAttribute(dense_nn_kernel<NC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dense_nn_kernel<NC4><<<(unsigned)ceil_div64(n, kNnRows), kNnThreads, smem, st>>>(A, lda, W, ldw, C, ldc, n, h, c);
+    const int h4 = (h + 3) & ~3;
+    const size_t smem = (size_t)h4 * NC4 * 4 * sizeof(float);
+    TG_REQUIRE(smem <= 200 * 1024, TG_ERR_UNSUPPORTED, "inner dimension %d too large for the skinny product", h);
+    const bool vec_a = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0);
+    const unsigned grid = (unsigned)ceil_div64(n, kNnRows);
+    if (vec_a) {
+        TG_CUDA(cudaFuncSetAttribute(dense_nn_kernel<NC4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense_nn_kernel<NC4, true><<<grid, kNnThreads, smem, st>>>(A, lda, W, ldw, C, ldc, n, h, c);
+    } else {
+        TG_CUDA(cudaFuncSetAttribute(dense_nn_kernel<NC4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense_nn_kernel<NC4, false><<<grid, kNnThreads, smem, st>>>(A, lda, W, ldw, C, ldc, n, h, c);
+    }
     TG_LAUNCH_CHECK();
     return TG_OK;
 }
@@ -122,11 +141,12 @@ static int launch_dense_nn(const float* A, int64_t lda, const float* W, int64_t 
 // Fused hidden-layer backward.  One thread per hidden unit j: W2[j,:] and the dW2[j,:] accumulators live in
 // registers; rows are streamed, the dS2 row is read from a small shared tile at a warp-uniform address.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kHbTile = 32;        // rows per staged dS2 tile
-constexpr int kHbMaxGrid = 2 * kNumSM;
+constexpr int kHbTile = 64;        // rows per staged dS2 tile
+constexpr int kHbBatch = 8;        // H1 rows in flight per thread
+constexpr int kHbMaxGrid = 3 * kNumSM;  // 80 registers x 256 threads: three CTAs per SM
 
 template <int NC4, int TB>
-__global__ void __launch_bounds__(TB) hidden_bwd_kernel(const float* __restrict__ H1, int64_t ldh,
+__global__ void __launch_bounds__(TB, (TB == 256 ? 3 : 1)) hidden_bwd_kernel(const float* __restrict__ H1, int64_t ldh,
                                                           const float* __restrict__ dS2, int64_t ldd,
                                                           const float* __restrict__ W2, int64_t ldw, float scale,
                                                           float* __restrict__ dZ1, int64_t ldz,
@@ -154,30 +174,37 @@ __global__ void __launch_bounds__(TB) hidden_bwd_kernel(const float* __restrict_
         }
         __syncthreads();
         if (!live) continue;
-        for (int rb = 0; rb < tile; rb += 4) {
-            float a[4];
+        // running pointers (one 64-bit add per row) instead of re-deriving row*ld+j for every access
+        const float* hp = H1 + r0 * ldh + j;
+        float* zp = dZ1 + r0 * ldz + j;
+        for (int rb = 0; rb < tile; rb += kHbBatch) {
+            float a[kHbBatch];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) a[u] = (rb + u < tile) ? __ldg(H1 + (r0 + rb + u) * ldh + j) : 0.f;
+            for (int u = 0; u < kHbBatch; ++u) a[u] = (rb + u < tile) ? __ldg(hp + (int64_t)u * ldh) : 0.f;
+            const float* dsr = ds + rb * CP;
+            // all kHbBatch rows are computed unconditionally (rows past the tile read zeros), so the compiler can
+            // interleave their independent FMA chains; dh is kept as four partial sums to shorten the dependent chain
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (rb + u >= tile) break;
-                float dh = 0.f;
+            for (int u = 0; u < kHbBatch; ++u) {
+                float dh0 = 0.f, dh1 = 0.f, dh2 = 0.f, dh3 = 0.f;
 #pragma unroll
                 for (int q4 = 0; q4 < NC4; ++q4) {
-                    const float4 d = *reinterpret_cast<const float4*>(ds + (rb + u) * CP + q4 * 4);
-                    dh = fmaf(d.x, w[q4 * 4 + 0], dh);
-                    dh = fmaf(d.y, w[q4 * 4 + 1], dh);
-                    dh = fmaf(d.z, w[q4 * 4 + 2], dh);
-                    dh = fmaf(d.w, w[q4 * 4 + 3], dh);
+                    const float4 d = *reinterpret_cast<const float4*>(dsr + u * CP + q4 * 4);
+                    dh0 = fmaf(d.x, w[q4 * 4 + 0], dh0);
+                    dh1 = fmaf(d.y, w[q4 * 4 + 1], dh1);
+                    dh2 = fmaf(d.z, w[q4 * 4 + 2], dh2);
+                    dh3 = fmaf(d.w, w[q4 * 4 + 3], dh3);
                     gw[q4 * 4 + 0] = fmaf(a[u], d.x, gw[q4 * 4 + 0]);
                     gw[q4 * 4 + 1] = fmaf(a[u], d.y, gw[q4 * 4 + 1]);
                     gw[q4 * 4 + 2] = fmaf(a[u], d.z, gw[q4 * 4 + 2]);
                     gw[q4 * 4 + 3] = fmaf(a[u], d.w, gw[q4 * 4 + 3]);
                 }
-                const float dz = (a[u] > 0.f) ? dh * scale : 0.f;
-                dZ1[(r0 + rb + u) * ldz + j] = dz;
+                const float dz = (a[u] > 0.f) ? ((dh0 + dh1) + (dh2 + dh3)) * scale : 0.f;
+                if (rb + u < tile) zp[(int64_t)u * ldz] = dz;
                 gb += dz;
             }
+            hp += (int64_t)kHbBatch * ldh;
+            zp += (int64_t)kHbBatch * ldz;
         }
     }
     if (live) {
@@ -204,7 +231,7 @@ template <int NC4>
 static int launch_hidden_bwd(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw,
                              float scale, float* dZ1, int64_t ldz, float* dW2, float* db1, float* partials, int64_t n,
                              int h, int c, cudaStream_t st) {
-    int64_t grid = ceil_div64(n, 4 * kHbTile);
+    int64_t grid = ceil_div64(n, 2 * kHbTile);
     if (grid > kHbMaxGrid) grid = kHbMaxGrid;
     if (grid < 1) grid = 1;
     int64_t rpb = ceil_div64(n, grid);
