@@ -254,10 +254,11 @@ def run_ours(args):
     else:
         from topicgcn_b200 import shard
         sg = shard.make_sharded_config(name, rank=rank, world=world, device=dev, seed=0)
-        torch.manual_seed(0)
+        torch.manual_seed(rank)
         model = shard.ShardedGCN(sg, hidden, n_class, 0.5).to(dev)
+        model.sync_replicated()
         model.train()
-        csr = sg.csr_doc
+        csr = shard._csr(sg)
         labels_host = sg.labels.cpu().pin_memory()
         index_host = sg.train_idx.cpu().pin_memory()
         row_label = ops.make_row_label(sg.n_local, sg.labels, sg.train_idx)

@@ -85,10 +85,19 @@ struct EpiStore {
     float scale;
     uint64_t seed, offset;
     int32_t n_feat;
+    int64_t raw_row_begin;  // rows >= raw_row_begin are stored as plain sums (document-sharded mode), INT64_MAX = none
 
     template <int VEC, int G, int CPL>
     __device__ __forceinline__ void apply(int64_t row, int gl, unsigned gmask, int n_chunks,
                                           Chunk<VEC> (&acc)[CPL]) const {
+        if (row >= raw_row_begin) {
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int chunk = gl + i * G;
+                if (chunk < n_chunks) chunk_st<VEC>(Y + row * ldy + chunk * VEC, acc[i]);
+            }
+            return;
+        }
         Philox4 rnd = Philox4{0, 0, 0, 0};
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {

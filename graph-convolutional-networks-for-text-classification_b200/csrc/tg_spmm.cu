@@ -305,6 +305,7 @@ int tg_spmm_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colid
     EpiStore epi{};
     epi.Y = Y; epi.ldy = ldy; epi.bias = bias; epi.relu = 0; epi.drop_mode = 0; epi.keep_mask = nullptr;
     epi.keep_thr = 0; epi.scale = 1.f; epi.seed = 0; epi.offset = 0; epi.n_feat = n_feat;
+    epi.raw_row_begin = INT64_MAX;
     const bool ok4 = (ldy % 4 == 0) && aligned16(Y) && (!bias || aligned16(bias));
     return run_spmm(plan, rowptr, colidx, vals, B, ldb, n_feat, ok4, epi, workspace, workspace_bytes,
                     as_stream(stream));
@@ -312,8 +313,8 @@ int tg_spmm_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colid
 
 int tg_gc1_fwd_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                    const float* S, int64_t lds, const float* bias, float* H1, int64_t ldh, int32_t n_feat, float p,
-                   int32_t training, const uint8_t* keep_mask, uint64_t seed, uint64_t offset, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+                   int32_t training, const uint8_t* keep_mask, uint64_t seed, uint64_t offset, int64_t raw_row_begin,
+                   void* workspace, size_t workspace_bytes, void* stream) {
     using namespace tg;
     TG_REQUIRE(H1, TG_ERR_INVALID_ARG, "null output");
     TG_REQUIRE(ldh >= n_feat, TG_ERR_INVALID_ARG, "ldh < n_feat");
@@ -321,6 +322,7 @@ int tg_gc1_fwd_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* co
     EpiStore epi{};
     epi.Y = H1; epi.ldy = ldh; epi.bias = bias; epi.relu = 1; epi.n_feat = n_feat;
     epi.seed = seed; epi.offset = offset; epi.keep_mask = keep_mask;
+    epi.raw_row_begin = raw_row_begin < 0 ? INT64_MAX : raw_row_begin;
     const bool drop = training && p > 0.f;
     epi.drop_mode = !drop ? 0 : (keep_mask ? 2 : 1);
     epi.keep_thr = dropout_keep_threshold(p);

@@ -106,8 +106,8 @@ def spmm(csr: DeviceCSR, B: torch.Tensor, bias: Optional[torch.Tensor] = None,
 
 def gc1_forward(csr: DeviceCSR, S: torch.Tensor, bias: Optional[torch.Tensor], p: float, training: bool,
                 keep_mask: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """H1 = dropout(relu(A @ S + b1)): tg_gc1_fwd_f32."""
+                out: Optional[torch.Tensor] = None, raw_row_begin: int = -1) -> torch.Tensor:
+    """H1 = dropout(relu(A @ S + b1)): tg_gc1_fwd_f32.  Rows >= raw_row_begin (if >= 0) get the plain sums."""
     S = _dense2d(S, "S")
     if S.shape[0] != csr.n_cols:
         raise N.TopicGCNError(f"shape mismatch: A is {csr.n_rows}x{csr.n_cols}, S has {S.shape[0]} rows")
@@ -123,8 +123,8 @@ def gc1_forward(csr: DeviceCSR, S: torch.Tensor, bias: Optional[torch.Tensor], p
     with torch.cuda.device(S.device), _call("gc1_fwd", 1, n_feat=F, csr=csr):
         N.check(N.lib().tg_gc1_fwd_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(S), _ld(S),
                                        N.ptr(bias), N.ptr(out), _ld(out), F, float(p), int(bool(training)),
-                                       N.ptr(keep_mask), int(seed) & (2**64 - 1), int(offset) & (2**64 - 1), ws,
-                                       ws_bytes, _stream()), "tg_gc1_fwd_f32")
+                                       N.ptr(keep_mask), int(seed) & (2**64 - 1), int(offset) & (2**64 - 1),
+                                       int(raw_row_begin), ws, ws_bytes, _stream()), "tg_gc1_fwd_f32")
     return out
 
 
@@ -230,7 +230,8 @@ FUSED_BWD_MAX_CLASSES = 32
 FUSED_BWD_MAX_HIDDEN = 1024
 
 
-def hidden_backward(H1: torch.Tensor, dS2: torch.Tensor, W2: torch.Tensor, scale: float):
+def hidden_backward(H1: torch.Tensor, dS2: torch.Tensor, W2: torch.Tensor, scale: float,
+                    out_dZ1: Optional[torch.Tensor] = None):
     """(dZ1, dW2, db1) — fused backward of S2 = H1 @ W2, dropout, relu, +b1: tg_hidden_bwd_f32.
     Class counts above 32 (or hidden widths above 1024) are plain library GEMMs (cuBLAS via torch.mm) followed by the
     elementwise/colsum kernels."""
@@ -242,15 +243,19 @@ def hidden_backward(H1: torch.Tensor, dS2: torch.Tensor, W2: torch.Tensor, scale
         dH1 = torch.mm(dS2, W2.t())
         dW2 = torch.mm(H1.t(), dS2)
         dZ1 = relu_dropout_backward(H1, dH1, scale)
+        if out_dZ1 is not None:
+            out_dZ1.copy_(dZ1)
+            dZ1 = out_dZ1
         return dZ1, dW2, colsum(dZ1)
     dev = H1.device
-    dZ1 = torch.empty((n, h), dtype=torch.float32, device=dev)
+    dZ1 = out_dZ1 if out_dZ1 is not None else torch.empty((n, h), dtype=torch.float32, device=dev)
     dW2 = torch.empty((h, c), dtype=torch.float32, device=dev)
     db1 = torch.empty(h, dtype=torch.float32, device=dev)
     scratch = torch.empty(int(N.lib().tg_hidden_bwd_scratch_floats(n, h, c)), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev), _call("hidden_bwd", 2, n=n, h=h, c=c):
         N.check(N.lib().tg_hidden_bwd_f32(N.ptr(H1), _ld(H1), N.ptr(dS2), _ld(dS2), N.ptr(W2), _ld(W2), float(scale),
-                                          N.ptr(dZ1), h, N.ptr(dW2), N.ptr(db1), N.ptr(scratch), n, h, c, _stream()),
+                                          N.ptr(dZ1), _ld(dZ1), N.ptr(dW2), N.ptr(db1), N.ptr(scratch), n, h, c,
+                                          _stream()),
                 "tg_hidden_bwd_f32")
     return dZ1, dW2, db1
 

@@ -1,0 +1,361 @@
+"""Document-row sharding of the doc-topic-topic graph over G GPUs (one process per GPU, NCCL over NVLink).
+
+Partition.  Documents are row-sharded contiguously: rank g owns D_g documents together with their rows
+of Â, W1 (featureless), H1 and their labels.  The K topic nodes are REPLICATED: every rank keeps the K topic rows of
+every dense operand, and a local square adjacency over its (D_g + K) nodes:
+
+    document rows : complete        (self loop + topic columns: everything a document row touches is local)
+    topic rows    : local doc columns only, plus this rank's column slice of the K x K topic-topic block
+                    (the slices tile the block, so summing the ranks' partial topic rows gives the full rows)
+
+so  Y = Â B  on rank g is the local SpMM followed by ONE all-reduce (sum) of the K x F topic rows of Y — the only
+collective of a layer.  Â is symmetric, hence the backward products Â^T dZ are the same operation.  Replicated
+parameters (W2, b1, b2) get one packed all-reduce of their gradients (+ the loss) per step; W1 is row-sharded with
+the documents and its K topic rows stay bit-identical on all ranks because they only ever see all-reduced values.
+
+The local SpMM runs the fused kernels of the single-GPU path; rows >= D_g (the topic rows) are stored raw
+(`raw_row_begin`), all-reduced, and then given their epilogue.  The reference has nothing comparable (single process,
+single device: trainer.py:425); the numerical contract is that the sharded result equals the single-GPU result up to
+the summation grouping of the topic rows.
+
+`Comm` abstracts the collective: `TorchDistComm` (torch.distributed, NCCL on GPUs / gloo in the CPU tests) and
+`ThreadComm` (ranks emulated as threads of one process sharing one device — used to test the sharded step on a
+single GPU without waiting kernels).
+"""
+from __future__ import annotations
+
+import threading
+from dataclasses import dataclass
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+from . import graphgen
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# communicators
+# ---------------------------------------------------------------------------------------------------------------
+class TorchDistComm:
+    """torch.distributed process group (NCCL or gloo)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def broadcast(self, t: torch.Tensor, src: int = 0) -> torch.Tensor:
+        self.dist.broadcast(t, src=src, group=self.group)
+        return t
+
+
+class SingleComm:
+    rank, world = 0, 1
+
+    def all_reduce(self, t):
+        return t
+
+    def broadcast(self, t, src=0):
+        return t
+
+
+class ThreadComm:
+    """Ranks emulated as threads of ONE process on one device: an all-reduce is 'everybody deposits, barrier, everybody
+    adds the deposits in rank order, barrier'.  All work is enqueued on the same CUDA stream, so stream order makes the
+    deposits visible to the sums; no kernel ever waits on another."""
+
+    class _Shared:
+        def __init__(self, world):
+            self.world, self.slots, self.barrier = world, [None] * world, threading.Barrier(world)
+
+    def __init__(self, shared: "_Shared", rank: int):
+        self.s, self.rank, self.world = shared, rank, shared.world
+
+    @classmethod
+    def create(cls, world: int) -> List["ThreadComm"]:
+        sh = cls._Shared(world)
+        return [cls(sh, r) for r in range(world)]
+
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        self.s.slots[self.rank] = t.clone()
+        self.s.barrier.wait()
+        acc = self.s.slots[0].clone()
+        for r in range(1, self.world):
+            acc += self.s.slots[r]
+        self.s.barrier.wait()
+        t.copy_(acc)
+        return t
+
+    def broadcast(self, t: torch.Tensor, src: int = 0) -> torch.Tensor:
+        if self.rank == src:
+            self.s.slots[src] = t.clone()
+        self.s.barrier.wait()
+        t.copy_(self.s.slots[src])
+        self.s.barrier.wait()
+        return t
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# local graph of one rank
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class LocalGraph:
+    """Row-major COO of the rank-local square adjacency over (local documents | all topics)."""
+    rank: int
+    world: int
+    n_docs_local: int
+    n_topics: int
+    rows: torch.Tensor
+    cols: torch.Tensor
+    vals: torch.Tensor
+    n_docs_global: int = 0
+    nnz_global: int = 0
+    labels: Optional[torch.Tensor] = None
+    train_idx: Optional[torch.Tensor] = None
+    n_train_global: int = 0
+    n_class: int = 0
+    csr: object = None  # DeviceCSR, built lazily on CUDA
+
+    @property
+    def n_local(self) -> int:
+        return self.n_docs_local + self.n_topics
+
+    @property
+    def nnz(self) -> int:
+        return int(self.rows.numel())
+
+
+def topic_slice(n_topics: int, rank: int, world: int):
+    """Column slice [lo, hi) of the topic-topic block that rank owns."""
+    return (rank * n_topics) // world, ((rank + 1) * n_topics) // world
+
+
+def build_local_graph(doc: torch.Tensor, topic: torch.Tensor, w: torch.Tensor, tt_i: torch.Tensor, tt_j: torch.Tensor,
+                      tt_s: torch.Tensor, n_docs_local: int, n_topics: int, comm) -> LocalGraph:
+    """Normalise (reference utils.py:206-213 arithmetic, float64) and lay out one rank's local adjacency.
+
+    doc/topic/w : this rank's document-topic edges (local document index, topic index, fp32 weight)
+    tt_*        : ALL topic-topic edges i<j with fp32 similarity (identical on every rank)
+    The topic degrees need every rank's documents: one float64 all-reduce of K sums (exact in float64, so the result
+    does not depend on the reduction order)."""
+    dev = doc.device
+    D, K = int(n_docs_local), int(n_topics)
+    w64 = w.to(torch.float64)
+    deg_doc = torch.ones(D, dtype=torch.float64, device=dev).index_add_(0, doc, w64)
+    deg_top = torch.zeros(K, dtype=torch.float64, device=dev).index_add_(0, topic, w64)
+    comm.all_reduce(deg_top)
+    s64 = tt_s.to(torch.float64)
+    deg_top = deg_top + 1.0
+    deg_top.index_add_(0, tt_i, s64).index_add_(0, tt_j, s64)
+    with np.errstate(divide="ignore"):
+        dd = np.power(deg_doc.cpu().numpy(), -0.5)  # utils.py:210 (same libm call as the reference)
+        dt = np.power(deg_top.cpu().numpy(), -0.5)
+    dd[np.isinf(dd)] = 0.0
+    dt[np.isinf(dt)] = 0.0
+    dd, dt = torch.from_numpy(dd).to(dev), torch.from_numpy(dt).to(dev)
+    lo, hi = topic_slice(K, comm.rank, comm.world)
+    ar_d = torch.arange(D, dtype=torch.int64, device=dev)
+    # Â[i,j] = (Ã[j,i] * d_i) * d_j
+    r = [ar_d, doc, topic + D]
+    c = [ar_d, topic + D, doc]
+    v = [(dd * dd), (w64 * dd[doc]) * dt[topic], (w64 * dt[topic]) * dd[doc]]
+    # this rank's column slice of the topic-topic block (both directions) and of the topic self loops
+    for a, b in ((tt_i, tt_j), (tt_j, tt_i)):
+        keep = (b >= lo) & (b < hi)
+        r.append(a[keep] + D)
+        c.append(b[keep] + D)
+        v.append((s64[keep] * dt[a[keep]]) * dt[b[keep]])
+    ks = torch.arange(lo, hi, dtype=torch.int64, device=dev)
+    r.append(ks + D)
+    c.append(ks + D)
+    v.append(dt[ks] * dt[ks])
+    rows, cols, vals = torch.cat(r), torch.cat(c), torch.cat(v).to(torch.float32)
+    order = torch.argsort(rows * (D + K) + cols)
+    return LocalGraph(comm.rank, comm.world, D, K, rows[order], cols[order], vals[order])
+
+
+def make_sharded_config(name: str, rank: int, world: int, device, seed: int = 0, comm=None,
+                        docs_per_rank: Optional[int] = None) -> LocalGraph:
+    """One rank's shard of a named synthetic configuration: `docs_per_rank` documents (default: the configuration's
+    document count, i.e. weak scaling) generated from a rank-specific seed, topics and topic-topic edges from the shared
+    seed."""
+    builder, kw, hidden, n_class = graphgen.CONFIGS[name]
+    if builder is not graphgen.doc_topic_topic_graph:
+        raise ValueError(f"{name} is not a document-topic-topic configuration")
+    kw = dict(kw)
+    D = int(docs_per_rank or kw["n_docs"])
+    K = int(kw["n_topics"])
+    dev = torch.device(device)
+    comm = comm or (TorchDistComm() if world > 1 else SingleComm())
+    g_shared = torch.Generator(device=dev).manual_seed(seed)
+    tt_i, tt_j, tt_s = graphgen.topic_topic_edges(K, g_shared, dev, kw["dense_topics"])
+    g_rank = torch.Generator(device=dev).manual_seed(seed * 1000 + 17 + rank)
+    d, t, w = graphgen.doc_topic_edges(D, K, kw["deg_lo"], kw["deg_hi"], g_rank, dev)
+    lg = build_local_graph(d, t, w, tt_i, tt_j, tt_s, D, K, comm)
+    labels, tr, _va, _te = graphgen._labels_and_split(D, n_class, g_rank, dev)
+    lg.labels, lg.train_idx, lg.n_class = labels, tr, n_class
+    cnt = torch.tensor([float(D), float(tr.numel()), float(2 * d.numel() + D)], dtype=torch.float64, device=dev)
+    comm.all_reduce(cnt)
+    lg.n_docs_global, lg.n_train_global = int(cnt[0].item()), int(cnt[1].item())
+    lg.nnz_global = int(cnt[2].item()) + 2 * int(tt_i.numel()) + K
+    return lg
+
+
+def shard_edges(n_docs: int, world: int):
+    """Contiguous document ranges [lo, hi) per rank."""
+    return [((r * n_docs) // world, ((r + 1) * n_docs) // world) for r in range(world)]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the sharded SpMM and the sharded train step (CUDA)
+# ---------------------------------------------------------------------------------------------------------------
+def _csr(lg: LocalGraph):
+    if lg.csr is None:
+        from .csr import DeviceCSR
+        lg.csr = DeviceCSR.from_coo(lg.rows, lg.cols, lg.vals, lg.n_local, lg.n_local, symmetric=True)
+    return lg.csr
+
+
+def sharded_spmm(lg: LocalGraph, B: torch.Tensor, comm, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Y = Â B over the sharded graph: local SpMM + all-reduce of the K topic rows."""
+    from . import ops
+    Y = ops.spmm(_csr(lg), B, None, out=out)
+    comm.all_reduce(Y[lg.n_docs_local:])
+    return Y
+
+
+class ShardedGCN(torch.nn.Module):
+    """Featureless 2-layer GCN on one rank's shard.  Parameters: gc1.weight [D_g + K, nhid] (document rows are this
+    rank's, topic rows replicated), gc1.bias, gc2.weight, gc2.bias (replicated).  Same init distribution as the
+    reference layers (layer.py:67-82); replicated tensors are broadcast from rank 0 so all ranks start identical."""
+
+    def __init__(self, lg: LocalGraph, nhid: int, nclass: int, dropout: float, comm=None):
+        super().__init__()
+        from .layer import GraphConvolution
+        self.lg = lg
+        self.comm = comm or (TorchDistComm() if lg.world > 1 else SingleComm())
+        self.gc1 = GraphConvolution(lg.n_local, nhid)
+        self.gc2 = GraphConvolution(nhid, nclass)
+        self.dropout = float(dropout)
+        self._seed, self._calls = 0x5EED, 0
+
+    def sync_replicated(self) -> None:
+        """Make the replicated tensors identical on all ranks (call after moving the module to its device)."""
+        with torch.no_grad():
+            D = self.lg.n_docs_local
+            top = self.gc1.weight.data[D:].contiguous()
+            self.comm.broadcast(top)
+            self.gc1.weight.data[D:] = top
+            for p in (self.gc1.bias, self.gc2.weight, self.gc2.bias):
+                self.comm.broadcast(p.data)
+
+    def loss(self, labels: Optional[torch.Tensor] = None, index: Optional[torch.Tensor] = None,
+             row_label: Optional[torch.Tensor] = None, keep_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Global mean cross-entropy over all ranks' training documents (reference trainer.py:357-359 semantics)."""
+        from . import ops
+        lg = self.lg
+        if row_label is None:
+            labels = lg.labels if labels is None else labels
+            index = lg.train_idx if index is None else index
+            row_label = ops.make_row_label(lg.n_local, labels, index)
+        self._calls += int(self.training)
+        return _ShardedLoss.apply(self.gc1.weight, self.gc1.bias, self.gc2.weight, self.gc2.bias, self, row_label,
+                                  keep_mask)
+
+
+def sharded_forward(model: ShardedGCN, W1, b1, W2, b2, row_label, keep_mask):
+    """Train-mode forward on one rank.  Returns (global loss, saved tensors for the backward)."""
+    from . import ops
+    lg, comm = model.lg, model.comm
+    csr, D, K = _csr(lg), lg.n_docs_local, lg.n_topics
+    p, training = model.dropout, model.training
+    inv = 1.0 / max(lg.n_train_global, 1)
+    # layer 1: document rows get the fused epilogue, topic rows are stored raw, summed over ranks, then finished
+    H1 = ops.gc1_forward(csr, W1, b1, p, training, keep_mask, model._seed, model._calls, raw_row_begin=D)
+    top = H1[D:]
+    comm.all_reduce(top)
+    ops.gc1_forward(ops.identity_csr(K, H1.device), top, b1, p, training,
+                    None if keep_mask is None else keep_mask[D:].contiguous(), model._seed ^ 0x7091C, model._calls, out=top)
+    # layer 2 + loss: only document rows carry labels, so their logits need no collective in the forward
+    S2 = ops.dense_nn(H1, W2)
+    loss_local, _, dZ2 = ops.gc2_loss_forward(csr, S2, b2, row_label, inv, want_logits=False, want_grad=True)
+    loss = loss_local.clone()
+    comm.all_reduce(loss)
+    return loss, (H1, dZ2)
+
+
+def sharded_backward(model: ShardedGCN, W2, saved, dloss=None):
+    """Backward on one rank: returns (dW1, db1, dW2, db2), replicated gradients already summed over ranks."""
+    from . import ops
+    lg, comm = model.lg, model.comm
+    csr, D, K = _csr(lg), lg.n_docs_local, lg.n_topics
+    H1, dZ2 = saved
+    if dloss is not None:
+        dZ2 = dZ2 * dloss
+    scale = 1.0 / (1.0 - model.dropout) if (model.training and model.dropout > 0) else 1.0
+    db2 = ops.colsum(dZ2)  # topic rows of dZ2 are zero: every rank contributes its documents only
+    dS2 = ops.spmm(csr, dZ2)
+    comm.all_reduce(dS2[D:])
+    dZ1 = torch.empty_like(H1)
+    _, dW2, db1 = ops.hidden_backward(H1[:D], dS2[:D], W2, scale, out_dZ1=dZ1[:D])
+    _, dW2_t, db1_t = ops.hidden_backward(H1[D:], dS2[D:], W2, scale, out_dZ1=dZ1[D:])
+    if comm.rank == 0:  # the replicated topic rows count once
+        dW2 = dW2 + dW2_t
+        db1 = db1 + db1_t
+    packed = torch.cat([dW2.reshape(-1), db1, db2])
+    comm.all_reduce(packed)
+    h, c = dW2.shape
+    dW2, db1, db2 = packed[:h * c].view(h, c), packed[h * c:h * c + h], packed[h * c + h:]
+    dW1 = ops.spmm(csr, dZ1)
+    comm.all_reduce(dW1[D:])
+    return dW1, db1, dW2, db2
+
+
+class _ShardedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, W1, b1, W2, b2, model, row_label, keep_mask):
+        loss, saved = sharded_forward(model, W1, b1, W2, b2, row_label, keep_mask)
+        ctx.model = model
+        ctx.save_for_backward(W2, *saved)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        W2, H1, dZ2 = ctx.saved_tensors
+        dW1, db1, dW2, db2 = sharded_backward(ctx.model, W2, (H1, dZ2), dloss)
+        return dW1, db1, dW2, db2, None, None, None
+
+
+def run_threads(world: int, fn: Callable[[int, ThreadComm], object]) -> list:
+    """Run fn(rank, comm) for `world` emulated ranks as threads; returns their results (exceptions re-raised)."""
+    comms = ThreadComm.create(world)
+    out: list = [None] * world
+    err: list = [None] * world
+
+    def target(r):
+        try:
+            out[r] = fn(r, comms[r])
+        except BaseException as exc:  # noqa: BLE001
+            err[r] = exc
+            try:
+                comms[r].s.barrier.abort()
+            except Exception:
+                pass
+
+    ts = [threading.Thread(target=target, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in err:
+        if e is not None and not isinstance(e, threading.BrokenBarrierError):
+            raise e
+    for e in err:
+        if e is not None:
+            raise e
+    return out

@@ -107,11 +107,14 @@ int tg_spmm_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colid
  *              that reproduces torch's `bernoulli_(1-p)` mask bit for bit; NULL -> counter-based
  *              Philox4x32-10 keyed on (seed, offset, row, col), see tg_dropout_keep_mask.
  *   p == 0 or training == 0 -> no dropout (eval mode, layer.py:185 `train=self.training`).
+ *   raw_row_begin: rows >= raw_row_begin are stored as plain sums A*S without bias/relu/dropout (negative = none).
+ *              The document-sharded multi-GPU mode uses it for the replicated topic rows, whose partial sums are
+ *              all-reduced across ranks before the epilogue is applied to them (a second call on those rows).
  * ---------------------------------------------------------------------------------------------- */
 int tg_gc1_fwd_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                    const float* S, int64_t lds, const float* bias, float* H1, int64_t ldh, int32_t n_feat,
                    float p, int32_t training, const uint8_t* keep_mask, uint64_t seed, uint64_t offset,
-                   void* workspace, size_t workspace_bytes, void* stream);
+                   int64_t raw_row_begin, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Materialise the Philox keep mask the fused kernel uses (tests / debugging). */
 int tg_dropout_keep_mask(uint8_t* keep_mask, int64_t n_rows, int32_t n_feat, float p, uint64_t seed,
