@@ -60,6 +60,9 @@ struct tg_plan {
     float* hval = nullptr;           // [hub_nnz]
     int32_t* htab = nullptr;         // [n_chunks][n_hub+1] offsets into hcol/hval: segment (chunk, hub slot)
     int4* cdesc = nullptr;           // [n_chunks] {first CSR entry of the chunk's rows, one past the last, htab[c][0], htab[c][n_hub]}
+    int32_t n_vslot = 0;             // virtual hub slots (heavy hub rows are split; multiple of 64)
+    int32_t* vmap = nullptr;         // [n_hub][8] virtual slots of each hub row
+    int32_t* vcnt = nullptr;         // [n_hub]
     int32_t* rsplit = nullptr;       // [n_rows] first hub-column entry of each row in colidx2 (rows are reordered: others | hubs)
 };
 

@@ -20,6 +20,7 @@
 #include <cub/cub.cuh>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "tg_stream.cuh"
@@ -46,6 +47,9 @@ struct StreamArgs {
     int64_t nnz, hub_nnz;
     int32_t n_chunks4;  // n_feat / 4
     int32_t T, n_chunks, Kh, hub_threshold;
+    int32_t Kv;                          // virtual hub slots (table width): heavy hub rows are split into several
+    const int32_t* __restrict__ vmap;    // [Kh][8] virtual slots of every hub row
+    const int32_t* __restrict__ vcnt;    // [Kh]    how many
     int32_t cap_doc, cap_hub;
     int32_t n_slices, n_groups;
     float* partials;
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(kSThreads, 1) stream_spmm_kernel(const StreamA
 
     float* BH = reinterpret_cast<float*>(smem_raw);
     const size_t bh_bytes = align16((size_t)a.Kh * FT * 4);
-    const size_t st_bytes = stage_bytes(a.T, FT, a.cap_doc, a.cap_hub, a.Kh);
+    const size_t st_bytes = stage_bytes(a.T, FT, a.cap_doc, a.cap_hub, a.Kv);
     auto stage_at = [&](int buf) {
         return stage_view(smem_raw + bh_bytes + (size_t)buf * st_bytes, a.T, FT, a.cap_doc, a.cap_hub);
     };
@@ -169,8 +173,8 @@ __global__ void __launch_bounds__(kSThreads, 1) stream_spmm_kernel(const StreamA
             const bool ok = p < d.w;
             cp_async16(sv.hent + 2 * idx, ok ? a.hent + p : a.hent, ok);
         }
-        for (int idx = tid; idx <= a.Kh; idx += kSThreads)
-            cp_async4(sv.htab + idx, a.htab + (int64_t)c * (a.Kh + 1) + idx, true);
+        for (int idx = tid; idx <= a.Kv; idx += kSThreads)
+            cp_async4(sv.htab + idx, a.htab + (int64_t)c * (a.Kv + 1) + idx, true);
     };
 
     Chunk<4> hacc[KPG][CPL];
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(kSThreads, 1) stream_spmm_kernel(const StreamA
 #pragma unroll
             for (int kk = 0; kk < KPG; ++kk) {
                 const int k = grp + kNG * kk;
-                if (k < a.Kh) {
+                if (k < a.Kv) {
                     const int h0 = sv.htab[k], h1 = sv.htab[k + 1];
                     if (h1 <= hwin_end) {
                         const int2* ent = sv.hent - hwin0;
@@ -296,11 +300,373 @@ __global__ void __launch_bounds__(kSThreads, 1) stream_spmm_kernel(const StreamA
 #pragma unroll
     for (int kk = 0; kk < KPG; ++kk) {
         const int k = grp + kNG * kk;
-        if (k < a.Kh) {
+        if (k < a.Kv) {
 #pragma unroll
             for (int i = 0; i < CPL; ++i)
                 if (q0 + 8 * i < a.n_chunks4)
-                    chunk_st<4>(a.partials + ((int64_t)cg * a.Kh + k) * a.ldp + (int64_t)(q0 + 8 * i) * 4, hacc[kk][i]);
+                    chunk_st<4>(a.partials + ((int64_t)cg * a.Kv + k) * a.ldp + (int64_t)(q0 + 8 * i) * 4, hacc[kk][i]);
+        }
+    }
+}
+
+// ---- role-specialised streaming kernel (wide rows) ----------------------------------------------------------------------
+// The combined kernel above keeps BOTH the hub rows of B and the staged chunk in shared memory, which caps its column
+// slice at 64 and its chunk at 128 nodes.  Splitting the two uses of B over two kinds of CTAs in ONE launch removes that:
+//   hub CTAs  (64-column slices): stream 256-node chunks through shared memory (cp.async double buffer) and accumulate
+//             acc[k] += sum_{j in chunk} A[k,j] * B[j]  in registers — no copy of the hub rows needed;
+//   doc CTAs  (32*CPLD-column slices, CPLD = 4 -> 128 columns): keep the K hub rows of B resident in shared memory and
+//             produce the short rows: hub columns from shared memory, the self loop straight from L2; no staging, no
+//             block-level synchronisation after the prologue.
+// Both kinds sweep the node range front to back in round-robin (chunk c -> hub CTA c mod n; row block j -> doc CTA
+// j mod m), so the two fronts advance together and the second reader of a row of B hits L2: DRAM sees B once.
+struct RolesArgs {
+    StreamArgs s;
+    int32_t hub_slices, hub_lanes;  // hub CTAs = hub_slices * hub_lanes (slice fastest)
+    int32_t doc_slices, doc_lanes;  // doc CTAs = doc_slices * doc_lanes
+    int32_t doc_job_rows;           // rows per doc-role job
+    int32_t n_doc_jobs;
+    int32_t only_role;              // debugging/profiling knob: 1 = hub CTAs only, 2 = document CTAs only, 0 = both
+};
+
+template <int THREADS, int CPLD, int KPG, class Epi>
+__global__ void __launch_bounds__(THREADS, 1) stream_roles_kernel(const RolesArgs ra, const Epi epi) {
+    const StreamArgs& a = ra.s;
+    constexpr int NGr = THREADS / kGW;  // row groups per CTA
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int gl = lane & (kGW - 1);
+    const int grp = tid / kGW;
+    const unsigned gmask = group_mask<kGW>(lane);
+    const int n_hub_ctas = ra.hub_slices * ra.hub_lanes;
+
+    if (ra.only_role == 2 && (int)blockIdx.x < n_hub_ctas) return;
+    if (ra.only_role == 1 && (int)blockIdx.x >= n_hub_ctas) return;
+    if ((int)blockIdx.x < n_hub_ctas) {
+        // ================================ hub role ================================
+        constexpr int CPL = 2, FT = 64, QS = 16;
+        const int slice = blockIdx.x % ra.hub_slices;
+        const int hl = blockIdx.x / ra.hub_slices;
+        const int q0 = slice * QS + gl;
+        const size_t st_bytes = align16((size_t)a.T * FT * 4) + align16((size_t)a.cap_hub * 8) + align16((size_t)(a.Kv + 1) * 4);
+        auto Bs_at = [&](int buf) { return reinterpret_cast<float*>(smem_raw + (size_t)buf * st_bytes); };
+        auto he_at = [&](int buf) { return reinterpret_cast<int2*>(smem_raw + (size_t)buf * st_bytes + align16((size_t)a.T * FT * 4)); };
+        auto ht_at = [&](int buf) {
+            return reinterpret_cast<int32_t*>(smem_raw + (size_t)buf * st_bytes + align16((size_t)a.T * FT * 4) +
+                                              align16((size_t)a.cap_hub * 8));
+        };
+        auto issue = [&](int buf, int c, const int4 d) {
+            const int64_t c0 = (int64_t)c * a.T;
+            float* Bs = Bs_at(buf);
+            for (int idx = tid; idx < a.T * QS; idx += THREADS) {
+                const int r = idx / QS, q = idx % QS;
+                const int64_t row = c0 + r;
+                const bool ok = row < a.n && (slice * QS + q) < a.n_chunks4;
+                cp_async16(Bs + r * FT + q * 4, ok ? a.B + row * a.ldb + (int64_t)(slice * QS + q) * 4 : a.B, ok);
+            }
+            int2* he = he_at(buf);
+            const int64_t h0 = d.z & ~1;
+            for (int idx = tid; idx < a.cap_hub / 2; idx += THREADS) {
+                const int64_t p = h0 + 2 * idx;
+                const bool ok = p < d.w;
+                cp_async16(he + 2 * idx, ok ? a.hent + p : a.hent, ok);
+            }
+            int32_t* ht = ht_at(buf);
+            for (int idx = tid; idx <= a.Kv; idx += THREADS)
+                cp_async4(ht + idx, a.htab + (int64_t)c * (a.Kv + 1) + idx, true);
+        };
+        Chunk<4> hacc[KPG][CPL];
+#pragma unroll
+        for (int kk = 0; kk < KPG; ++kk)
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) hacc[kk][i] = chunk_zero<4>();
+        int c = hl;
+        if (c < a.n_chunks) {
+            int4 d_cur = __ldg(a.cdesc + c);
+            issue(0, c, d_cur);
+            cp_async_commit();
+            int4 d_next = (c + ra.hub_lanes < a.n_chunks) ? __ldg(a.cdesc + c + ra.hub_lanes) : make_int4(0, 0, 0, 0);
+            for (int it = 0; c < a.n_chunks; c += ra.hub_lanes, ++it) {
+                const int buf = it & 1;
+                const int cn = c + ra.hub_lanes;
+                if (cn < a.n_chunks) {
+                    issue(buf ^ 1, cn, d_next);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncthreads();
+                const int4 d_new = (cn + ra.hub_lanes < a.n_chunks) ? __ldg(a.cdesc + cn + ra.hub_lanes) : make_int4(0, 0, 0, 0);
+                const float* Bs = Bs_at(buf);
+                const int2* he = he_at(buf);
+                const int32_t* ht = ht_at(buf);
+                const int hwin0 = d_cur.z & ~1;
+                const int hwin_end = hwin0 + a.cap_hub;
+#pragma unroll
+                for (int kk = 0; kk < KPG; ++kk) {
+                    const int k = grp + NGr * kk;
+                    if (k < a.Kv) {
+                        const int h0 = ht[k], h1 = ht[k + 1];
+                        if (h1 <= hwin_end) {
+                            const int2* ent = he - hwin0;
+#pragma unroll 4
+                            for (int q = h0; q < h1; ++q) {
+                                const int2 en = ent[q];
+                                fma_row_smem<CPL>(hacc[kk], __int_as_float(en.y), Bs + en.x * FT, gl);
+                            }
+                        } else {
+                            for (int q = h0; q < h1; ++q) {
+                                const int2 en = (q < hwin_end) ? he[q - hwin0] : __ldg(a.hent + q);
+                                fma_row_smem<CPL>(hacc[kk], __int_as_float(en.y), Bs + en.x * FT, gl);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                d_cur = d_next;
+                d_next = d_new;
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < KPG; ++kk) {
+            const int k = grp + NGr * kk;
+            if (k < a.Kv) {
+#pragma unroll
+                for (int i = 0; i < CPL; ++i)
+                    if (q0 + 8 * i < a.n_chunks4)
+                        chunk_st<4>(a.partials + ((int64_t)hl * a.Kv + k) * a.ldp + (int64_t)(q0 + 8 * i) * 4, hacc[kk][i]);
+            }
+        }
+        return;
+    }
+
+    // ================================ document role ================================
+    constexpr int FT = 32 * CPLD, QS = 8 * CPLD;
+    const int bid = blockIdx.x - n_hub_ctas;
+    const int slice = bid % ra.doc_slices;
+    const int dl = bid / ra.doc_slices;
+    const int q0 = slice * QS + gl;
+    float* BH = reinterpret_cast<float*>(smem_raw);
+    for (int idx = tid; idx < a.Kh * QS; idx += THREADS) {
+        const int k = idx / QS, q = idx % QS;
+        const bool ok = (slice * QS + q) < a.n_chunks4;
+        cp_async16(BH + k * FT + q * 4, ok ? a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb + (int64_t)(slice * QS + q) * 4 : a.B, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    constexpr int RPG = (THREADS >= 1024) ? 2 : 4;  // rows per group per job
+    for (int job = dl; job < ra.n_doc_jobs; job += ra.doc_lanes) {
+        const int64_t r_base = (int64_t)job * ra.doc_job_rows;
+        // row pointers of this group's rows first: they head the dependent chain rowptr -> entries -> FMA
+        int rs_[RPG], re_[RPG], rm_[RPG];
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) {
+            const int64_t row = r_base + grp + (int64_t)NGr * i;
+            const bool ok = (grp + NGr * i) < ra.doc_job_rows && row < a.n;
+            rs_[i] = ok ? __ldg(a.rowptr + row) : 0;
+            re_[i] = ok ? __ldg(a.rowptr + row + 1) : 0;
+            rm_[i] = ok ? __ldg(a.rsplit + row) : 0;
+            if (re_[i] - rs_[i] > a.hub_threshold) re_[i] = rs_[i];  // hub rows belong to the hub role
+        }
+        int2 first[RPG];
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) {
+            const int p = rm_[i] + gl;
+            first[i] = (p < re_[i]) ? __ldg(a.dent + p) : make_int2(0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) {
+            const int s = rs_[i], e = re_[i], m = rm_[i];
+            if (e <= s) continue;
+            const int64_t row = r_base + grp + (int64_t)NGr * i;
+            Chunk<4> acc[CPLD];
+#pragma unroll
+            for (int u = 0; u < CPLD; ++u) acc[u] = chunk_zero<4>();
+            for (int p = s; p < m; ++p) {  // non-hub columns (the self loop): L2
+                const int2 en = __ldg(a.dent + p);
+                const float v = __int_as_float(en.y);
+                const float* src = a.B + (int64_t)en.x * a.ldb;
+#pragma unroll
+                for (int u = 0; u < CPLD; ++u)
+                    if (q0 + 8 * u < a.n_chunks4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(src + (int64_t)(q0 + 8 * u) * 4));
+                        acc[u].v[0] = fmaf(v, b.x, acc[u].v[0]); acc[u].v[1] = fmaf(v, b.y, acc[u].v[1]);
+                        acc[u].v[2] = fmaf(v, b.z, acc[u].v[2]); acc[u].v[3] = fmaf(v, b.w, acc[u].v[3]);
+                    }
+            }
+            int2 my = first[i];
+            for (int base = m; base < e; base += kGW) {
+                if (base != m) {
+                    const int p = base + gl;
+                    my = (p < e) ? __ldg(a.dent + p) : make_int2(0, 0);
+                }
+                const int cnt = min(kGW, e - base);
+#pragma unroll 4
+                for (int j = 0; j < cnt; ++j) {
+                    const int slot = __shfl_sync(gmask, my.x, j, kGW);
+                    const float v = __int_as_float(__shfl_sync(gmask, my.y, j, kGW));
+                    fma_row_smem<CPLD>(acc, v, BH + slot * FT, gl);
+                }
+            }
+            epi.template apply<4, kGW, CPLD>(row, q0, gmask, a.n_chunks4, acc);
+        }
+    }
+}
+
+// ---- narrow rows (F <= 32): one LANE per row ------------------------------------------------------------------------
+// With 8-20 classes a row is only 2-5 float4 chunks: the lane-group layout above would spend most of its instructions on
+// index handling.  Here every lane owns a whole output row (document side) and a whole hub row (hub side): NV float4
+// accumulators in registers, entries read at lane-private shared-memory addresses, row epilogue entirely inside the lane
+// (the group epilogues are instantiated with a group of ONE lane).  Same staging, same partial/finish scheme, same
+// fixed summation order as the wide kernel.
+constexpr int kNThreads = 256;
+
+template <int NV>
+__device__ __forceinline__ void fma_row_lane(Chunk<4> (&acc)[NV], float v, const float* row) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 b = *reinterpret_cast<const float4*>(row + i * 4);
+        acc[i].v[0] = fmaf(v, b.x, acc[i].v[0]);
+        acc[i].v[1] = fmaf(v, b.y, acc[i].v[1]);
+        acc[i].v[2] = fmaf(v, b.z, acc[i].v[2]);
+        acc[i].v[3] = fmaf(v, b.w, acc[i].v[3]);
+    }
+}
+
+template <int NV, int KPT, class Epi>
+__global__ void __launch_bounds__(kNThreads) stream_narrow_kernel(const StreamArgs a, const Epi epi) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int FT = a.n_chunks4 * 4;  // == n_feat (one slice)
+    const int cg = blockIdx.x;
+    const int c_begin = (int)((int64_t)cg * a.n_chunks / a.n_groups);
+    const int c_end = (int)((int64_t)(cg + 1) * a.n_chunks / a.n_groups);
+    const unsigned lmask = 1u << (tid & 31);
+
+    float* BH = reinterpret_cast<float*>(smem_raw);
+    const size_t bh_bytes = align16((size_t)a.Kh * FT * 4);
+    const size_t st_bytes = stage_bytes(a.T, FT, a.cap_doc, a.cap_hub, a.Kv);
+    auto stage_at = [&](int buf) {
+        return stage_view(smem_raw + bh_bytes + (size_t)buf * st_bytes, a.T, FT, a.cap_doc, a.cap_hub);
+    };
+    auto issue_stage = [&](const StageView& sv, int c, const int4 d) {
+        const int64_t c0 = (int64_t)c * a.T;
+        for (int idx = tid; idx < a.T * NV; idx += kNThreads) {
+            const int r = idx / NV, q = idx % NV;
+            const int64_t row = c0 + r;
+            const bool ok = row < a.n && q < a.n_chunks4;
+            cp_async16(sv.Bs + r * FT + q * 4, ok ? a.B + row * a.ldb + q * 4 : a.B, ok);
+        }
+        for (int idx = tid; idx <= a.T; idx += kNThreads) {
+            const bool ok = c0 + idx <= a.n;
+            cp_async4(sv.rp + idx, ok ? a.rowptr + c0 + idx : a.rowptr, ok);
+        }
+        for (int idx = tid; idx < a.T; idx += kNThreads) {
+            const bool ok = c0 + idx < a.n;
+            cp_async4(sv.rs + idx, ok ? a.rsplit + c0 + idx : a.rsplit, ok);
+        }
+        const int64_t d0 = d.x & ~1, h0 = d.z & ~1;
+        for (int idx = tid; idx < a.cap_doc / 2; idx += kNThreads) {
+            const int64_t p = d0 + 2 * idx;
+            const bool ok = p < d.y;
+            cp_async16(sv.dent + 2 * idx, ok ? a.dent + p : a.dent, ok);
+        }
+        for (int idx = tid; idx < a.cap_hub / 2; idx += kNThreads) {
+            const int64_t p = h0 + 2 * idx;
+            const bool ok = p < d.w;
+            cp_async16(sv.hent + 2 * idx, ok ? a.hent + p : a.hent, ok);
+        }
+        for (int idx = tid; idx <= a.Kv; idx += kNThreads)
+            cp_async4(sv.htab + idx, a.htab + (int64_t)c * (a.Kv + 1) + idx, true);
+    };
+
+    Chunk<4> hacc[KPT][NV];
+#pragma unroll
+    for (int kk = 0; kk < KPT; ++kk)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) hacc[kk][i] = chunk_zero<4>();
+
+    if (c_begin < c_end) {
+        for (int idx = tid; idx < a.Kh * NV; idx += kNThreads) {
+            const int k = idx / NV, q = idx % NV;
+            const bool ok = q < a.n_chunks4;
+            cp_async16(BH + k * FT + q * 4, ok ? a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb + q * 4 : a.B, ok);
+        }
+        int4 d_cur = __ldg(a.cdesc + c_begin);
+        issue_stage(stage_at(0), c_begin, d_cur);
+        cp_async_commit();
+        int4 d_next = (c_begin + 1 < c_end) ? __ldg(a.cdesc + c_begin + 1) : make_int4(0, 0, 0, 0);
+        for (int c = c_begin; c < c_end; ++c) {
+            const int buf = (c - c_begin) & 1;
+            if (c + 1 < c_end) {
+                issue_stage(stage_at(buf ^ 1), c + 1, d_next);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+            const int4 d_new = (c + 2 < c_end) ? __ldg(a.cdesc + c + 2) : make_int4(0, 0, 0, 0);
+            const StageView sv = stage_at(buf);
+            const int c0 = c * a.T;
+            const int dwin0 = d_cur.x & ~1, hwin0 = d_cur.z & ~1;
+            const int dwin_end = dwin0 + a.cap_doc, hwin_end = hwin0 + a.cap_hub;
+
+            // ---- (i) short rows: one lane per row -------------------------------------------------------------------
+            for (int lr = tid; lr < a.T; lr += kNThreads) {
+                const int64_t row = (int64_t)c0 + lr;
+                if (row >= a.n) break;
+                const int s = sv.rp[lr], e = sv.rp[lr + 1];
+                if (e - s > a.hub_threshold) continue;
+                const int m = sv.rs[lr];
+                Chunk<4> acc[NV];
+#pragma unroll
+                for (int i = 0; i < NV; ++i) acc[i] = chunk_zero<4>();
+                for (int p = s; p < e; ++p) {
+                    const int2 en = (p < dwin_end) ? sv.dent[p - dwin0] : __ldg(a.dent + p);
+                    const float v = __int_as_float(en.y);
+                    if (p >= m) {
+                        fma_row_lane<NV>(acc, v, BH + en.x * FT);
+                    } else if ((unsigned)(en.x - c0) < (unsigned)a.T) {
+                        fma_row_lane<NV>(acc, v, sv.Bs + (en.x - c0) * FT);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(a.B + (int64_t)en.x * a.ldb + i * 4));
+                            acc[i].v[0] = fmaf(v, b.x, acc[i].v[0]); acc[i].v[1] = fmaf(v, b.y, acc[i].v[1]);
+                            acc[i].v[2] = fmaf(v, b.z, acc[i].v[2]); acc[i].v[3] = fmaf(v, b.w, acc[i].v[3]);
+                        }
+                    }
+                }
+                epi.template apply<4, 1, NV>(row, 0, lmask, a.n_chunks4, acc);
+            }
+
+            // ---- (ii) hub rows: one lane per hub row ----------------------------------------------------------------
+#pragma unroll
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int k = tid + kNThreads * kk;
+                if (k < a.Kv) {
+                    const int h0 = sv.htab[k], h1 = sv.htab[k + 1];
+                    for (int q = h0; q < h1; ++q) {
+                        const int2 en = (q < hwin_end) ? sv.hent[q - hwin0] : __ldg(a.hent + q);
+                        fma_row_lane<NV>(hacc[kk], __int_as_float(en.y), sv.Bs + en.x * FT);
+                    }
+                }
+            }
+            __syncthreads();
+            d_cur = d_next;
+            d_next = d_new;
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KPT; ++kk) {
+        const int k = tid + kNThreads * kk;
+        if (k < a.Kv) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (i < a.n_chunks4) chunk_st<4>(a.partials + ((int64_t)cg * a.Kv + k) * a.ldp + i * 4, hacc[kk][i]);
         }
     }
 }
@@ -308,48 +674,84 @@ __global__ void __launch_bounds__(kSThreads, 1) stream_spmm_kernel(const StreamA
 // ---- finishing kernel: hub row k = sum over CTA groups (fixed order) + epilogue --------------------------------------
 template <int VEC, int G, int CPL, class Epi>
 __global__ void __launch_bounds__(256) stream_finish_kernel(const float* __restrict__ partials, int64_t ldp, int n_groups,
-                                                            int Kh, const int32_t* __restrict__ hub_rows, int n_chunks,
+                                                            int Kh, int Kv, const int32_t* __restrict__ vmap,
+                                                            const int32_t* __restrict__ vcnt,
+                                                            const int32_t* __restrict__ hub_rows, int n_chunks,
                                                             const Epi epi) {
+    // One block row-group per hub row; the 8 warps of a block take the CTA partials g = w, w+8, ... (each warp in
+    // ascending order), deposit their sums in shared memory and warp 0 adds the 8 deposits in warp order: a fixed tree.
     constexpr int GPW = 32 / G;
-    constexpr int GPB = 8 * GPW;
+    extern __shared__ __align__(16) float fin_s[];  // [8 warps][GPW groups][G*CPL*VEC]
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int gl = lane & (G - 1);
+    const int gw = lane / G;
     const unsigned gmask = group_mask<G>(lane);
-    const int k = blockIdx.x * GPB + (threadIdx.x >> 5) * GPW + lane / G;
-    if (k >= Kh) return;
+    const int k = blockIdx.x * GPW + gw;
     Chunk<VEC> acc[CPL];
 #pragma unroll
     for (int i = 0; i < CPL; ++i) acc[i] = chunk_zero<VEC>();
-    for (int g = 0; g < n_groups; ++g) {
-        const float* src = partials + ((int64_t)g * Kh + k) * ldp;
+    if (k < Kh) {
+        const int nv = __ldg(vcnt + k);
+        for (int j = 0; j < nv; ++j) {
+            const int v = __ldg(vmap + k * 8 + j);
+            for (int g = warp; g < n_groups; g += 8) {
+                const float* src = partials + ((int64_t)g * Kv + v) * ldp;
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-            const int chunk = gl + i * G;
-            if (chunk < n_chunks) {
-                const Chunk<VEC> t = chunk_ldg<VEC>(src + (int64_t)chunk * VEC);
+                for (int i = 0; i < CPL; ++i) {
+                    const int chunk = gl + i * G;
+                    if (chunk < n_chunks) {
+                        const Chunk<VEC> t = chunk_ldg<VEC>(src + (int64_t)chunk * VEC);
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) acc[i].v[v] += t.v[v];
+                        for (int e = 0; e < VEC; ++e) acc[i].v[e] += t.v[e];
+                    }
+                }
             }
         }
+    }
+    constexpr int ROWF = G * CPL * VEC;
+    float* mine = fin_s + ((size_t)warp * GPW + gw) * ROWF;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) mine[(gl + i * G) * VEC + e] = acc[i].v[e];
+    __syncthreads();
+    if (warp != 0 || k >= Kh) return;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) acc[i] = chunk_zero<VEC>();
+    for (int w = 0; w < 8; ++w) {
+        const float* src = fin_s + ((size_t)w * GPW + gw) * ROWF;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[i].v[e] += src[(gl + i * G) * VEC + e];
     }
     epi.template apply<VEC, G, CPL>((int64_t)__ldg(hub_rows + k), gl, gmask, n_chunks, acc);
 }
 
+struct FinishArgs {
+    const float* partials;
+    int64_t ldp;
+    int n_groups, Kh, Kv;
+    const int32_t *vmap, *vcnt, *hub_rows;
+    int n_chunks;
+};
+
 template <int VEC, int G, int CPL, class Epi>
-static int launch_finish(const float* partials, int64_t ldp, int n_groups, int Kh, const int32_t* hub_rows, int n_chunks,
-                         const Epi& epi, cudaStream_t st) {
-    constexpr int GPB = 8 * (32 / G);
-    stream_finish_kernel<VEC, G, CPL, Epi><<<(unsigned)ceil_div64(Kh, GPB), 256, 0, st>>>(partials, ldp, n_groups, Kh,
-                                                                                          hub_rows, n_chunks, epi);
+static int launch_finish(const FinishArgs& f, const Epi& epi, cudaStream_t st) {
+    constexpr int GPW = 32 / G;
+    const size_t smem = (size_t)8 * GPW * G * CPL * VEC * sizeof(float);
+    stream_finish_kernel<VEC, G, CPL, Epi><<<(unsigned)ceil_div64(f.Kh, GPW), 256, smem, st>>>(
+        f.partials, f.ldp, f.n_groups, f.Kh, f.Kv, f.vmap, f.vcnt, f.hub_rows, f.n_chunks, epi);
     TG_LAUNCH_CHECK();
     return TG_OK;
 }
 
 template <class Epi>
-static int finish_dispatch(const float* partials, int64_t ldp, int n_groups, int Kh, const int32_t* hub_rows,
-                           int n_chunks, const Epi& epi, cudaStream_t st) {
-#define TG_LAUNCH_FIN(V, G, C) launch_finish<V, G, C>(partials, ldp, n_groups, Kh, hub_rows, n_chunks, epi, st)
-    TG_SHAPE_SWITCH(4, n_chunks, TG_LAUNCH_FIN);
+static int finish_dispatch(const StreamArgs& a, const float* partials, int n_groups, const Epi& epi, cudaStream_t st) {
+    FinishArgs f{partials, a.ldp, n_groups, a.Kh, a.Kv, a.vmap, a.vcnt, a.hub_rows, a.n_chunks4};
+#define TG_LAUNCH_FIN(V, G, C) launch_finish<V, G, C>(f, epi, st)
+    TG_SHAPE_SWITCH(4, f.n_chunks, TG_LAUNCH_FIN);
 #undef TG_LAUNCH_FIN
     set_error("n_feat too wide for the streaming finish kernel");
     return TG_ERR_UNSUPPORTED;
@@ -363,7 +765,7 @@ static int env_int(const char* name, int dflt) {
 
 static size_t stream_smem_bytes(const tg_plan* pl, int CPL) {
     const int FT = 32 * CPL;
-    return align16((size_t)pl->n_hub * FT * 4) + 2 * stage_bytes(pl->chunk_rows, FT, pl->cap_doc, pl->cap_hub, pl->n_hub);
+    return align16((size_t)pl->n_hub * FT * 4) + 2 * stage_bytes(pl->chunk_rows, FT, pl->cap_doc, pl->cap_hub, pl->n_vslot);
 }
 
 // chunks per lane: 2 (64-column slices) when the row is wide enough and the hub rows fit, else 1 (32-column slices)
@@ -377,17 +779,112 @@ static int pick_cpl(const tg_plan* pl, int n_feat, bool whole_row) {
     return 0;
 }
 
+// ---- role-specialised launch -------------------------------------------------------------------------------------------
+static size_t roles_hub_smem(const tg_plan* pl) {
+    return 2 * (align16((size_t)pl->chunk_rows * 64 * 4) + align16((size_t)pl->cap_hub * 8) + align16((size_t)(pl->n_vslot + 1) * 4));
+}
+static size_t roles_doc_smem(const tg_plan* pl, int CPLD) { return align16((size_t)pl->n_hub * 32 * CPLD * 4); }
+
+static int roles_cpld(const tg_plan* pl, int n_feat) {
+    for (int CPLD = 4; CPLD >= 2; CPLD -= 2) {
+        if (n_feat < 32 * CPLD && CPLD > 2) continue;
+        if (roles_doc_smem(pl, CPLD) <= kSmemBudget) return CPLD;
+    }
+    return 0;
+}
+
+static bool roles_applicable(const tg_plan* pl, int n_feat) {
+    if (env_int("TG_STREAM_ROLES", 1) == 0) return false;
+    if (n_feat < 64 || n_feat % 4 != 0) return false;
+    if (roles_hub_smem(pl) > kSmemBudget || pl->n_vslot > kNG * 8) return false;
+    return roles_cpld(pl, n_feat) != 0;
+}
+
+template <int THREADS, int CPLD, int KPG, class Epi>
+static int launch_roles(const tg_plan* pl, const StreamCall& c, RolesArgs ra, const Epi& epi, cudaStream_t st) {
+    size_t smem = roles_hub_smem(pl);
+    if (roles_doc_smem(pl, CPLD) > smem) smem = roles_doc_smem(pl, CPLD);
+    TG_CUDA(cudaFuncSetAttribute(stream_roles_kernel<THREADS, CPLD, KPG, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    StreamArgs& a = ra.s;
+    ra.hub_slices = (int)ceil_div64(a.n_chunks4, 16);
+    ra.doc_slices = (int)ceil_div64(a.n_chunks4, 8 * CPLD);
+    // share of the SMs given to the hub role (per-node work of the two roles is roughly 55:45)
+    const int hub_pct = env_int("TG_ROLES_HUB_PCT", 55);
+    int hub_lanes = (kNumSM * hub_pct / 100) / ra.hub_slices;
+    if (hub_lanes < 1) hub_lanes = 1;
+    int doc_lanes = (kNumSM - hub_lanes * ra.hub_slices) / ra.doc_slices;
+    if (doc_lanes < 1) doc_lanes = 1;
+    if (hub_lanes > a.n_chunks) hub_lanes = a.n_chunks;
+    ra.hub_lanes = hub_lanes;
+    ra.doc_lanes = doc_lanes;
+    ra.doc_job_rows = 256;
+    ra.only_role = env_int("TG_ROLES_ONLY", 0);
+    ra.n_doc_jobs = (int)ceil_div64(a.n, ra.doc_job_rows);
+    a.n_groups = hub_lanes;
+    const size_t need = (size_t)hub_lanes * pl->n_vslot * a.ldp * sizeof(float);
+    TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
+               c.workspace_bytes, need + 16);
+    const unsigned grid = (unsigned)(ra.hub_slices * hub_lanes + ra.doc_slices * doc_lanes);
+    stream_roles_kernel<THREADS, CPLD, KPG, Epi><<<grid, THREADS, smem, st>>>(ra, epi);
+    TG_LAUNCH_CHECK();
+    return finish_dispatch(a, a.partials, hub_lanes, epi, st);
+}
+
+template <class Epi>
+static int run_roles(const tg_plan* pl, const StreamCall& c, const Epi& epi, cudaStream_t st) {
+    RolesArgs ra;
+    StreamArgs& a = ra.s;
+    a.rowptr = c.rowptr; a.rsplit = pl->rsplit; a.dent = reinterpret_cast<const int2*>(pl->colidx2);
+    a.hent = reinterpret_cast<const int2*>(pl->hcol); a.htab = pl->htab; a.cdesc = pl->cdesc;
+    a.hub_rows = pl->hub_rows; a.B = c.B; a.ldb = c.ldb; a.n = pl->n_rows; a.nnz = pl->nnz; a.hub_nnz = pl->hub_nnz;
+    a.n_chunks4 = c.n_feat / 4; a.T = pl->chunk_rows; a.n_chunks = pl->n_chunks; a.Kh = pl->n_hub;
+    a.Kv = pl->n_vslot; a.vmap = pl->vmap; a.vcnt = pl->vcnt;
+    a.hub_threshold = pl->hub_threshold; a.cap_doc = pl->cap_doc; a.cap_hub = pl->cap_hub;
+    a.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(c.workspace) + 15u) & ~(uintptr_t)15u);
+    a.ldp = (int64_t)((c.n_feat + 3) / 4) * 4;
+    a.n_slices = a.n_groups = 0;
+    const int CPLD = roles_cpld(pl, c.n_feat);
+    // 1024-thread CTAs (64 registers per thread, 32 warps per SM) hide the shared-memory latency better; they need the
+    // virtual slots to fit 128 groups x 4
+    const bool big = env_int("TG_ROLES_THREADS", 512) >= 1024 && pl->n_vslot <= 128 * 4;
+    const int kpg = (int)ceil_div64(pl->n_vslot, big ? 128 : kNG);
+#define TG_ROLES_CASE(Tv, Cv)                                                          \
+    if (CPLD == Cv && big == (Tv == 1024)) {                                           \
+        if (kpg <= 1) return launch_roles<Tv, Cv, 1>(pl, c, ra, epi, st);              \
+        if (kpg <= 2) return launch_roles<Tv, Cv, 2>(pl, c, ra, epi, st);              \
+        if (kpg <= 4) return launch_roles<Tv, Cv, 4>(pl, c, ra, epi, st);              \
+        if (Tv == 512) return launch_roles<512, Cv, 8>(pl, c, ra, epi, st);            \
+    }
+    TG_ROLES_CASE(512, 2)
+    TG_ROLES_CASE(512, 4)
+    TG_ROLES_CASE(1024, 2)
+    TG_ROLES_CASE(1024, 4)
+#undef TG_ROLES_CASE
+    set_error("no role-specialised configuration fits");
+    return TG_ERR_UNSUPPORTED;
+}
+
+static size_t narrow_smem_bytes(const tg_plan* pl, int n_feat) {
+    return align16((size_t)pl->n_hub * n_feat * 4) + 2 * stage_bytes(pl->chunk_rows, n_feat, pl->cap_doc, pl->cap_hub, pl->n_vslot);
+}
+
+static bool narrow_applicable(const tg_plan* pl, int n_feat) {
+    return env_int("TG_STREAM_NARROW", 1) != 0 && n_feat <= 32 && n_feat % 4 == 0 && pl->n_vslot <= 2 * kNThreads &&
+           narrow_smem_bytes(pl, n_feat) <= kSmemBudget;
+}
+
 bool stream_applicable(const tg_plan* pl, const StreamCall& c, bool out_vec4_ok, bool whole_row) {
     if (!pl || !pl->stream_ok) return false;
     if (!(c.n_feat % 4 == 0 && c.ldb % 4 == 0 && aligned16(c.B) && out_vec4_ok)) return false;
     if (c.n_feat > 1024) return false;
+    if (narrow_applicable(pl, c.n_feat)) return true;
     return pick_cpl(pl, c.n_feat, whole_row) != 0;
 }
 
 size_t stream_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
     if (!pl || !pl->stream_ok) return 0;
     const size_t ld = (size_t)((n_feat + 3) / 4) * 4;
-    return (size_t)kNumSM * pl->n_hub * ld * sizeof(float) + 16;
+    return (size_t)kNumSM * (n_feat <= 32 ? 4 : 1) * pl->n_vslot * ld * sizeof(float) + 16;
 }
 
 template <int CPL, int KPG, class Epi>
@@ -399,16 +896,54 @@ static int launch_stream(const tg_plan* pl, const StreamCall& c, StreamArgs a, c
     if (groups < 1) groups = 1;
     if (groups > a.n_chunks) groups = a.n_chunks;
     a.n_groups = groups;
-    const size_t need = (size_t)groups * pl->n_hub * a.ldp * sizeof(float);
+    const size_t need = (size_t)groups * pl->n_vslot * a.ldp * sizeof(float);
     TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
                c.workspace_bytes, need + 16);
     stream_spmm_kernel<CPL, KPG, Epi><<<(unsigned)(groups * a.n_slices), kSThreads, smem, st>>>(a, epi);
     TG_LAUNCH_CHECK();
-    return finish_dispatch(a.partials, a.ldp, groups, pl->n_hub, pl->hub_rows, a.n_chunks4, epi, st);
+    return finish_dispatch(a, a.partials, groups, epi, st);
+}
+
+template <int NV, int KPT, class Epi>
+static int launch_narrow(const tg_plan* pl, const StreamCall& c, StreamArgs a, const Epi& epi, cudaStream_t st) {
+    const size_t smem = narrow_smem_bytes(pl, c.n_feat);
+    TG_CUDA(cudaFuncSetAttribute(stream_narrow_kernel<NV, KPT, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a.n_slices = 1;
+    int per_sm = (int)(kSmemBudget / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int groups = kNumSM * per_sm;
+    if (groups > a.n_chunks) groups = a.n_chunks;
+    a.n_groups = groups;
+    const size_t need = (size_t)groups * pl->n_vslot * a.ldp * sizeof(float);
+    TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
+               c.workspace_bytes, need + 16);
+    stream_narrow_kernel<NV, KPT, Epi><<<(unsigned)groups, kNThreads, smem, st>>>(a, epi);
+    TG_LAUNCH_CHECK();
+    return finish_dispatch(a, a.partials, groups, epi, st);
 }
 
 template <class Epi>
 static int run_stream(const tg_plan* pl, const StreamCall& c, const Epi& epi, bool whole_row, cudaStream_t st) {
+    if (narrow_applicable(pl, c.n_feat)) {
+        StreamArgs a;
+        a.rowptr = c.rowptr; a.rsplit = pl->rsplit; a.dent = reinterpret_cast<const int2*>(pl->colidx2);
+        a.hent = reinterpret_cast<const int2*>(pl->hcol); a.htab = pl->htab; a.cdesc = pl->cdesc;
+        a.hub_rows = pl->hub_rows; a.B = c.B; a.ldb = c.ldb; a.n = pl->n_rows; a.nnz = pl->nnz; a.hub_nnz = pl->hub_nnz;
+        a.n_chunks4 = c.n_feat / 4; a.T = pl->chunk_rows; a.n_chunks = pl->n_chunks; a.Kh = pl->n_hub;
+    a.Kv = pl->n_vslot; a.vmap = pl->vmap; a.vcnt = pl->vcnt;
+        a.hub_threshold = pl->hub_threshold; a.cap_doc = pl->cap_doc; a.cap_hub = pl->cap_hub;
+        a.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(c.workspace) + 15u) & ~(uintptr_t)15u);
+        a.ldp = (int64_t)((c.n_feat + 3) / 4) * 4;
+        a.n_slices = a.n_groups = 0;
+        const bool two = pl->n_vslot > kNThreads;
+#define TG_NARROW_CASE(NVv)                                                                   \
+        if (a.n_chunks4 == NVv) return two ? launch_narrow<NVv, 2>(pl, c, a, epi, st) : launch_narrow<NVv, 1>(pl, c, a, epi, st);
+        TG_NARROW_CASE(1) TG_NARROW_CASE(2) TG_NARROW_CASE(3) TG_NARROW_CASE(4)
+        TG_NARROW_CASE(5) TG_NARROW_CASE(6) TG_NARROW_CASE(7) TG_NARROW_CASE(8)
+#undef TG_NARROW_CASE
+    }
+    if (!whole_row && roles_applicable(pl, c.n_feat)) return run_roles(pl, c, epi, st);
     const int CPL = pick_cpl(pl, c.n_feat, whole_row);
     TG_REQUIRE(CPL != 0, TG_ERR_UNSUPPORTED, "streaming kernel not applicable");
     StreamArgs a;
@@ -416,11 +951,12 @@ static int run_stream(const tg_plan* pl, const StreamCall& c, const Epi& epi, bo
     a.hent = reinterpret_cast<const int2*>(pl->hcol); a.htab = pl->htab; a.cdesc = pl->cdesc;
     a.hub_rows = pl->hub_rows; a.B = c.B; a.ldb = c.ldb; a.n = pl->n_rows; a.nnz = pl->nnz; a.hub_nnz = pl->hub_nnz;
     a.n_chunks4 = c.n_feat / 4; a.T = pl->chunk_rows; a.n_chunks = pl->n_chunks; a.Kh = pl->n_hub;
+    a.Kv = pl->n_vslot; a.vmap = pl->vmap; a.vcnt = pl->vcnt;
     a.hub_threshold = pl->hub_threshold; a.cap_doc = pl->cap_doc; a.cap_hub = pl->cap_hub;
     a.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(c.workspace) + 15u) & ~(uintptr_t)15u);
     a.ldp = (int64_t)((c.n_feat + 3) / 4) * 4;
     a.n_slices = a.n_groups = 0;
-    const int kpg = (int)ceil_div64(pl->n_hub, kNG);
+    const int kpg = (int)ceil_div64(pl->n_vslot, kNG);
 #define TG_STREAM_CASE(CPLv)                                                        \
     if (CPL == CPLv) {                                                              \
         if (kpg <= 1) return launch_stream<CPLv, 1>(pl, c, a, epi, st);             \
@@ -471,14 +1007,18 @@ __global__ void reorder_rows_kernel(const int32_t* __restrict__ rowptr, const in
 
 // one block per hub row: key = chunk * Kh + slot for each of its entries, in storage (column) order
 __global__ void hub_keys_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                                const int32_t* __restrict__ hub_rows, const int64_t* __restrict__ hub_ofs, int Kh, int T,
+                                const int32_t* __restrict__ hub_rows, const int64_t* __restrict__ hub_ofs, int Kv, int T,
+                                const int32_t* __restrict__ vmap, const int32_t* __restrict__ vcnt,
                                 uint32_t* __restrict__ keys, int32_t* __restrict__ src) {
     const int k = blockIdx.x;
     const int r = hub_rows[k];
     const int s = rowptr[r], e = rowptr[r + 1];
     const int64_t o = hub_ofs[k];
+    const int nv = vcnt[k];
     for (int p = s + threadIdx.x; p < e; p += blockDim.x) {
-        keys[o + (p - s)] = (uint32_t)(colidx[p] / T) * (uint32_t)Kh + (uint32_t)k;
+        const int c = colidx[p];
+        // a heavy hub row is dealt over nv virtual slots by column residue: every slot sees every chunk
+        keys[o + (p - s)] = (uint32_t)(c / T) * (uint32_t)Kv + (uint32_t)vmap[k * 8 + (c % nv)];
         src[o + (p - s)] = p;
     }
 }
@@ -521,8 +1061,9 @@ __global__ void chunk_desc_kernel(const int32_t* __restrict__ rowptr, const int3
 void stream_plan_free(tg_plan* pl) {
     if (!pl) return;
     cudaFree(pl->colidx2); cudaFree(pl->hcol); cudaFree(pl->htab); cudaFree(pl->cdesc); cudaFree(pl->rsplit);
+    cudaFree(pl->vmap); cudaFree(pl->vcnt);
     pl->colidx2 = nullptr; pl->hcol = nullptr; pl->hval = nullptr; pl->htab = nullptr; pl->cdesc = nullptr;
-    pl->rsplit = nullptr;
+    pl->rsplit = nullptr; pl->vmap = nullptr; pl->vcnt = nullptr;
     pl->stream_ok = false;
 }
 
@@ -534,8 +1075,8 @@ int stream_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         return TG_OK;
     const int64_t n = pl->n_rows;
     const int Kh = pl->n_hub;
-    int T = env_int("TG_STREAM_CHUNK", 128);
-    if (T < 32 || T > 1024 || (T % 32) != 0) T = 128;
+    int T = env_int("TG_STREAM_CHUNK", 256);
+    if (T < 32 || T > 1024 || (T % 32) != 0) T = 256;
     const int n_chunks = (int)ceil_div64(n, T);
     if ((uint64_t)n_chunks * (uint64_t)Kh >= 0xFFFFFFFFull) return TG_OK;
     // only worth it when the hub rows carry a real share of the entries
@@ -555,6 +1096,43 @@ int stream_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     }
     const int64_t hub_nnz = run;
 
+    // ---- virtual hub slots: split heavy hub rows, then balance the 64 row groups of a CTA (longest first) ----------
+    // Group g of the wide kernels owns the slots {g + 64*kk}; the groups of a CTA meet at a barrier after every chunk,
+    // so the slowest group sets the pace.  Topic popularity is heavily skewed (a single topic can carry more than the
+    // average group's share), hence rows are first split by column residue until no piece exceeds 0.6 of the mean
+    // group load, and the pieces are then dealt to the groups with the LPT rule.
+    std::vector<int32_t> vcnt((size_t)Kh, 1), vmap((size_t)Kh * 8, 0);
+    int Kv = 0;
+    {
+        const double mean_load = (double)hub_nnz / kNG;
+        struct Piece { double w; int k, j; };
+        std::vector<Piece> pieces;
+        for (int k = 0; k < Kh; ++k) {
+            const double len = (double)(h_rowptr[(size_t)hub_rows[(size_t)k] + 1] - h_rowptr[(size_t)hub_rows[(size_t)k]]);
+            int nv = (int)(len / (0.6 * mean_load)) + 1;
+            if (nv > 8) nv = 8;
+            if (nv < 1) nv = 1;
+            vcnt[(size_t)k] = nv;
+            for (int j = 0; j < nv; ++j) pieces.push_back(Piece{len / nv, k, j});
+        }
+        int kpg = 1;
+        while (kpg * kNG < (int)pieces.size()) kpg *= 2;
+        if (kpg > 8) return TG_OK;  // too many hub rows for the streaming layout
+        Kv = kpg * kNG;
+        std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) { return x.w > y.w; });
+        std::vector<double> load((size_t)kNG, 0.0);
+        std::vector<int> used((size_t)kNG, 0);
+        for (const Piece& pc : pieces) {
+            int best = -1;
+            for (int g = 0; g < kNG; ++g)
+                if (used[(size_t)g] < kpg && (best < 0 || load[(size_t)g] < load[(size_t)best])) best = g;
+            vmap[(size_t)pc.k * 8 + pc.j] = best + kNG * used[(size_t)best];
+            used[(size_t)best] += 1;
+            load[(size_t)best] += pc.w;
+        }
+    }
+    if ((uint64_t)n_chunks * (uint64_t)Kv >= 0xFFFFFFFFull) return TG_OK;
+
     int32_t* d_slot = nullptr;
     int64_t* d_ofs = nullptr;
     uint32_t *keys_a = nullptr, *keys_b = nullptr;
@@ -571,6 +1149,10 @@ int stream_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     TG_TRY(cudaMemcpyAsync(d_slot, slot_of.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     TG_TRY(cudaMalloc((void**)&d_ofs, (size_t)Kh * sizeof(int64_t)));
     TG_TRY(cudaMemcpyAsync(d_ofs, hub_ofs.data(), (size_t)Kh * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    TG_TRY(cudaMalloc((void**)&pl->vmap, (size_t)Kh * 8 * sizeof(int32_t)));
+    TG_TRY(cudaMemcpyAsync(pl->vmap, vmap.data(), (size_t)Kh * 8 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    TG_TRY(cudaMalloc((void**)&pl->vcnt, (size_t)Kh * sizeof(int32_t)));
+    TG_TRY(cudaMemcpyAsync(pl->vcnt, vcnt.data(), (size_t)Kh * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     // +2 entries of padding so that the kernel's aligned 16-byte pair copies never leave the allocation
     TG_TRY(cudaMalloc((void**)&pl->colidx2, ((size_t)pl->nnz + 2) * sizeof(int2)));
     TG_TRY(cudaMemsetAsync(pl->colidx2, 0, ((size_t)pl->nnz + 2) * sizeof(int2), st));
@@ -582,32 +1164,33 @@ int stream_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     TG_TRY(cudaMalloc((void**)&keys_b, (size_t)hub_nnz * sizeof(uint32_t)));
     TG_TRY(cudaMalloc((void**)&src_a, (size_t)hub_nnz * sizeof(int32_t)));
     TG_TRY(cudaMalloc((void**)&src_b, (size_t)hub_nnz * sizeof(int32_t)));
-    hub_keys_kernel<<<Kh, 256, 0, st>>>(rowptr, colidx, pl->hub_rows, d_ofs, Kh, T, keys_a, src_a);
+    hub_keys_kernel<<<Kh, 256, 0, st>>>(rowptr, colidx, pl->hub_rows, d_ofs, Kv, T, pl->vmap, pl->vcnt, keys_a, src_a);
     TG_TRY(cudaGetLastError());
     size_t tmp_bytes = 0;
     int end_bit = 1;
-    while (end_bit < 32 && (1ull << end_bit) < (uint64_t)n_chunks * Kh) ++end_bit;
+    while (end_bit < 32 && (1ull << end_bit) < (uint64_t)n_chunks * Kv) ++end_bit;
     TG_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, src_a, src_b, (int)hub_nnz, 0, end_bit, st));
     TG_TRY(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
     // stable: inside a (chunk, hub) segment the entries keep their column order
     TG_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_a, keys_b, src_a, src_b, (int)hub_nnz, 0, end_bit, st));
     TG_TRY(cudaMalloc((void**)&pl->hcol, ((size_t)hub_nnz + 2) * sizeof(int2)));
     TG_TRY(cudaMemsetAsync(pl->hcol, 0, ((size_t)hub_nnz + 2) * sizeof(int2), st));
-    hub_gather_kernel<<<(unsigned)ceil_div64(hub_nnz, 256), 256, 0, st>>>(keys_b, src_b, colidx, vals, hub_nnz, Kh, T,
+    hub_gather_kernel<<<(unsigned)ceil_div64(hub_nnz, 256), 256, 0, st>>>(keys_b, src_b, colidx, vals, hub_nnz, Kv, T,
                                                                          reinterpret_cast<int2*>(pl->hcol));
     TG_TRY(cudaGetLastError());
-    TG_TRY(cudaMalloc((void**)&pl->htab, (size_t)n_chunks * (Kh + 1) * sizeof(int32_t)));
-    hub_table_kernel<<<(unsigned)ceil_div64((int64_t)n_chunks * (Kh + 1), 256), 256, 0, st>>>(keys_b, hub_nnz, n_chunks, Kh,
+    TG_TRY(cudaMalloc((void**)&pl->htab, (size_t)n_chunks * (Kv + 1) * sizeof(int32_t)));
+    hub_table_kernel<<<(unsigned)ceil_div64((int64_t)n_chunks * (Kv + 1), 256), 256, 0, st>>>(keys_b, hub_nnz, n_chunks, Kv,
                                                                                               pl->htab);
     TG_TRY(cudaGetLastError());
     TG_TRY(cudaMalloc((void**)&pl->cdesc, (size_t)n_chunks * sizeof(int4)));
-    chunk_desc_kernel<<<(unsigned)ceil_div64(n_chunks, 256), 256, 0, st>>>(rowptr, pl->htab, n, T, n_chunks, Kh, pl->cdesc);
+    chunk_desc_kernel<<<(unsigned)ceil_div64(n_chunks, 256), 256, 0, st>>>(rowptr, pl->htab, n, T, n_chunks, Kv, pl->cdesc);
     TG_TRY(cudaGetLastError());
     TG_TRY(cudaStreamSynchronize(st));
 #undef TG_TRY
     cudaFree(d_slot); cudaFree(d_ofs); cudaFree(keys_a); cudaFree(keys_b); cudaFree(src_a); cudaFree(src_b); cudaFree(tmp);
     pl->chunk_rows = T;
     pl->n_chunks = n_chunks;
+    pl->n_vslot = Kv;
     // staged entry windows: average occupancy of a chunk plus slack (rows beyond the window take the L2 path)
     const int64_t avg_doc = ceil_div64(pl->nnz - hub_nnz, n_chunks), avg_hub = ceil_div64(hub_nnz, n_chunks);
     pl->cap_doc = (int32_t)(((avg_doc + avg_doc / 4 + 64) + 1) & ~(int64_t)1);
