@@ -869,7 +869,7 @@ static size_t narrow_smem_bytes(const tg_plan* pl, int n_feat) {
 }
 
 static bool narrow_applicable(const tg_plan* pl, int n_feat) {
-    return env_int("TG_STREAM_NARROW", 1) != 0 && n_feat <= 32 && n_feat % 4 == 0 && pl->n_vslot <= 2 * kNThreads &&
+    return env_int("TG_STREAM_NARROW", 0) != 0 && n_feat <= 32 && n_feat % 4 == 0 && pl->n_vslot <= 2 * kNThreads &&
            narrow_smem_bytes(pl, n_feat) <= kSmemBudget;
 }
 
@@ -878,6 +878,10 @@ bool stream_applicable(const tg_plan* pl, const StreamCall& c, bool out_vec4_ok,
     if (!(c.n_feat % 4 == 0 && c.ldb % 4 == 0 && aligned16(c.B) && out_vec4_ok)) return false;
     if (c.n_feat > 1024) return false;
     if (narrow_applicable(pl, c.n_feat)) return true;
+    // rows of <= 32 columns: at the single-GPU sizes B (N x F x 4 B, 80 MB at C3) stays in L2 and the gather kernel
+    // (tg_spmm.cu, 8 lanes per row) is faster than streaming; TG_STREAM_NARROW=1 selects the lane-per-row streaming
+    // kernel, which keeps DRAM traffic at the algorithmic minimum when B outgrows L2.
+    if (c.n_feat <= 32 && env_int("TG_STREAM_NARROW", 0) == 0) return false;
     return pick_cpl(pl, c.n_feat, whole_row) != 0;
 }
 

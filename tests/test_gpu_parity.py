@@ -160,6 +160,22 @@ def test_spmm_deterministic_and_split_rows(tg, streaming):
     assert rel_err(y[nd:], ref[nd:]) <= max(SPMM_RTOL, 2 * e_ref)
 
 
+def test_narrow_streaming_kernel_env_knob(tg, small_golden, monkeypatch):
+    """TG_STREAM_NARROW=1 routes F <= 32 through the lane-per-row streaming kernel (default: gather kernel)."""
+    coo = golden_adj(small_golden)
+    csr = to_csr(tg, coo, hub_threshold=16, segment_nnz=8)
+    assert csr.streaming
+    rng = np.random.default_rng(0)
+    for F in (8, 20, 32):
+        B = rng.normal(size=(coo.shape[1], F)).astype(np.float32)
+        ref = O.spmm(coo, B)
+        monkeypatch.setenv("TG_STREAM_NARROW", "1")
+        y1 = tg.spmm(csr, torch.tensor(B, device=dev())).cpu().numpy()
+        monkeypatch.setenv("TG_STREAM_NARROW", "0")
+        y0 = tg.spmm(csr, torch.tensor(B, device=dev())).cpu().numpy()
+        assert rel_err(y1, ref) <= SPMM_RTOL and rel_err(y0, ref) <= SPMM_RTOL
+
+
 def test_spmm_textgcn_skew(tg):
     """C5: power-law word rows (median ~200, max ~1.5e4 entries) - every row class of the plan in one graph."""
     from topicgcn_b200 import graphgen
