@@ -18,6 +18,7 @@
 // small finishing kernel that also applies the epilogue.  Every floating-point addition has a fixed order: the
 // result is bitwise reproducible (no float atomics).  Data movement global->shared uses cp.async double buffering.
 #include <cub/cub.cuh>
+#include <cuda.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -31,6 +32,7 @@ constexpr int kSThreads = 512;
 constexpr int kGW = 8;                    // lanes per row group: a quarter warp reads one 128-byte line of a row slice
 constexpr int kNG = kSThreads / kGW;      // row groups per CTA
 constexpr int kMaxHubStream = 512;
+constexpr int kHtabPad = 4;               // htab rows hold Kv + 1 offsets, padded to Kv + 4 ints (16-byte aligned rows)
 constexpr size_t kSmemBudget = 227 * 1024;
 
 struct StreamArgs {
@@ -72,6 +74,46 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+
+// ---- TMA (bulk async copy) + mbarrier helpers: one elected thread moves a whole stage -----------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 2-D tile [box rows x box cols] of a row-major matrix described by a tensor map -> shared memory (zero fill outside)
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int col, int row, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(col), "r"(row), "r"(smem_u32(bar))
+        : "memory");
+}
+// contiguous run global -> shared memory (16-byte aligned, size multiple of 16)
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__host__ __device__ inline size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
 
 struct StageView {
     float* Bs;       // [T][FT]
@@ -174,7 +216,7 @@ __global__ void __launch_bounds__(kSThreads, 1) stream_spmm_kernel(const StreamA
             cp_async16(sv.hent + 2 * idx, ok ? a.hent + p : a.hent, ok);
         }
         for (int idx = tid; idx <= a.Kv; idx += kSThreads)
-            cp_async4(sv.htab + idx, a.htab + (int64_t)c * (a.Kv + 1) + idx, true);
+            cp_async4(sv.htab + idx, a.htab + (int64_t)c * (a.Kv + kHtabPad) + idx, true);
     };
 
     Chunk<4> hacc[KPG][CPL];
@@ -326,13 +368,18 @@ struct RolesArgs {
     int32_t doc_job_rows;           // rows per doc-role job
     int32_t n_doc_jobs;
     int32_t only_role;              // debugging/profiling knob: 1 = hub CTAs only, 2 = document CTAs only, 0 = both
+    int32_t use_tma;                // hub role: stage chunks with TMA bulk copies + mbarrier instead of cp.async
 };
 
 template <int THREADS, int CPLD, int KPG, class Epi>
-__global__ void __launch_bounds__(THREADS, 1) stream_roles_kernel(const RolesArgs ra, const Epi epi) {
+__global__ void __launch_bounds__(THREADS, 1) stream_roles_kernel(const RolesArgs ra, const Epi epi,
+                                                                  const __grid_constant__ CUtensorMap tmapB) {
     const StreamArgs& a = ra.s;
     constexpr int NGr = THREADS / kGW;  // row groups per CTA
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    // TMA destinations must be 128-byte aligned: align the dynamic base by hand (the launch requests 128 spare bytes)
+    unsigned char* smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int gl = lane & (kGW - 1);
@@ -348,32 +395,31 @@ __global__ void __launch_bounds__(THREADS, 1) stream_roles_kernel(const RolesArg
         const int slice = blockIdx.x % ra.hub_slices;
         const int hl = blockIdx.x / ra.hub_slices;
         const int q0 = slice * QS + gl;
-        const size_t st_bytes = align16((size_t)a.T * FT * 4) + align16((size_t)a.cap_hub * 8) + align16((size_t)(a.Kv + 1) * 4);
+        const size_t bs_bytes = align128((size_t)a.T * FT * 4), he_bytes = align128((size_t)a.cap_hub * 8);
+        const size_t st_bytes = bs_bytes + he_bytes + align128((size_t)(a.Kv + kHtabPad) * 4);
         auto Bs_at = [&](int buf) { return reinterpret_cast<float*>(smem_raw + (size_t)buf * st_bytes); };
-        auto he_at = [&](int buf) { return reinterpret_cast<int2*>(smem_raw + (size_t)buf * st_bytes + align16((size_t)a.T * FT * 4)); };
-        auto ht_at = [&](int buf) {
-            return reinterpret_cast<int32_t*>(smem_raw + (size_t)buf * st_bytes + align16((size_t)a.T * FT * 4) +
-                                              align16((size_t)a.cap_hub * 8));
-        };
+        auto he_at = [&](int buf) { return reinterpret_cast<int2*>(smem_raw + (size_t)buf * st_bytes + bs_bytes); };
+        auto ht_at = [&](int buf) { return reinterpret_cast<int32_t*>(smem_raw + (size_t)buf * st_bytes + bs_bytes + he_bytes); };
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        // One thread moves a whole stage: a 2-D TMA tile of B (T rows x 64 columns, zero filled past the matrix), the
+        // chunk's contiguous run of hub entries and its offset-table row; the stage's mbarrier counts the bytes.
         auto issue = [&](int buf, int c, const int4 d) {
-            const int64_t c0 = (int64_t)c * a.T;
-            float* Bs = Bs_at(buf);
-            for (int idx = tid; idx < a.T * QS; idx += THREADS) {
-                const int r = idx / QS, q = idx % QS;
-                const int64_t row = c0 + r;
-                const bool ok = row < a.n && (slice * QS + q) < a.n_chunks4;
-                cp_async16(Bs + r * FT + q * 4, ok ? a.B + row * a.ldb + (int64_t)(slice * QS + q) * 4 : a.B, ok);
-            }
-            int2* he = he_at(buf);
-            const int64_t h0 = d.z & ~1;
-            for (int idx = tid; idx < a.cap_hub / 2; idx += THREADS) {
-                const int64_t p = h0 + 2 * idx;
-                const bool ok = p < d.w;
-                cp_async16(he + 2 * idx, ok ? a.hent + p : a.hent, ok);
-            }
-            int32_t* ht = ht_at(buf);
-            for (int idx = tid; idx <= a.Kv; idx += THREADS)
-                cp_async4(ht + idx, a.htab + (int64_t)c * (a.Kv + 1) + idx, true);
+            if (tid != 0) return;
+            const int h0 = d.z & ~1;
+            int n_e = d.w - h0;
+            n_e = n_e < 0 ? 0 : (n_e > a.cap_hub ? a.cap_hub : n_e);
+            n_e = (n_e + 1) & ~1;
+            const unsigned ht_b = (unsigned)((a.Kv + kHtabPad) * 4);
+            fence_proxy_async();  // the buffer was last read through the generic proxy (ordered by the block barrier)
+            mbar_expect_tx(&mbar[buf], (unsigned)(a.T * FT * 4) + (unsigned)n_e * 8u + ht_b);
+            tma_load_2d(Bs_at(buf), &tmapB, slice * FT, c * a.T, &mbar[buf]);
+            if (n_e) bulk_load_1d(he_at(buf), a.hent + h0, (unsigned)n_e * 8u, &mbar[buf]);
+            bulk_load_1d(ht_at(buf), a.htab + (int64_t)c * (a.Kv + kHtabPad), ht_b, &mbar[buf]);
         };
         Chunk<4> hacc[KPG][CPL];
 #pragma unroll
@@ -384,19 +430,12 @@ __global__ void __launch_bounds__(THREADS, 1) stream_roles_kernel(const RolesArg
         if (c < a.n_chunks) {
             int4 d_cur = __ldg(a.cdesc + c);
             issue(0, c, d_cur);
-            cp_async_commit();
             int4 d_next = (c + ra.hub_lanes < a.n_chunks) ? __ldg(a.cdesc + c + ra.hub_lanes) : make_int4(0, 0, 0, 0);
             for (int it = 0; c < a.n_chunks; c += ra.hub_lanes, ++it) {
                 const int buf = it & 1;
                 const int cn = c + ra.hub_lanes;
-                if (cn < a.n_chunks) {
-                    issue(buf ^ 1, cn, d_next);
-                    cp_async_commit();
-                    cp_async_wait<1>();
-                } else {
-                    cp_async_wait<0>();
-                }
-                __syncthreads();
+                if (cn < a.n_chunks) issue(buf ^ 1, cn, d_next);
+                mbar_wait(&mbar[buf], (unsigned)(it >> 1) & 1u);  // every thread observes the stage's bytes itself
                 const int4 d_new = (cn + ra.hub_lanes < a.n_chunks) ? __ldg(a.cdesc + cn + ra.hub_lanes) : make_int4(0, 0, 0, 0);
                 const float* Bs = Bs_at(buf);
                 const int2* he = he_at(buf);
@@ -579,7 +618,7 @@ __global__ void __launch_bounds__(kNThreads) stream_narrow_kernel(const StreamAr
             cp_async16(sv.hent + 2 * idx, ok ? a.hent + p : a.hent, ok);
         }
         for (int idx = tid; idx <= a.Kv; idx += kNThreads)
-            cp_async4(sv.htab + idx, a.htab + (int64_t)c * (a.Kv + 1) + idx, true);
+            cp_async4(sv.htab + idx, a.htab + (int64_t)c * (a.Kv + kHtabPad) + idx, true);
     };
 
     Chunk<4> hacc[KPT][NV];
@@ -780,15 +819,52 @@ static int pick_cpl(const tg_plan* pl, int n_feat, bool whole_row) {
 }
 
 // ---- role-specialised launch -------------------------------------------------------------------------------------------
+static inline bool epi_runs_rng(const EpiStore& e) { return e.drop_mode == 1; }
+static inline bool epi_runs_rng(const EpiLoss&) { return false; }
+
 static size_t roles_hub_smem(const tg_plan* pl) {
-    return 2 * (align16((size_t)pl->chunk_rows * 64 * 4) + align16((size_t)pl->cap_hub * 8) + align16((size_t)(pl->n_vslot + 1) * 4));
+    return 2 * (align128((size_t)pl->chunk_rows * 64 * 4) + align128((size_t)pl->cap_hub * 8) +
+                align128((size_t)(pl->n_vslot + kHtabPad) * 4));
+}
+
+// ---- tensor map for the TMA tile loads of B (driver entry point fetched at run time: no libcuda link dependency) ----
+typedef CUresult (*tg_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static tg_encode_tiled_fn encode_tiled_fn() {
+    static tg_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tg_encode_tiled_fn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// [rows x cols] fp32 row-major with leading dimension ldb, tiles of box_rows x 64 columns, no swizzle, zero OOB fill
+static bool make_tensor_map(CUtensorMap* map, const float* B, int64_t rows, int64_t cols, int64_t ldb, int box_rows) {
+    tg_encode_tiled_fn fn = encode_tiled_fn();
+    if (!fn || box_rows > 256 || (ldb * 4) % 16 != 0) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ldb * 4};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(B), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 static size_t roles_doc_smem(const tg_plan* pl, int CPLD) { return align16((size_t)pl->n_hub * 32 * CPLD * 4); }
 
 static int roles_cpld(const tg_plan* pl, int n_feat) {
     for (int CPLD = 4; CPLD >= 2; CPLD -= 2) {
         if (n_feat < 32 * CPLD && CPLD > 2) continue;
-        if (roles_doc_smem(pl, CPLD) <= kSmemBudget) return CPLD;
+        if (roles_doc_smem(pl, CPLD) + 128 <= kSmemBudget) return CPLD;
     }
     return 0;
 }
@@ -796,7 +872,8 @@ static int roles_cpld(const tg_plan* pl, int n_feat) {
 static bool roles_applicable(const tg_plan* pl, int n_feat) {
     if (env_int("TG_STREAM_ROLES", 1) == 0) return false;
     if (n_feat < 64 || n_feat % 4 != 0) return false;
-    if (roles_hub_smem(pl) > kSmemBudget || pl->n_vslot > kNG * 8) return false;
+    if (!encode_tiled_fn() || pl->chunk_rows > 256) return false;  // the hub role stages B with TMA tiles
+    if (roles_hub_smem(pl) + 128 > kSmemBudget || pl->n_vslot > kNG * 8) return false;
     return roles_cpld(pl, n_feat) != 0;
 }
 
@@ -804,12 +881,14 @@ template <int THREADS, int CPLD, int KPG, class Epi>
 static int launch_roles(const tg_plan* pl, const StreamCall& c, RolesArgs ra, const Epi& epi, cudaStream_t st) {
     size_t smem = roles_hub_smem(pl);
     if (roles_doc_smem(pl, CPLD) > smem) smem = roles_doc_smem(pl, CPLD);
+    smem += 128;  // slack for the in-kernel 128-byte alignment of the dynamic base
     TG_CUDA(cudaFuncSetAttribute(stream_roles_kernel<THREADS, CPLD, KPG, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StreamArgs& a = ra.s;
     ra.hub_slices = (int)ceil_div64(a.n_chunks4, 16);
     ra.doc_slices = (int)ceil_div64(a.n_chunks4, 8 * CPLD);
-    // share of the SMs given to the hub role (per-node work of the two roles is roughly 55:45)
-    const int hub_pct = env_int("TG_ROLES_HUB_PCT", 55);
+    // share of the SMs given to the hub role: measured balance point on the 1M x 256 graph is 18 hub lanes x 4 slices
+    // (72 SMs) without dropout and 16 (64 SMs) when the document role also runs the Philox dropout epilogue
+    const int hub_pct = env_int("TG_ROLES_HUB_PCT", epi_runs_rng(epi) ? 45 : 50);
     int hub_lanes = (kNumSM * hub_pct / 100) / ra.hub_slices;
     if (hub_lanes < 1) hub_lanes = 1;
     int doc_lanes = (kNumSM - hub_lanes * ra.hub_slices) / ra.doc_slices;
@@ -819,13 +898,18 @@ static int launch_roles(const tg_plan* pl, const StreamCall& c, RolesArgs ra, co
     ra.doc_lanes = doc_lanes;
     ra.doc_job_rows = 256;
     ra.only_role = env_int("TG_ROLES_ONLY", 0);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    ra.use_tma = 1;
+    TG_REQUIRE(make_tensor_map(&tmap, a.B, a.n, c.n_feat, a.ldb, a.T), TG_ERR_UNSUPPORTED,
+               "cuTensorMapEncodeTiled failed (TMA tile of the dense operand)");
     ra.n_doc_jobs = (int)ceil_div64(a.n, ra.doc_job_rows);
     a.n_groups = hub_lanes;
     const size_t need = (size_t)hub_lanes * pl->n_vslot * a.ldp * sizeof(float);
     TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
                c.workspace_bytes, need + 16);
     const unsigned grid = (unsigned)(ra.hub_slices * hub_lanes + ra.doc_slices * doc_lanes);
-    stream_roles_kernel<THREADS, CPLD, KPG, Epi><<<grid, THREADS, smem, st>>>(ra, epi);
+    stream_roles_kernel<THREADS, CPLD, KPG, Epi><<<grid, THREADS, smem, st>>>(ra, epi, tmap);
     TG_LAUNCH_CHECK();
     return finish_dispatch(a, a.partials, hub_lanes, epi, st);
 }
@@ -1041,8 +1125,10 @@ __global__ void hub_gather_kernel(const uint32_t* __restrict__ keys, const int32
 __global__ void hub_table_kernel(const uint32_t* __restrict__ keys, int64_t hub_nnz, int n_chunks, int Kh,
                                  int32_t* __restrict__ htab) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)n_chunks * (Kh + 1)) return;
-    const int c = (int)(i / (Kh + 1)), k = (int)(i % (Kh + 1));
+    if (i >= (int64_t)n_chunks * (Kh + kHtabPad)) return;
+    const int c = (int)(i / (Kh + kHtabPad));
+    int k = (int)(i % (Kh + kHtabPad));
+    if (k > Kh) k = Kh;  // padding entries repeat the end offset
     const uint64_t want = (uint64_t)c * Kh + k;
     int64_t lo = 0, hi = hub_nnz;
     while (lo < hi) {
@@ -1059,7 +1145,7 @@ __global__ void chunk_desc_kernel(const int32_t* __restrict__ rowptr, const int3
     if (c >= n_chunks) return;
     const int64_t r0 = (int64_t)c * T;
     const int64_t r1 = (r0 + T < n) ? r0 + T : n;
-    cdesc[c] = make_int4(rowptr[r0], rowptr[r1], htab[(int64_t)c * (Kh + 1)], htab[(int64_t)c * (Kh + 1) + Kh]);
+    cdesc[c] = make_int4(rowptr[r0], rowptr[r1], htab[(int64_t)c * (Kh + kHtabPad)], htab[(int64_t)c * (Kh + kHtabPad) + Kh]);
 }
 
 void stream_plan_free(tg_plan* pl) {
@@ -1182,8 +1268,8 @@ int stream_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     hub_gather_kernel<<<(unsigned)ceil_div64(hub_nnz, 256), 256, 0, st>>>(keys_b, src_b, colidx, vals, hub_nnz, Kv, T,
                                                                          reinterpret_cast<int2*>(pl->hcol));
     TG_TRY(cudaGetLastError());
-    TG_TRY(cudaMalloc((void**)&pl->htab, (size_t)n_chunks * (Kv + 1) * sizeof(int32_t)));
-    hub_table_kernel<<<(unsigned)ceil_div64((int64_t)n_chunks * (Kv + 1), 256), 256, 0, st>>>(keys_b, hub_nnz, n_chunks, Kv,
+    TG_TRY(cudaMalloc((void**)&pl->htab, (size_t)n_chunks * (Kv + kHtabPad) * sizeof(int32_t)));
+    hub_table_kernel<<<(unsigned)ceil_div64((int64_t)n_chunks * (Kv + kHtabPad), 256), 256, 0, st>>>(keys_b, hub_nnz, n_chunks, Kv,
                                                                                               pl->htab);
     TG_TRY(cudaGetLastError());
     TG_TRY(cudaMalloc((void**)&pl->cdesc, (size_t)n_chunks * sizeof(int4)));
