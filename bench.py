@@ -356,10 +356,16 @@ def run_ours(args):
         tot_bytes = sum(v["algorithmic_GB"] * v["launches"] for _, v in dom)
         n_l = sum(v["launches"] for _, v in dom)
         achieved = tot_bytes * 1e3 / tot_ms
-        kname = (f"stream_spmm_kernel<CPL=2,EpiStore> + stream_finish_kernel (column-chunk streaming SpMM, F={hidden})"
+        kname = (f"stream_roles_kernel<512,4,KPG,EpiStore> + stream_finish_kernel (role-specialised column-chunk streaming "
+                 f"SpMM with TMA-staged chunks, F={hidden})"
                  if csr.streaming else f"spmm_kernel<4,32,{(hidden // 4 + 31) // 32},EpiStore> (gather SpMM, F={hidden})")
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if csr.streaming and world == 1 and os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(name)  # dram bytes per launch from the committed ncu --set full capture
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": kname,
+                "traffic": traffic, "kernel": kname,
                 "launches_timed": n_l, "avg_launch_ms": tot_ms / n_l, "algorithmic_bytes_per_launch": tot_bytes * 1e9 / n_l,
                 "share_of_step": tot_ms / (ms_step * args.steps), "peak_source": peak_src,
                 "frac_of_nominal_8TBps": achieved / 8000.0,

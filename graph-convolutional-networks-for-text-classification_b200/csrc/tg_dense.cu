@@ -269,8 +269,18 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
     const int64_t r_end = min(n, r_begin + rows_per_block);
     for (int c0 = 0; c0 < c; c0 += cw) {
         float s = 0.f;
-        if (c0 + col < c)
-            for (int64_t r = r_begin + rl; r < r_end; r += rstep) s += __ldg(X + r * ldx + c0 + col);
+        if (c0 + col < c) {
+            // 8 independent loads in flight, added in a fixed order
+            int64_t r = r_begin + rl;
+            for (; r + 7 * (int64_t)rstep < r_end; r += 8 * (int64_t)rstep) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(X + (r + (int64_t)u * rstep) * ldx + c0 + col);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += v[u];
+            }
+            for (; r < r_end; r += rstep) s += __ldg(X + r * ldx + c0 + col);
+        }
         sh[t] = s;
         __syncthreads();
         if (rl == 0 && c0 + col < c) {

@@ -86,6 +86,7 @@ struct EpiStore {
     uint64_t seed, offset;
     int32_t n_feat;
     int64_t raw_row_begin;  // rows >= raw_row_begin are stored as plain sums (document-sharded mode), INT64_MAX = none
+    const float* out_scale; // optional DEVICE scalar multiplied into every output element (autograd upstream gradient)
 
     template <int VEC, int G, int CPL>
     __device__ __forceinline__ void apply(int64_t row, int gl, unsigned gmask, int n_chunks,
@@ -113,6 +114,11 @@ struct EpiStore {
             if (relu) {
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) y.v[k] = fmaxf(y.v[k], 0.f);
+            }
+            if (out_scale) {
+                const float g = __ldg(out_scale);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) y.v[k] *= g;
             }
             if (drop_mode == 1) {
                 if (VEC == 4) {

@@ -298,14 +298,14 @@ extern "C" {
 
 int tg_spmm_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                 const float* B, int64_t ldb, float* Y, int64_t ldy, int32_t n_feat, const float* bias,
-                void* workspace, size_t workspace_bytes, void* stream) {
+                const float* out_scale, void* workspace, size_t workspace_bytes, void* stream) {
     using namespace tg;
     TG_REQUIRE(Y, TG_ERR_INVALID_ARG, "null output");
     TG_REQUIRE(ldy >= n_feat, TG_ERR_INVALID_ARG, "ldy < n_feat");
     EpiStore epi{};
     epi.Y = Y; epi.ldy = ldy; epi.bias = bias; epi.relu = 0; epi.drop_mode = 0; epi.keep_mask = nullptr;
     epi.keep_thr = 0; epi.scale = 1.f; epi.seed = 0; epi.offset = 0; epi.n_feat = n_feat;
-    epi.raw_row_begin = INT64_MAX;
+    epi.raw_row_begin = INT64_MAX; epi.out_scale = out_scale;
     const bool ok4 = (ldy % 4 == 0) && aligned16(Y) && (!bias || aligned16(bias));
     return run_spmm(plan, rowptr, colidx, vals, B, ldb, n_feat, ok4, epi, workspace, workspace_bytes,
                     as_stream(stream));
@@ -323,6 +323,7 @@ int tg_gc1_fwd_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* co
     epi.Y = H1; epi.ldy = ldh; epi.bias = bias; epi.relu = 1; epi.n_feat = n_feat;
     epi.seed = seed; epi.offset = offset; epi.keep_mask = keep_mask;
     epi.raw_row_begin = raw_row_begin < 0 ? INT64_MAX : raw_row_begin;
+    epi.out_scale = nullptr;
     const bool drop = training && p > 0.f;
     epi.drop_mode = !drop ? 0 : (keep_mask ? 2 : 1);
     epi.keep_thr = dropout_keep_threshold(p);

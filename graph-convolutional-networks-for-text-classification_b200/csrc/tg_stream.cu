@@ -1189,22 +1189,31 @@ int stream_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     // ---- virtual hub slots: split heavy hub rows, then balance the 64 row groups of a CTA (longest first) ----------
     // Group g of the wide kernels owns the slots {g + 64*kk}; the groups of a CTA meet at a barrier after every chunk,
     // so the slowest group sets the pace.  Topic popularity is heavily skewed (a single topic can carry more than the
-    // average group's share), hence rows are first split by column residue until no piece exceeds 0.6 of the mean
-    // group load, and the pieces are then dealt to the groups with the LPT rule.
+    // average group's share), hence the heaviest rows are split by column residue into the spare accumulator slots, and
+    // the pieces are then dealt to the groups with the LPT rule.
     std::vector<int32_t> vcnt((size_t)Kh, 1), vmap((size_t)Kh * 8, 0);
     int Kv = 0;
     {
-        const double mean_load = (double)hub_nnz / kNG;
         struct Piece { double w; int k, j; };
         std::vector<Piece> pieces;
-        for (int k = 0; k < Kh; ++k) {
-            const double len = (double)(h_rowptr[(size_t)hub_rows[(size_t)k] + 1] - h_rowptr[(size_t)hub_rows[(size_t)k]]);
-            int nv = (int)(len / (0.6 * mean_load)) + 1;
-            if (nv > 8) nv = 8;
-            if (nv < 1) nv = 1;
-            vcnt[(size_t)k] = nv;
-            for (int j = 0; j < nv; ++j) pieces.push_back(Piece{len / nv, k, j});
+        std::vector<double> len((size_t)Kh);
+        for (int k = 0; k < Kh; ++k)
+            len[(size_t)k] = (double)(h_rowptr[(size_t)hub_rows[(size_t)k] + 1] - h_rowptr[(size_t)hub_rows[(size_t)k]]);
+        // slots are free: 64 groups x (smallest power of two >= Kh/64) accumulators; every spare slot is spent on
+        // halving (then thirding, ...) whichever hub row currently has the heaviest pieces
+        int kpg0 = 1;
+        while (kpg0 * kNG < Kh) kpg0 *= 2;
+        int spare = kpg0 * kNG - Kh;
+        while (spare > 0) {
+            int best = -1;
+            for (int k = 0; k < Kh; ++k)
+                if (vcnt[(size_t)k] < 8 && (best < 0 || len[(size_t)k] / vcnt[(size_t)k] > len[(size_t)best] / vcnt[(size_t)best])) best = k;
+            if (best < 0) break;
+            vcnt[(size_t)best] += 1;
+            --spare;
         }
+        for (int k = 0; k < Kh; ++k)
+            for (int j = 0; j < vcnt[(size_t)k]; ++j) pieces.push_back(Piece{len[(size_t)k] / vcnt[(size_t)k], k, j});
         int kpg = 1;
         while (kpg * kNG < (int)pieces.size()) kpg *= 2;
         if (kpg > 8) return TG_OK;  // too many hub rows for the streaming layout

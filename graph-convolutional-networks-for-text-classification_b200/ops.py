@@ -88,8 +88,8 @@ def _stream() -> int:
 # 1:1 wrappers
 # ---------------------------------------------------------------------------------------------------------------
 def spmm(csr: DeviceCSR, B: torch.Tensor, bias: Optional[torch.Tensor] = None,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Y = A @ B (+ bias): tg_spmm_f32."""
+         out: Optional[torch.Tensor] = None, out_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Y = (A @ B (+ bias)) * out_scale: tg_spmm_f32.  out_scale is an optional 0-dim CUDA tensor (no host sync)."""
     B = _dense2d(B, "B")
     if B.shape[0] != csr.n_cols:
         raise N.TopicGCNError(f"shape mismatch: A is {csr.n_rows}x{csr.n_cols}, B has {B.shape[0]} rows")
@@ -100,7 +100,8 @@ def spmm(csr: DeviceCSR, B: torch.Tensor, bias: Optional[torch.Tensor] = None,
     ws, ws_bytes = csr.workspace(F)
     with torch.cuda.device(B.device), _call("spmm", 1, n_feat=F, csr=csr):
         N.check(N.lib().tg_spmm_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(B), _ld(B),
-                                    N.ptr(out), _ld(out), F, N.ptr(bias), ws, ws_bytes, _stream()), "tg_spmm_f32")
+                                    N.ptr(out), _ld(out), F, N.ptr(bias), N.ptr(out_scale), ws, ws_bytes, _stream()),
+                "tg_spmm_f32")
     return out
 
 
@@ -351,10 +352,12 @@ class GCNLossFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss, _dlogits):
         H1, W2, dZ2 = ctx.saved_tensors
-        dZ2 = dZ2 * dloss  # dloss is a device scalar (1.0 for loss.backward()); no host sync
+        # dloss is a device scalar (1.0 for loss.backward()): it is folded into dS2 = (A^T dZ2) * dloss by the SpMM
+        # epilogue and into db2 on 20 elements — no pass over the [N x C] gradient, no host sync
+        g = dloss.reshape(()).to(torch.float32).contiguous()
         csr_t = ctx.csr.transpose()
-        db2 = colsum(dZ2) if ctx.has_b2 else None
-        dS2 = spmm(csr_t, dZ2)
+        db2 = colsum(dZ2) * g if ctx.has_b2 else None
+        dS2 = spmm(csr_t, dZ2, out_scale=g)
         dZ1, dW2, db1 = hidden_backward(H1, dS2, W2, ctx.scale)
         dS1 = spmm(csr_t, dZ1) if ctx.needs_input_grad[0] else None
         return dS1, (db1 if ctx.has_b1 else None), dW2, db2, None, None, None, None, None, None, None, None, None

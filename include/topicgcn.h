@@ -95,11 +95,12 @@ size_t tg_plan_workspace_bytes(const tg_plan* plan, int32_t n_feat);
 /* ------------------------------------------------------------------------------------------------
  * Y[n_rows x F] = A_csr * B[n_cols x F]  (+ bias)            replaces layer.py:106 (+ :109-110)
  * Same call with the transposed CSR (or the same CSR when symmetric) is the backward dS = A^T dZ.
- * bias may be NULL.
+ * bias may be NULL.  out_scale: optional DEVICE scalar multiplied into the result (the upstream gradient of a scalar
+ * loss in the backward pass, so that no separate scaling pass over dZ is needed); NULL = 1.
  * ---------------------------------------------------------------------------------------------- */
 int tg_spmm_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                 const float* B, int64_t ldb, float* Y, int64_t ldy, int32_t n_feat, const float* bias,
-                void* workspace, size_t workspace_bytes, void* stream);
+                const float* out_scale, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Layer-1 fused forward:  H1 = dropout(relu(A*S + b1), p)   replaces layer.py:106,109-110,182,185
