@@ -45,8 +45,8 @@ class DeviceCSR:
         self._plan = C.c_void_p()
         self._streaming_requested = bool(streaming)
         with torch.cuda.device(self.device):
-            # colidx/vals = NULL -> no column-chunk streaming layout (gather kernel only)
-            N.check(N.lib().tg_plan_create(N.ptr(rowptr), N.ptr(colidx) if streaming else 0,
+            # vals = NULL -> no column-chunk streaming layout (gather kernel only; colidx still orders its segments)
+            N.check(N.lib().tg_plan_create(N.ptr(rowptr), N.ptr(colidx),
                                            N.ptr(vals) if streaming else 0, self.n_rows, self.n_cols, self.nnz,
                                            self._hub_threshold, self._segment_nnz, C.byref(self._plan),
                                            N.current_stream_ptr()), "tg_plan_create")

@@ -49,6 +49,7 @@ struct tg_plan {
     int32_t* seg_begin = nullptr;    // [n_seg]   first stored entry of the segment
     int32_t* seg_end = nullptr;      // [n_seg]   one past the last stored entry
     uint32_t* tickets = nullptr;     // [n_hub]   arrival counters (integer; reset by the last arriver)
+    int32_t* seg_order = nullptr;    // [n_seg]   execution order: segments sorted by their first column (L2 reuse of B)
 
     // ---- column-chunk streaming sub-plan (tg_stream.cu); present when the hub set is compact -------------------
     bool stream_ok = false;

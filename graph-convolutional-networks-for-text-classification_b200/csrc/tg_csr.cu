@@ -6,6 +6,7 @@
 // row-major sorted and duplicate free, so the common case is a sort-free pass; arbitrary COO input gets
 // coalesce() semantics (stable radix sort on (row, col), duplicates summed in input order).
 #include <cub/cub.cuh>
+#include <algorithm>
 #include <vector>
 
 #include "tg_stream.cuh"
@@ -103,6 +104,12 @@ __global__ void compare_csr_kernel(const int32_t* __restrict__ a_ptr, const int3
     if (i < n_ptr && a_ptr[i] != b_ptr[i]) bad = true;
     if (i < nnz && (a_col[i] != b_col[i] || __float_as_uint(a_val[i]) != __float_as_uint(b_val[i]))) bad = true;
     if (bad) atomicOr(flags, kFlagMismatch);
+}
+
+__global__ void seg_first_col_kernel(const int32_t* __restrict__ colidx, const int32_t* __restrict__ seg_begin, int n_seg,
+                                     int32_t* __restrict__ first_col) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_seg) first_col[s] = colidx[seg_begin[s]];
 }
 
 struct DevBuf {  // plan-time scratch with RAII
@@ -321,6 +328,33 @@ int tg_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* va
         tg_plan_destroy(pl);
         return cuda_fail(e, "plan upload", __FILE__, __LINE__);
     }
+    // Execution order of the split-row segments: by first column.  Segments of DIFFERENT hub rows that cover the same
+    // stretch of columns then run at the same time, so a row of B fetched for one of them is an L2 hit for the others
+    // (in storage order every hub row would re-read its ~nnz rows of B from HBM).  Only the order of execution changes:
+    // partial rows stay indexed by segment id and are still added in segment order.
+    {
+        std::vector<int32_t> order((size_t)pl->n_seg);
+        for (int32_t i = 0; i < pl->n_seg; ++i) order[(size_t)i] = i;
+        if (colidx && pl->n_seg > 1) {
+            DevBuf d_first;
+            std::vector<int32_t> first((size_t)pl->n_seg);
+            e = d_first.alloc((size_t)pl->n_seg * sizeof(int32_t));
+            if (e == cudaSuccess) {
+                seg_first_col_kernel<<<grid1d(pl->n_seg), 256, 0, st>>>(colidx, pl->seg_begin, pl->n_seg, d_first.as<int32_t>());
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaMemcpyAsync(first.data(), d_first.p, first.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e == cudaSuccess)
+                std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return first[(size_t)x] < first[(size_t)y]; });
+        }
+        if (e == cudaSuccess) e = upload(&pl->seg_order, order);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            tg_plan_destroy(pl);
+            return cuda_fail(e, "segment order", __FILE__, __LINE__);
+        }
+    }
     // optional streaming sub-plan (square matrices with a compact hub set: the document-topic-topic graphs)
     const int rc = stream_plan_build(pl, rowptr, colidx, vals, h_ptr.data(), st);
     if (rc != TG_OK) {
@@ -335,7 +369,7 @@ void tg_plan_destroy(tg_plan* pl) {
     if (!pl) return;
     tg::stream_plan_free(pl);
     cudaFree(pl->hub_rows); cudaFree(pl->hub_seg_ptr); cudaFree(pl->seg_hub);
-    cudaFree(pl->seg_begin); cudaFree(pl->seg_end); cudaFree(pl->tickets);
+    cudaFree(pl->seg_begin); cudaFree(pl->seg_end); cudaFree(pl->tickets); cudaFree(pl->seg_order);
     delete pl;
 }
 

@@ -40,6 +40,7 @@ struct SpmmArgs {
     const int32_t* __restrict__ seg_hub;
     const int32_t* __restrict__ seg_begin;
     const int32_t* __restrict__ seg_end;
+    const int32_t* __restrict__ seg_order;
     uint32_t* tickets;
     float* partials;
     int64_t ldp;
@@ -107,8 +108,9 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(const SpmmArgs a, const 
 
     if ((int)blockIdx.x < a.n_hub_blocks) {
         // ---- split-row role: one group per segment --------------------------------------------------------
-        const int seg = blockIdx.x * GPB + grp;
-        if (seg >= a.n_seg) return;
+        const int slot = blockIdx.x * GPB + grp;
+        if (slot >= a.n_seg) return;
+        const int seg = a.seg_order ? __ldg(a.seg_order + slot) : slot;  // executed in column order, stored/added in segment order
         const int hub = __ldg(a.seg_hub + seg);
         accumulate_range<VEC, G, CPL>(a, __ldg(a.seg_begin + seg), __ldg(a.seg_end + seg), gl, gmask, acc);
         const int s0 = __ldg(a.hub_seg_ptr + hub), s1 = __ldg(a.hub_seg_ptr + hub + 1);
@@ -265,6 +267,8 @@ static int run_spmm(const tg_plan* pl, const int32_t* rowptr, const int32_t* col
     a.n_rows = pl->n_rows; a.n_feat = n_feat; a.hub_threshold = pl->hub_threshold;
     a.hub_rows = pl->hub_rows; a.hub_seg_ptr = pl->hub_seg_ptr; a.seg_hub = pl->seg_hub;
     a.seg_begin = pl->seg_begin; a.seg_end = pl->seg_end; a.tickets = pl->tickets;
+    // column order pays off when B exceeds L2; narrow operands (<= 32 columns) are L2 resident and prefer storage order
+    a.seg_order = (n_feat > 32) ? pl->seg_order : nullptr;
     // partial rows start 16 B aligned inside the caller's workspace
     a.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 15u) & ~(uintptr_t)15u);
     a.ldp = (int64_t)((n_feat + 3) / 4) * 4;

@@ -79,7 +79,8 @@ typedef struct tg_plan tg_plan;
  * When the matrix is square and its hub set is compact (<= 512 hub rows holding >= 1/8 of the entries: the
  * document-topic-topic graphs), the plan also carries the "column-chunk streaming" layout (tg_stream.cu): a
  * chunk-major copy of the hub rows' entries and an (index, value) interleaved copy of all entries.  The plan
- * therefore SNAPSHOTS the values: rebuild it when `vals` change.  colidx/vals may be NULL (no streaming layout).
+ * therefore SNAPSHOTS the values: rebuild it when `vals` change.  vals may be NULL (no streaming layout); colidx may
+ * be NULL too (then the split-row segments of the gather kernel run in storage order instead of column order).
  * Environment knobs read at creation: TG_STREAM=0 disables it, TG_STREAM_CHUNK=nodes per chunk (multiple of 32, default 128).
  * ---------------------------------------------------------------------------------------------- */
 int tg_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* vals, int64_t n_rows,
