@@ -8,8 +8,9 @@ from . import _native
 from ._native import TopicGCNError, LIB_PATH
 from .csr import DeviceCSR, cached_csr
 from .layer import GCN, GraphConvolution, Featureless
+from .graph import CapturedTrainStep
 from .ops import masked_cross_entropy, spmm
 
-__all__ = ["GCN", "GraphConvolution", "Featureless", "DeviceCSR", "cached_csr", "masked_cross_entropy", "spmm",
+__all__ = ["GCN", "GraphConvolution", "Featureless", "DeviceCSR", "cached_csr", "masked_cross_entropy", "spmm", "CapturedTrainStep",
            "TopicGCNError", "LIB_PATH"]
 __version__ = "0.1.0"

@@ -55,7 +55,7 @@ def _declare(lib) -> None:
     sig("tg_plan_workspace_bytes", _sz, _p, _i32)
     sig("tg_spmm_f32", C.c_int, _p, _p, _p, _p, _p, _i64, _p, _i64, _i32, _p, _p, _p, _sz, _p)
     sig("tg_gc1_fwd_f32", C.c_int, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _i32, _f32, _i32, _p, _u64, _u64,
-        _i64, _p, _sz, _p)
+        _p, _i64, _p, _sz, _p)
     sig("tg_dropout_keep_mask", C.c_int, _p, _i64, _i32, _f32, _u64, _u64, _p)
     sig("tg_gc2_loss_fwd_f32", C.c_int, _p, _p, _p, _p, _p, _i64, _p, _p, _f32, _p, _i64, _p, _i64, _p, _i32,
         _p, _sz, _p)

@@ -87,6 +87,7 @@ struct EpiStore {
     int32_t n_feat;
     int64_t raw_row_begin;  // rows >= raw_row_begin are stored as plain sums (document-sharded mode), INT64_MAX = none
     const float* out_scale; // optional DEVICE scalar multiplied into every output element (autograd upstream gradient)
+    const unsigned long long* offset_dev;  // optional DEVICE counter added to `offset` (lets a captured CUDA graph draw a fresh mask per replay)
 
     template <int VEC, int G, int CPL>
     __device__ __forceinline__ void apply(int64_t row, int gl, unsigned gmask, int n_chunks,
@@ -100,6 +101,7 @@ struct EpiStore {
             return;
         }
         Philox4 rnd = Philox4{0, 0, 0, 0};
+        const uint64_t offset = (drop_mode == 1 && offset_dev) ? this->offset + __ldg(offset_dev) : this->offset;
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const int chunk = gl + i * G;

@@ -107,12 +107,53 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(const SpmmArgs a, const 
     for (int i = 0; i < CPL; ++i) acc[i] = chunk_zero<VEC>();
 
     if ((int)blockIdx.x < a.n_hub_blocks) {
-        // ---- split-row role: one group per segment --------------------------------------------------------
-        const int slot = blockIdx.x * GPB + grp;
+        // ---- split-row role: one WARP per segment ---------------------------------------------------------
+        // The 32/G lane groups of the warp take the segment's entries round-robin and their partial sums are combined
+        // with a fixed butterfly of shuffles (warp-cooperative segmented reduction): for narrow rows (G = 2..16) a
+        // segment is no longer a serial chain of 256 dependent gathers by a handful of lanes.
+        const int slot = blockIdx.x * kWarps + warp;
         if (slot >= a.n_seg) return;
         const int seg = a.seg_order ? __ldg(a.seg_order + slot) : slot;  // executed in column order, stored/added in segment order
         const int hub = __ldg(a.seg_hub + seg);
-        accumulate_range<VEC, G, CPL>(a, __ldg(a.seg_begin + seg), __ldg(a.seg_end + seg), gl, gmask, acc);
+        if (G == 32) {
+            accumulate_range<VEC, G, CPL>(a, __ldg(a.seg_begin + seg), __ldg(a.seg_end + seg), gl, gmask, acc);
+        } else {
+            const int sb = __ldg(a.seg_begin + seg), se = __ldg(a.seg_end + seg);
+            const int sub = lane / G;
+            for (int p = sb + sub; p < se; p += GPW * kUnroll) {
+                int c[kUnroll];
+                float v[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const int q = p + u * GPW;
+                    c[u] = (q < se) ? __ldg(a.colidx + q) : -1;
+                    v[u] = (q < se) ? __ldg(a.vals + q) : 0.f;
+                }
+                Chunk<VEC> b[kUnroll][CPL];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+                    for (int i = 0; i < CPL; ++i) {
+                        const int chunk = gl + i * G;
+                        b[u][i] = (c[u] >= 0 && chunk < a.n_chunks)
+                                      ? chunk_ldg<VEC>(a.B + (int64_t)c[u] * a.ldb + (int64_t)chunk * VEC)
+                                      : chunk_zero<VEC>();
+                    }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+                    for (int i = 0; i < CPL; ++i)
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) acc[i].v[k] = fmaf(v[u], b[u][i].v[k], acc[i].v[k]);
+            }
+#pragma unroll
+            for (int off = G; off < 32; off <<= 1)
+#pragma unroll
+                for (int i = 0; i < CPL; ++i)
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[i].v[k] += __shfl_xor_sync(0xffffffffu, acc[i].v[k], off);
+            if (sub != 0) return;  // group 0 of the warp carries the segment's partial row from here on
+        }
         const int s0 = __ldg(a.hub_seg_ptr + hub), s1 = __ldg(a.hub_seg_ptr + hub + 1);
         float* my = a.partials + (int64_t)seg * a.ldp;
 #pragma unroll
@@ -178,7 +219,7 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(const SpmmArgs a, const 
 template <int VEC, int G, int CPL, class Epi>
 static int launch_cfg(SpmmArgs a, const Epi& epi, cudaStream_t st) {
     constexpr int GPB = kWarps * (32 / G);
-    a.n_hub_blocks = (int32_t)ceil_div64(a.n_seg, GPB);
+    a.n_hub_blocks = (int32_t)ceil_div64(a.n_seg, kWarps);  // one warp per split-row segment
     const int64_t row_blocks = ceil_div64(a.n_rows, GPB);
     const int64_t grid = a.n_hub_blocks + row_blocks;
     if (grid == 0) return TG_OK;
@@ -309,7 +350,7 @@ int tg_spmm_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colid
     EpiStore epi{};
     epi.Y = Y; epi.ldy = ldy; epi.bias = bias; epi.relu = 0; epi.drop_mode = 0; epi.keep_mask = nullptr;
     epi.keep_thr = 0; epi.scale = 1.f; epi.seed = 0; epi.offset = 0; epi.n_feat = n_feat;
-    epi.raw_row_begin = INT64_MAX; epi.out_scale = out_scale;
+    epi.raw_row_begin = INT64_MAX; epi.out_scale = out_scale; epi.offset_dev = nullptr;
     const bool ok4 = (ldy % 4 == 0) && aligned16(Y) && (!bias || aligned16(bias));
     return run_spmm(plan, rowptr, colidx, vals, B, ldb, n_feat, ok4, epi, workspace, workspace_bytes,
                     as_stream(stream));
@@ -317,8 +358,8 @@ int tg_spmm_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colid
 
 int tg_gc1_fwd_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                    const float* S, int64_t lds, const float* bias, float* H1, int64_t ldh, int32_t n_feat, float p,
-                   int32_t training, const uint8_t* keep_mask, uint64_t seed, uint64_t offset, int64_t raw_row_begin,
-                   void* workspace, size_t workspace_bytes, void* stream) {
+                   int32_t training, const uint8_t* keep_mask, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                   int64_t raw_row_begin, void* workspace, size_t workspace_bytes, void* stream) {
     using namespace tg;
     TG_REQUIRE(H1, TG_ERR_INVALID_ARG, "null output");
     TG_REQUIRE(ldh >= n_feat, TG_ERR_INVALID_ARG, "ldh < n_feat");
@@ -328,6 +369,7 @@ int tg_gc1_fwd_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* co
     epi.seed = seed; epi.offset = offset; epi.keep_mask = keep_mask;
     epi.raw_row_begin = raw_row_begin < 0 ? INT64_MAX : raw_row_begin;
     epi.out_scale = nullptr;
+    epi.offset_dev = reinterpret_cast<const unsigned long long*>(offset_dev);
     const bool drop = training && p > 0.f;
     epi.drop_mode = !drop ? 0 : (keep_mask ? 2 : 1);
     epi.keep_thr = dropout_keep_threshold(p);

@@ -132,6 +132,7 @@ class GCN(Module):
         self._dropout_seed: Optional[int] = None
         self._dropout_calls = 0
         self._next_keep_mask: Optional[torch.Tensor] = None
+        self._offset_dev: Optional[torch.Tensor] = None  # device-side call counter (CUDA-graph replays, graph.py)
 
     # ---- dropout control -------------------------------------------------------------------------------------
     def set_dropout_seed(self, seed: int) -> None:
@@ -149,7 +150,8 @@ class GCN(Module):
             return None, 0, 0
         if self._dropout_seed is None:
             self._dropout_seed = int(torch.randint(0, 2**62, (1,)).item())
-        self._dropout_calls += 1
+        if self._offset_dev is None:
+            self._dropout_calls += 1  # (with a device counter the host-side offset stays fixed: CUDA-graph replays)
         return mask, self._dropout_seed, self._dropout_calls
 
     # ---- reference API --------------------------------------------------------------------------------------
@@ -158,7 +160,7 @@ class GCN(Module):
         S1 = _support(x, self.gc1.weight)
         mask, seed, off = self._dropout_state()
         return ops.GCNCoreFunction.apply(S1, self.gc1.bias, self.gc2.weight, self.gc2.bias, csr, float(self.dropout),
-                                         bool(self.training), mask, seed, off)
+                                         bool(self.training), mask, seed, off, self._offset_dev)
 
     # ---- fused train-step API -----------------------------------------------------------------------------------
     def loss(self, x, adj, target: torch.Tensor, index: torch.Tensor, return_logits: bool = False,
@@ -173,5 +175,5 @@ class GCN(Module):
         inv = 1.0 / max(int(index.numel()), 1)
         loss, logits = ops.GCNLossFunction.apply(S1, self.gc1.bias, self.gc2.weight, self.gc2.bias, csr,
                                                  float(self.dropout), bool(self.training), mask, seed, off, row_label,
-                                                 inv, bool(return_logits))
+                                                 inv, bool(return_logits), self._offset_dev)
         return (loss, logits) if return_logits else loss

@@ -107,8 +107,10 @@ def spmm(csr: DeviceCSR, B: torch.Tensor, bias: Optional[torch.Tensor] = None,
 
 def gc1_forward(csr: DeviceCSR, S: torch.Tensor, bias: Optional[torch.Tensor], p: float, training: bool,
                 keep_mask: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
-                out: Optional[torch.Tensor] = None, raw_row_begin: int = -1) -> torch.Tensor:
-    """H1 = dropout(relu(A @ S + b1)): tg_gc1_fwd_f32.  Rows >= raw_row_begin (if >= 0) get the plain sums."""
+                out: Optional[torch.Tensor] = None, raw_row_begin: int = -1,
+                offset_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """H1 = dropout(relu(A @ S + b1)): tg_gc1_fwd_f32.  Rows >= raw_row_begin (if >= 0) get the plain sums.
+    offset_dev: optional int64 CUDA scalar added to `offset` on the device (CUDA-graph replays)."""
     S = _dense2d(S, "S")
     if S.shape[0] != csr.n_cols:
         raise N.TopicGCNError(f"shape mismatch: A is {csr.n_rows}x{csr.n_cols}, S has {S.shape[0]} rows")
@@ -125,7 +127,7 @@ def gc1_forward(csr: DeviceCSR, S: torch.Tensor, bias: Optional[torch.Tensor], p
         N.check(N.lib().tg_gc1_fwd_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(S), _ld(S),
                                        N.ptr(bias), N.ptr(out), _ld(out), F, float(p), int(bool(training)),
                                        N.ptr(keep_mask), int(seed) & (2**64 - 1), int(offset) & (2**64 - 1),
-                                       int(raw_row_begin), ws, ws_bytes, _stream()), "tg_gc1_fwd_f32")
+                                       N.ptr(offset_dev), int(raw_row_begin), ws, ws_bytes, _stream()), "tg_gc1_fwd_f32")
     return out
 
 
@@ -293,8 +295,9 @@ class GCNCoreFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, S1, b1, W2, b2, csr: DeviceCSR, p: float, training: bool, keep_mask, seed: int, offset: int):
-        H1 = gc1_forward(csr, S1, b1, p, training, keep_mask, seed, offset)
+    def forward(ctx, S1, b1, W2, b2, csr: DeviceCSR, p: float, training: bool, keep_mask, seed: int, offset: int,
+                offset_dev=None):
+        H1 = gc1_forward(csr, S1, b1, p, training, keep_mask, seed, offset, offset_dev=offset_dev)
         S2 = dense_nn(H1, W2)
         logits = spmm(csr, S2, b2)
         ctx.save_for_backward(H1, W2)
@@ -311,7 +314,7 @@ class GCNCoreFunction(torch.autograd.Function):
         dS2 = spmm(csr_t, dlogits)
         dZ1, dW2, db1 = hidden_backward(H1, dS2, W2, ctx.scale)
         dS1 = spmm(csr_t, dZ1) if ctx.needs_input_grad[0] else None
-        return dS1, (db1 if ctx.has_b1 else None), dW2, db2, None, None, None, None, None, None
+        return dS1, (db1 if ctx.has_b1 else None), dW2, db2, None, None, None, None, None, None, None
 
 
 def identity_csr(n: int, device) -> DeviceCSR:
@@ -337,8 +340,8 @@ class GCNLossFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, S1, b1, W2, b2, csr: DeviceCSR, p: float, training: bool, keep_mask, seed: int, offset: int,
-                row_label, inv_count: float, want_logits: bool):
-        H1 = gc1_forward(csr, S1, b1, p, training, keep_mask, seed, offset)
+                row_label, inv_count: float, want_logits: bool, offset_dev=None):
+        H1 = gc1_forward(csr, S1, b1, p, training, keep_mask, seed, offset, offset_dev=offset_dev)
         S2 = dense_nn(H1, W2)
         loss, logits, dZ2 = gc2_loss_forward(csr, S2, b2, row_label, inv_count, want_logits=want_logits, want_grad=True)
         ctx.save_for_backward(H1, W2, dZ2)
@@ -360,7 +363,7 @@ class GCNLossFunction(torch.autograd.Function):
         dS2 = spmm(csr_t, dZ2, out_scale=g)
         dZ1, dW2, db1 = hidden_backward(H1, dS2, W2, ctx.scale)
         dS1 = spmm(csr_t, dZ1) if ctx.needs_input_grad[0] else None
-        return dS1, (db1 if ctx.has_b1 else None), dW2, db2, None, None, None, None, None, None, None, None, None
+        return dS1, (db1 if ctx.has_b1 else None), dW2, db2, None, None, None, None, None, None, None, None, None, None
 
 
 class MaskedCrossEntropy(torch.autograd.Function):

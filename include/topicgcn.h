@@ -108,6 +108,8 @@ int tg_spmm_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colid
  *   keep_mask: optional explicit [n_rows x F] uint8 keep mask (1 keep / 0 drop, ld = F), the parity mode
  *              that reproduces torch's `bernoulli_(1-p)` mask bit for bit; NULL -> counter-based
  *              Philox4x32-10 keyed on (seed, offset, row, col), see tg_dropout_keep_mask.
+ *   offset_dev: optional DEVICE uint64 added to `offset` when the Philox mask is used: a train step captured in a
+ *              CUDA graph bumps it on the device, so every replay draws a fresh mask (NULL = none).
  *   p == 0 or training == 0 -> no dropout (eval mode, layer.py:185 `train=self.training`).
  *   raw_row_begin: rows >= raw_row_begin are stored as plain sums A*S without bias/relu/dropout (negative = none).
  *              The document-sharded multi-GPU mode uses it for the replicated topic rows, whose partial sums are
@@ -116,7 +118,8 @@ int tg_spmm_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colid
 int tg_gc1_fwd_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                    const float* S, int64_t lds, const float* bias, float* H1, int64_t ldh, int32_t n_feat,
                    float p, int32_t training, const uint8_t* keep_mask, uint64_t seed, uint64_t offset,
-                   int64_t raw_row_begin, void* workspace, size_t workspace_bytes, void* stream);
+                   const uint64_t* offset_dev, int64_t raw_row_begin, void* workspace, size_t workspace_bytes,
+                   void* stream);
 
 /* Materialise the Philox keep mask the fused kernel uses (tests / debugging). */
 int tg_dropout_keep_mask(uint8_t* keep_mask, int64_t n_rows, int32_t n_feat, float p, uint64_t seed,

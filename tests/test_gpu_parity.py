@@ -446,3 +446,39 @@ def test_cpu_inputs_fail_loudly(tg, small_golden):
     model = tg.GCN(n, 16, 5, 0.5)
     with pytest.raises(tg.TopicGCNError):
         model.forward(tg.Featureless(n), adj_cpu)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CUDA-graph captured train step
+# ---------------------------------------------------------------------------------------------------------------
+def test_captured_train_step_matches_eager(tg, small_golden):
+    g = small_golden
+    n = int(g["n_docs"] + g["n_topics"])
+    adj = _sparse(g["adj_rows"], g["adj_cols"], g["adj_vals"], (n, n))
+    target = torch.tensor(g["target"], device=dev())
+    index = torch.tensor(g["index"], device=dev())
+    x = tg.Featureless(n)
+    # (a) without dropout the replayed graph reproduces the eager step bit for bit
+    m1 = _load_params(tg.GCN(n, int(g["nhid"]), int(g["nclass"]), 0.0), g, "fl")
+    m2 = _load_params(tg.GCN(n, int(g["nhid"]), int(g["nclass"]), 0.0), g, "fl")
+    m1.train()
+    loss_e = m1.loss(x, adj, target, index)
+    loss_e.backward()
+    step = tg.CapturedTrainStep(m2, x, adj, target, index)
+    for _ in range(3):
+        loss_g = step.step()
+    assert torch.equal(loss_g.detach(), loss_e.detach())
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(p1.grad, p2.grad), k
+    # (b) with dropout every replay draws a fresh Philox mask (device-side call counter)
+    m3 = _load_params(tg.GCN(n, int(g["nhid"]), int(g["nclass"]), 0.5), g, "fl")
+    m3.set_dropout_seed(77)
+    step3 = tg.CapturedTrainStep(m3, x, adj, target, index, warmup=2)
+    losses = [float(step3.step().detach()) for _ in range(4)]
+    assert len(set(losses)) == 4
+    # replay r uses offset = r + warmup (the counter advanced during the warm-up steps): check against the oracle
+    coo = golden_adj(g)
+    params = {k: g[f"fl_{k}"] for k in ("gc1.weight", "gc1.bias", "gc2.weight", "gc2.bias")}
+    mask = O.philox_keep_mask(n, int(g["nhid"]), 0.5, 77, 2 + 3)
+    ref_loss, _, _ = O.gcn_loss_and_grads(None, coo, params, g["target"], g["index"], p=0.5, training=True, keep_mask=mask)
+    assert abs(losses[3] - float(ref_loss)) <= 1e-5 * max(1.0, abs(float(ref_loss)))
