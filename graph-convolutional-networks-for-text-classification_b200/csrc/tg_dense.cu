@@ -10,6 +10,8 @@
 // All of them read an [N x H] operand once from HBM; the arithmetic (2*N*H*C flop per product) is done on the
 // fp32 FMA pipes because the reference's parity budget (1e-5 relative) rules out TF32 tensor-core inputs.
 // Every cross-block reduction is two-stage with a fixed order: no float atomics.
+#include <stdlib.h>
+
 #include "tg_common.cuh"
 
 namespace tg {
@@ -118,6 +120,154 @@ __global__ void __launch_bounds__(kNnThreads) dense_nn_kernel(const float* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Tensor-core variant of the skinny product:  C[n x c] = A[n x h] * W[h x c]  with 3xTF32 split accumulation.
+// ncu shows the FFMA version is not bandwidth bound (DRAM 29 % of peak, L1/issue bound, profiles/r01_dense_a_full.md),
+// so per the north star the product moves to the tensor cores.  fp32 parity needs more than TF32's 10-bit mantissa:
+// every operand is split  x = hi + lo  (hi = tf32(x), lo = tf32(x - hi)) and  hi*hi + hi*lo + lo*hi  is accumulated in
+// fp32 (relative error ~2^-21).  mma.sync.m16n8k8 (legacy HMMA path) is enough to make this product HBM-bound; the
+// operand A is streamed from global memory straight into fragment layout: one k-step of a row is one 32-byte sector.
+//   warp tile: 32 rows (two m16 tiles) x 24 columns (three n8 tiles, columns >= c are zero), k in steps of 8
+//   W hi/lo are staged once per CTA in shared memory as [h8][24] (row stride 24 floats: conflict-free fragment reads)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int kMmaWarps = 8;
+constexpr int kMmaRowsPerWarp = 32;
+constexpr int kMmaNP = 24;   // padded column count (three n8 tiles)
+constexpr int kMmaWS = 26;   // row stride of the staged W (floats): 4*26 = 8 (mod 32) makes the fragment reads conflict free
+
+// A is read with one 128-bit load per row per 16 k: lane (g, t) holds A[row][k16 + 4t .. 4t+3].  The k index inside an
+// MMA is only a summation index, so the two k8 steps of a 16-block use the permutation  slot t -> k = 4t + 2s,
+// slot t+4 -> k = 4t + 2s + 1  (s = 0, 1) on BOTH operands: the 16 bytes a lane loaded are exactly its two fragments.
+__global__ void __launch_bounds__(kMmaWarps * 32) dense_nn_mma_kernel(const float* __restrict__ A, int64_t lda,
+                                                                    const float* __restrict__ W, int64_t ldw,
+                                                                    float* __restrict__ C, int64_t ldc, int64_t n, int h,
+                                                                    int c) {
+    extern __shared__ __align__(16) float wsm[];  // Whi [h16][26] | Wlo [h16][26]
+    const int h16 = (h + 15) & ~15;
+    float* Whi = wsm;
+    float* Wlo = wsm + (size_t)h16 * kMmaWS;
+    for (int idx = threadIdx.x; idx < h16 * kMmaNP; idx += blockDim.x) {
+        const int k = idx / kMmaNP, j = idx % kMmaNP;
+        const float w = (k < h && j < c) ? __ldg(W + (int64_t)k * ldw + j) : 0.f;
+        const float hi = __uint_as_float(to_tf32(w));
+        Whi[k * kMmaWS + j] = hi;
+        Wlo[k * kMmaWS + j] = __uint_as_float(to_tf32(w - hi));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t row0 = ((int64_t)blockIdx.x * kMmaWarps + warp) * kMmaRowsPerWarp;
+    if (row0 >= n) return;
+    // rows of the two m16 tiles this lane touches: row0 + {g, g+8, g+16, g+24}
+    const float* ap[4];
+    bool ok[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t row = row0 + g + 8 * r;
+        ok[r] = row < n;
+        ap[r] = A + (ok[r] ? row : 0) * lda + 4 * t;
+    }
+    float acc[2][3][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
+
+    auto load_a = [&](int k16, float4 (&v)[4]) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int k = k16 + 4 * t;
+            if (ok[r] && k + 3 < h) {
+                v[r] = __ldg(reinterpret_cast<const float4*>(ap[r] + k16));
+            } else {
+                v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok[r]) {
+                    if (k + 0 < h) v[r].x = __ldg(ap[r] + k16 + 0);
+                    if (k + 1 < h) v[r].y = __ldg(ap[r] + k16 + 1);
+                    if (k + 2 < h) v[r].z = __ldg(ap[r] + k16 + 2);
+                }
+            }
+        }
+    };
+    float4 cur[4], nxt[4];
+    load_a(0, cur);
+    for (int k16 = 0; k16 < h16; k16 += 16) {
+        load_a(k16 + 16, nxt);  // next block travels while this one is multiplied (past h it loads zeros)
+#pragma unroll
+        for (int sstep = 0; sstep < 2; ++sstep) {
+            uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                // fragment order a0:(g, slot t) a1:(g+8, slot t) a2:(g, slot t+4) a3:(g+8, slot t+4)
+                const float4 lo_row = cur[2 * m], hi_row = cur[2 * m + 1];
+                const float x[4] = {sstep ? lo_row.z : lo_row.x, sstep ? hi_row.z : hi_row.x,
+                                    sstep ? lo_row.w : lo_row.y, sstep ? hi_row.w : hi_row.y};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    ahi[m][e] = to_tf32(x[e]);
+                    alo[m][e] = to_tf32(x[e] - __uint_as_float(ahi[m][e]));
+                }
+            }
+            const int kb = k16 + 4 * t + 2 * sstep;  // actual k of slot t; slot t+4 is kb + 1
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                uint32_t bhi[2], blo[2];
+                bhi[0] = __float_as_uint(Whi[kb * kMmaWS + 8 * j + g]);
+                bhi[1] = __float_as_uint(Whi[(kb + 1) * kMmaWS + 8 * j + g]);
+                blo[0] = __float_as_uint(Wlo[kb * kMmaWS + 8 * j + g]);
+                blo[1] = __float_as_uint(Wlo[(kb + 1) * kMmaWS + 8 * j + g]);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    mma_tf32(acc[m][j], alo[m], bhi);  // small terms first
+                    mma_tf32(acc[m][j], ahi[m], blo);
+                    mma_tf32(acc[m][j], ahi[m], bhi);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) cur[r] = nxt[r];
+    }
+    // c0:(g, 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int64_t row = row0 + 16 * m + g + 8 * hh;
+            if (row >= n) continue;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int col = 8 * j + 2 * t;
+                if (col < c) C[row * ldc + col] = acc[m][j][2 * hh];
+                if (col + 1 < c) C[row * ldc + col + 1] = acc[m][j][2 * hh + 1];
+            }
+        }
+}
+
+static size_t dense_mma_smem(int h) { return (size_t)2 * ((h + 15) & ~15) * kMmaWS * sizeof(float); }
+
+static int launch_dense_nn_mma(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t n,
+                               int h, int c, cudaStream_t st) {
+    const size_t smem = dense_mma_smem(h);
+    TG_CUDA(cudaFuncSetAttribute(dense_nn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)ceil_div64(n, kMmaWarps * kMmaRowsPerWarp);
+    dense_nn_mma_kernel<<<grid, kMmaWarps * 32, smem, st>>>(A, lda, W, ldw, C, ldc, n, h, c);
+    TG_LAUNCH_CHECK();
+    return TG_OK;
+}
+
 template <int NC4>
 static int launch_dense_nn(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
                            int64_t n, int h, int c, cudaStream_t st) {
@@ -141,19 +291,42 @@ static int launch_dense_nn(const float* A, int64_t lda, const float* W, int64_t 
 // Fused hidden-layer backward.  One thread per hidden unit j: W2[j,:] and the dW2[j,:] accumulators live in
 // registers; rows are streamed, the dS2 row is read from a small shared tile at a warp-uniform address.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kHbTile = 64;        // rows per staged dS2 tile
-constexpr int kHbBatch = 8;        // H1 rows in flight per thread
-constexpr int kHbMaxGrid = 3 * kNumSM;  // 80 registers x 256 threads: three CTAs per SM
+constexpr int kHbTile = 32;        // rows per staged tile (one bit per row in the per-thread activity mask)
+constexpr int kHbStages = 3;       // cp.async pipeline depth (tiles in flight: kHbStages - 1)
+constexpr int kHbMaxGrid = 2 * kNumSM;  // 96 KB of staged tiles per CTA: two CTAs per SM
 
+__device__ __forceinline__ void hb_cp16(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hb_cp4(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+
+// H1 and dS2 tiles travel through a cp.async pipeline in shared memory.  The FMAs exploit the sparsity of H1: after
+// ReLU and dropout (p = 0.5) about three quarters of its entries are exactly zero, and a zero entry contributes nothing
+// to dW2 and has dZ1 = 0.  Every thread (one hidden unit j) therefore builds a 32-bit mask of the rows of the tile
+// where H1[row, j] > 0 and walks only those rows; the loop runs for the warp's maximum population count (~13 of 32), the
+// finished lanes ride along with a = 0.  dZ1 is written in place over the staged H1 tile (entries that were zero are
+// already the correct dZ1 = 0) and the tile goes back to HBM with coalesced 128-bit stores.
+// History: the dense variants (register-loaded, register double-buffered, cp.async staged, two units per thread) all
+// ran in 0.97 ms at C3 — 320 M three-register FFMAs at ~0.3 per cycle per scheduler, an issue / register-port bound
+// (profiles/r01_hidden_a_full.md) — so the only way down was to issue fewer of them.
 template <int NC4, int TB>
-__global__ void __launch_bounds__(TB, (TB == 256 ? 3 : 1)) hidden_bwd_kernel(const float* __restrict__ H1, int64_t ldh,
+__global__ void __launch_bounds__(TB, (TB == 256 ? 2 : 1)) hidden_bwd_kernel(const float* __restrict__ H1, int64_t ldh,
                                                           const float* __restrict__ dS2, int64_t ldd,
                                                           const float* __restrict__ W2, int64_t ldw, float scale,
                                                           float* __restrict__ dZ1, int64_t ldz,
                                                           float* __restrict__ partials, int64_t n, int h, int c,
-                                                          int64_t rows_per_block) {
+                                                          int64_t rows_per_block, int vec_ok, int out_vec) {
     constexpr int CP = NC4 * 4;
-    __shared__ __align__(16) float ds[kHbTile * CP];
+    extern __shared__ __align__(16) float hb_smem[];
+    const int hp4 = (h + 3) & ~3;                     // row stride of the staged H1 tile (floats)
+    float* As = hb_smem;                              // [kHbStages][kHbTile][hp4]
+    float* Ds = hb_smem + (size_t)kHbStages * kHbTile * hp4;  // [kHbStages][kHbTile][CP]
     const int j = threadIdx.x;
     const bool live = j < h;
     float w[CP], gw[CP];
@@ -165,47 +338,98 @@ __global__ void __launch_bounds__(TB, (TB == 256 ? 3 : 1)) hidden_bwd_kernel(con
     float gb = 0.f;
     const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r_end = min(n, r_begin + rows_per_block);
-    for (int64_t r0 = r_begin; r0 < r_end; r0 += kHbTile) {
-        const int tile = (int)min((int64_t)kHbTile, r_end - r0);
-        __syncthreads();
-        for (int idx = j; idx < kHbTile * CP; idx += blockDim.x) {
-            const int rr = idx / CP, q = idx % CP;
-            ds[idx] = (rr < tile && q < c) ? __ldg(dS2 + (r0 + rr) * ldd + q) : 0.f;
-        }
-        __syncthreads();
-        if (!live) continue;
-        // running pointers (one 64-bit add per row) instead of re-deriving row*ld+j for every access
-        const float* hp = H1 + r0 * ldh + j;
-        float* zp = dZ1 + r0 * ldz + j;
-        for (int rb = 0; rb < tile; rb += kHbBatch) {
-            float a[kHbBatch];
-#pragma unroll
-            for (int u = 0; u < kHbBatch; ++u) a[u] = (rb + u < tile) ? __ldg(hp + (int64_t)u * ldh) : 0.f;
-            const float* dsr = ds + rb * CP;
-            // all kHbBatch rows are computed unconditionally (rows past the tile read zeros), so the compiler can
-            // interleave their independent FMA chains; dh is kept as four partial sums to shorten the dependent chain
-#pragma unroll
-            for (int u = 0; u < kHbBatch; ++u) {
-                float dh0 = 0.f, dh1 = 0.f, dh2 = 0.f, dh3 = 0.f;
-#pragma unroll
-                for (int q4 = 0; q4 < NC4; ++q4) {
-                    const float4 d = *reinterpret_cast<const float4*>(dsr + u * CP + q4 * 4);
-                    dh0 = fmaf(d.x, w[q4 * 4 + 0], dh0);
-                    dh1 = fmaf(d.y, w[q4 * 4 + 1], dh1);
-                    dh2 = fmaf(d.z, w[q4 * 4 + 2], dh2);
-                    dh3 = fmaf(d.w, w[q4 * 4 + 3], dh3);
-                    gw[q4 * 4 + 0] = fmaf(a[u], d.x, gw[q4 * 4 + 0]);
-                    gw[q4 * 4 + 1] = fmaf(a[u], d.y, gw[q4 * 4 + 1]);
-                    gw[q4 * 4 + 2] = fmaf(a[u], d.z, gw[q4 * 4 + 2]);
-                    gw[q4 * 4 + 3] = fmaf(a[u], d.w, gw[q4 * 4 + 3]);
+    const int n_tiles = (int)((r_end - r_begin + kHbTile - 1) / kHbTile);
+
+    auto issue = [&](int t) {
+        if (t < n_tiles) {
+            const int st = t % kHbStages;
+            const int64_t r0 = r_begin + (int64_t)t * kHbTile;
+            float* as = As + (size_t)st * kHbTile * hp4;
+            float* dsm = Ds + (size_t)st * kHbTile * CP;
+            if (vec_ok) {
+                const int per_row = hp4 / 4;
+                for (int idx = j; idx < kHbTile * per_row; idx += blockDim.x) {
+                    const int rr = idx / per_row, q = idx % per_row;
+                    const bool ok = r0 + rr < r_end && q * 4 < h;
+                    hb_cp16(as + rr * hp4 + q * 4, ok ? H1 + (r0 + rr) * ldh + q * 4 : H1, ok);
                 }
-                const float dz = (a[u] > 0.f) ? ((dh0 + dh1) + (dh2 + dh3)) * scale : 0.f;
-                if (rb + u < tile) zp[(int64_t)u * ldz] = dz;
+            } else {
+                for (int idx = j; idx < kHbTile * hp4; idx += blockDim.x) {
+                    const int rr = idx / hp4, q = idx % hp4;
+                    const bool ok = r0 + rr < r_end && q < h;
+                    hb_cp4(as + rr * hp4 + q, ok ? H1 + (r0 + rr) * ldh + q : H1, ok);
+                }
+            }
+            for (int idx = j; idx < kHbTile * CP; idx += blockDim.x) {
+                const int rr = idx / CP, q = idx % CP;
+                const bool ok = r0 + rr < r_end && q < c;
+                hb_cp4(dsm + idx, ok ? dS2 + (r0 + rr) * ldd + q : dS2, ok);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");  // (an empty group keeps the wait arithmetic uniform)
+    };
+
+#pragma unroll
+    for (int t = 0; t < kHbStages - 1; ++t) issue(t);
+    for (int t = 0; t < n_tiles; ++t) {
+        issue(t + kHbStages - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kHbStages - 1) : "memory");
+        __syncthreads();
+        const int st = t % kHbStages;
+        const int64_t r0 = r_begin + (int64_t)t * kHbTile;
+        const int tile = (int)min((int64_t)kHbTile, r_end - r0);
+        const float* dsm = Ds + (size_t)st * kHbTile * CP;
+        float* acol = As + (size_t)st * kHbTile * hp4 + j;  // column j of the staged tile, row stride hp4
+        unsigned mask = 0;
+        if (live) {
+#pragma unroll
+            for (int u = 0; u < kHbTile; ++u) mask |= (acol[u * hp4] > 0.f ? 1u : 0u) << u;
+        }
+        const int iters = __reduce_max_sync(0xffffffffu, __popc(mask));
+        for (int it = 0; it < iters; ++it) {
+            const bool act = mask != 0;
+            const int u = act ? (__ffs(mask) - 1) : 0;
+            mask &= mask - 1;  // (0 stays 0)
+            const float a = act ? acol[u * hp4] : 0.f;
+            const float* dr = dsm + u * CP;  // lane-private row of the dS2 tile
+            float dh0 = 0.f, dh1 = 0.f, dh2 = 0.f, dh3 = 0.f;
+#pragma unroll
+            for (int q4 = 0; q4 < NC4; ++q4) {
+                const float4 d = *reinterpret_cast<const float4*>(dr + q4 * 4);
+                dh0 = fmaf(d.x, w[q4 * 4 + 0], dh0);
+                dh1 = fmaf(d.y, w[q4 * 4 + 1], dh1);
+                dh2 = fmaf(d.z, w[q4 * 4 + 2], dh2);
+                dh3 = fmaf(d.w, w[q4 * 4 + 3], dh3);
+                gw[q4 * 4 + 0] = fmaf(a, d.x, gw[q4 * 4 + 0]);
+                gw[q4 * 4 + 1] = fmaf(a, d.y, gw[q4 * 4 + 1]);
+                gw[q4 * 4 + 2] = fmaf(a, d.z, gw[q4 * 4 + 2]);
+                gw[q4 * 4 + 3] = fmaf(a, d.w, gw[q4 * 4 + 3]);
+            }
+            if (act) {
+                const float dz = ((dh0 + dh1) + (dh2 + dh3)) * scale;
+                acol[u * hp4] = dz;  // in place: the tile turns into dZ1
                 gb += dz;
             }
-            hp += (int64_t)kHbBatch * ldh;
-            zp += (int64_t)kHbBatch * ldz;
         }
+        __syncthreads();
+        // coalesced write-back of the tile (rows past the range were zero filled and are skipped)
+        {
+            float* tile_s = As + (size_t)st * kHbTile * hp4;
+            if (out_vec) {
+                const int per_row = hp4 / 4;
+                for (int idx = j; idx < tile * per_row; idx += blockDim.x) {
+                    const int rr = idx / per_row, q = idx % per_row;
+                    if (q * 4 < h)
+                        *reinterpret_cast<float4*>(dZ1 + (r0 + rr) * ldz + q * 4) = *reinterpret_cast<const float4*>(tile_s + rr * hp4 + q * 4);
+                }
+            } else {
+                for (int idx = j; idx < tile * hp4; idx += blockDim.x) {
+                    const int rr = idx / hp4, q = idx % hp4;
+                    if (q < h) dZ1[(r0 + rr) * ldz + q] = tile_s[rr * hp4 + q];
+                }
+            }
+        }
+        __syncthreads();  // the stage is refilled kHbStages - 1 iterations later
     }
     if (live) {
         float* out = partials + (int64_t)blockIdx.x * h * (c + 1);
@@ -238,16 +462,24 @@ static int launch_hidden_bwd(const float* H1, int64_t ldh, const float* dS2, int
     rpb = ceil_div64(rpb, kHbTile) * kHbTile;
     grid = ceil_div64(n > 0 ? n : 1, rpb);
     const int threads = ((h + 31) / 32) * 32;
+    const int hp4 = (h + 3) & ~3;
+    const size_t smem = (size_t)kHbStages * kHbTile * (hp4 + NC4 * 4) * sizeof(float);
+    const int vec_ok = (ldh % 4 == 0) && ((reinterpret_cast<uintptr_t>(H1) & 15u) == 0);
+    const int out_vec = (ldz % 4 == 0) && (h % 4 == 0) && ((reinterpret_cast<uintptr_t>(dZ1) & 15u) == 0);
     // the register budget follows the block size: W2[j,:] and dW2[j,:] (2*CP floats) stay in registers for h <= 512
-    if (threads <= 256)
-        hidden_bwd_kernel<NC4, 256><<<(unsigned)grid, threads, 0, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz,
-                                                                        partials, n, h, c, rpb);
-    else if (threads <= 512)
-        hidden_bwd_kernel<NC4, 512><<<(unsigned)grid, threads, 0, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz,
-                                                                        partials, n, h, c, rpb);
-    else
-        hidden_bwd_kernel<NC4, 1024><<<(unsigned)grid, threads, 0, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz,
-                                                                         partials, n, h, c, rpb);
+    if (threads <= 256) {
+        TG_CUDA(cudaFuncSetAttribute(hidden_bwd_kernel<NC4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hidden_bwd_kernel<NC4, 256><<<(unsigned)grid, threads, smem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz,
+                                                                           partials, n, h, c, rpb, vec_ok, out_vec);
+    } else if (threads <= 512) {
+        TG_CUDA(cudaFuncSetAttribute(hidden_bwd_kernel<NC4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hidden_bwd_kernel<NC4, 512><<<(unsigned)grid, threads, smem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz,
+                                                                           partials, n, h, c, rpb, vec_ok, out_vec);
+    } else {
+        TG_CUDA(cudaFuncSetAttribute(hidden_bwd_kernel<NC4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        hidden_bwd_kernel<NC4, 1024><<<(unsigned)grid, threads, smem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz,
+                                                                            partials, n, h, c, rpb, vec_ok, out_vec);
+    }
     TG_LAUNCH_CHECK();
     const int64_t n_elem = (int64_t)h * (c + 1);
     sum_partials_kernel<<<(unsigned)ceil_div64(n_elem, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1);
@@ -322,6 +554,19 @@ int tg_dense_nn_f32(const float* A, int64_t lda, const float* W, int64_t ldw, fl
     TG_REQUIRE(n >= 0 && h > 0 && c > 0 && lda >= h && ldw >= c && ldc >= c, TG_ERR_INVALID_ARG, "bad shape");
     if (n == 0) return TG_OK;
     cudaStream_t st = as_stream(stream);
+    {
+        // tensor-core path (3xTF32) for column blocks of up to 24; TG_DENSE_MMA=0 selects the FFMA kernel
+        static const bool mma_ok = !(getenv("TG_DENSE_MMA") && atoi(getenv("TG_DENSE_MMA")) == 0);
+        const bool a_vec = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0);
+        if (mma_ok && a_vec && dense_mma_smem(h) <= 200 * 1024) {
+            for (int c0 = 0; c0 < c; c0 += kMmaNP) {
+                const int cb = (c - c0 < kMmaNP) ? (c - c0) : kMmaNP;
+                const int rc = launch_dense_nn_mma(A, lda, W + c0, ldw, C + c0, ldc, n, h, cb, st);
+                if (rc != TG_OK) return rc;
+            }
+            return TG_OK;
+        }
+    }
     for (int c0 = 0; c0 < c; c0 += 32) {
         const int cb = (c - c0 < 32) ? (c - c0) : 32;
         const int nc4 = (cb + 3) / 4;

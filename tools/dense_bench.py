@@ -31,7 +31,8 @@ def main():
     ap.add_argument("--c", type=int, default=20)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
-    H1 = torch.relu(torch.randn(a.n, a.h, device=dev))
+    # H1 as the layer produces it: relu then dropout(0.5) -> ~75 % exact zeros
+    H1 = torch.relu(torch.randn(a.n, a.h, device=dev)) * (torch.rand(a.n, a.h, device=dev) < 0.5) * 2.0
     W2 = torch.randn(a.h, a.c, device=dev)
     dS2 = torch.randn(a.n, a.c, device=dev)
     X = torch.randn(a.n, a.c, device=dev)
