@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libtopicgcn.so")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
-SOURCES = ["tg_api.cu", "tg_csr.cu", "tg_spmm.cu", "tg_dense.cu", "tg_stream.cu"]
+SOURCES = ["tg_api.cu", "tg_csr.cu", "tg_spmm.cu", "tg_dense.cu", "tg_stream.cu", "tg_roles2.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -39,10 +39,11 @@ def _sources() -> list[str]:
     return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-def _fingerprint() -> str:
+def _fingerprint(src: str | None = None) -> str:
+    """Hash of the flags, the C header, every .cuh and either one .cu (per-object stamp) or all of them (library stamp)."""
     h = hashlib.sha256()
-    files = sorted(os.listdir(CSRC)) + [os.path.join(INCLUDE, "topicgcn.h")]
-    for f in files:
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh") or (f.endswith(".cu") and (src is None or f == src)))
+    for f in files + [os.path.join(INCLUDE, "topicgcn.h")]:
         path = f if os.path.isabs(f) else os.path.join(CSRC, f)
         with open(path, "rb") as fh:
             h.update(f.encode())
@@ -51,14 +52,20 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
-def _compile_one(nvcc: str, src: str, log_dir: str) -> str:
+def _compile_one(nvcc: str, src: str, log_dir: str, force: bool = False) -> str:
     obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+    stamp = obj + ".stamp"
+    fp = _fingerprint(src)
+    if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == fp:
+        return obj  # this object is current: only changed translation units are recompiled
     cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     with open(os.path.join(log_dir, src + ".ptxas.log"), "w") as fh:
         fh.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
+    with open(stamp, "w") as fh:
+        fh.write(fp)
     return obj
 
 
@@ -76,7 +83,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
     if verbose:
         print(f"[topicgcn build] nvcc sm_100a: {', '.join(srcs)}")
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile_one(nvcc, s, OBJ_DIR), srcs))
+        objs = list(ex.map(lambda s: _compile_one(nvcc, s, OBJ_DIR, force), srcs))
     link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:

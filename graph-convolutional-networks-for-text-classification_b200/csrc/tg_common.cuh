@@ -65,6 +65,19 @@ struct tg_plan {
     int32_t* vmap = nullptr;         // [n_hub][8] virtual slots of each hub row
     int32_t* vcnt = nullptr;         // [n_hub]
     int32_t* rsplit = nullptr;       // [n_rows] first hub-column entry of each row in colidx2 (rows are reordered: others | hubs)
+
+    // ---- warp-per-slot role kernels (tg_roles2.cu): hub rows <= 256, 128-column slices -------------------------------
+    bool r2_ok = false;
+    int32_t r2_T = 0, r2_n_chunks = 0, r2_cap_hub = 0;   // hub role: nodes per chunk, chunks, staged entries per chunk (max)
+    int32_t r2_n_jobs = 0, r2_cap_doc = 0;               // document role: jobs of 64 rows, staged entries per job (max)
+    int2* r2_hent = nullptr;         // [hub_nnz+2] hub entries, (chunk, slot)-major: {byte offset of the column's row in the staged tile, value bits}
+    int32_t* r2_htab = nullptr;      // [r2_n_chunks][260] offsets of the 256 slots relative to the chunk's (even-aligned) base
+    int4* r2_cdesc = nullptr;        // [r2_n_chunks] {aligned base into r2_hent, staged entry count (even), first node, -}
+    int32_t* r2_vmap = nullptr;      // [n_hub][8] slots of each hub row (slot = warp * 16 + position)
+    int32_t* r2_vcnt = nullptr;      // [n_hub]
+    int2* r2_dent = nullptr;         // compact entries of the short rows, per row: other columns {col, v}, then hub columns {hub * 512, v}
+    int2* r2_rdesc = nullptr;        // [r2_n_jobs*64] {first entry relative to the job's base, n_entries << 16 | n_other}
+    int2* r2_jdesc = nullptr;        // [r2_n_jobs] {aligned base into r2_dent, staged entry count (even)}
 };
 
 namespace tg {

@@ -377,7 +377,7 @@ int tg_plan_info(const tg_plan* pl, int64_t info[8]) {
     TG_REQUIRE(pl && info, TG_ERR_INVALID_ARG, "null pointer");
     info[0] = pl->n_hub; info[1] = pl->n_seg; info[2] = pl->hub_nnz;
     info[3] = pl->max_row_nnz; info[4] = pl->hub_threshold; info[5] = pl->segment_nnz;
-    info[6] = pl->stream_ok ? 1 : 0; info[7] = pl->stream_ok ? pl->chunk_rows : 0;
+    info[6] = (pl->stream_ok ? 1 : 0) | (pl->r2_ok ? 2 : 0); info[7] = pl->stream_ok ? pl->chunk_rows : 0;
     return TG_OK;
 }
 

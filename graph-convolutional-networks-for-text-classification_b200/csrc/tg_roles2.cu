@@ -1,0 +1,826 @@
+// tg_roles2.cu — role-specialised streaming SpMM, second generation ("warp per hub slot").
+//
+// Same product and same data flow as the role kernel of tg_stream.cu (reference layer.py:106 and its autograd transpose
+// product; B is read from HBM once, its second use is served by L2), reorganised around what the profiles of the first
+// generation showed (profiles/r01_final_full.md: 42 % issue utilisation, shared-memory pipe at 50 %, short-scoreboard
+// and long-scoreboard stalls, and — simulated from the plan — a 2.3x lock-step loss in the hub role because the four
+// 8-lane groups of a warp ran slot loops of different lengths and the 64 groups met at a barrier after every chunk):
+//
+//   hub CTAs  (128-column slices, 16 warps): a WARP owns 16 hub slots; its 32 lanes cover the slice with one float4 each,
+//             so every lane of the warp works on the same entry (no divergence inside a warp) and the sixteen
+//             accumulators are sixteen float4 registers.  Heavy hub rows are split over the spare slots and the pieces
+//             are dealt to the warps longest-first, so the warps of a CTA carry the same load.  Chunks of T nodes are
+//             staged with one 2-D TMA tile + two bulk copies per stage (double buffered on mbarriers).  Entries carry
+//             the byte offset of their row inside the staged tile: address = base + offset, one LDS.128, two FFMA2.
+//   doc CTAs  (128-column slices, 64 groups of 8 lanes): the K hub rows of B stay resident in shared memory (bulk
+//             copies); a job is 64 consecutive rows — one row per group.  The job's entries and row descriptors arrive
+//             through a four-stage bulk-copy ring (mbarrier full/empty pairs, issued two jobs ahead by one thread), and
+//             each group prefetches the slice of B its NEXT row needs for the self loop into registers one job ahead,
+//             so no consumer instruction waits on global memory.
+//
+// All floating-point additions happen in an order fixed by the plan: bitwise reproducible, no float atomics.
+// Packed fp32 FMAs (FFMA2, fma.rn.f32x2) halve the issue slots of the arithmetic; the results are the IEEE fma results.
+#include <cub/cub.cuh>
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "tg_async.cuh"
+#include "tg_finish.cuh"
+#include "tg_stream.cuh"
+
+namespace tg {
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kKPW = 16;              // hub slots per warp
+constexpr int kKv = kWarps * kKPW;    // 256 slots per CTA
+constexpr int kHtW = kKv + 4;         // offset-table row: 257 offsets padded to a multiple of 16 bytes
+constexpr int kFT = 128;              // columns per CTA slice
+constexpr int kRowBytes = kFT * 4;
+constexpr int kJobRows = 64;          // document role: rows per job = row groups per CTA
+constexpr int kStages = 4;            // document role: entry ring depth
+constexpr int kPF = 2;                // ... jobs issued ahead
+constexpr int kL2PF = 4;              // document role: jobs whose self-loop rows of B are prefetched into L2 ahead
+constexpr size_t kSmemMax = 227 * 1024;
+
+struct R2Args {
+    // hub role
+    const int2* __restrict__ hent;
+    const int32_t* __restrict__ htab;
+    const int4* __restrict__ cdesc;     // {aligned base into hent, staged entries (even), first node of the chunk, -}
+    int32_t T, n_chunks, cap_hub;
+    // document role
+    const int2* __restrict__ dent;
+    const int2* __restrict__ rdesc;
+    const int2* __restrict__ jdesc;
+    int32_t n_jobs, cap_doc;
+    const int32_t* __restrict__ hub_rows;
+    int32_t Kh;
+    // operands
+    const float* __restrict__ B;
+    int64_t ldb, n;
+    int32_t n_chunks4;
+    float* partials;
+    int64_t ldp;
+    int32_t hub_slices, hub_lanes, doc_slices, doc_lanes, only_role;
+    const uint32_t* __restrict__ keep_bits;  // bit-packed dropout keep mask [n][n_feat/32] (bit b of word w = column 32w+b) or null
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// acc += v * b on packed pairs (two FFMA2)
+__device__ __forceinline__ void fma4p(float4& acc, float v, const float4& b) {
+    const float2 vv = make_float2(v, v);
+    const float2 lo = __ffma2_rn(vv, make_float2(b.x, b.y), make_float2(acc.x, acc.y));
+    const float2 hi = __ffma2_rn(vv, make_float2(b.z, b.w), make_float2(acc.z, acc.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// pull a 2-D tile of B into L2 ahead of the loads that need it (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int col, int row) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(col), "r"(row) : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(const unsigned char* p) { return *reinterpret_cast<const float4*>(p); }
+
+// =============================================== hub role ===============================================================
+__device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tmap, unsigned char* smem, uint64_t* bars,
+                                         int bid) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slice = bid % a.hub_slices, hl = bid / a.hub_slices;
+    const size_t bs_bytes = (size_t)a.T * kRowBytes;
+    const size_t he_bytes = align128((size_t)a.cap_hub * 8);
+    const size_t st_bytes = bs_bytes + he_bytes + align128((size_t)kHtW * 4);
+    uint64_t* full = bars;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // one thread moves a whole stage: the T x 128 tile of B (zero filled past the matrix), the chunk's run of hub entries
+    // and its offset-table row
+    auto issue = [&](int buf, int c, const int4 d) {
+        unsigned char* base = smem + (size_t)buf * st_bytes;
+        fence_proxy_async();  // the buffer was last read through the generic proxy (ordered by the block barrier)
+        mbar_expect_tx(&full[buf], (unsigned)bs_bytes + (unsigned)d.y * 8u + (unsigned)(kHtW * 4));
+        tma_load_2d(base, tmap, slice * kFT, d.z, &full[buf]);
+        if (d.y) bulk_load_1d(base + bs_bytes, a.hent + d.x, (unsigned)d.y * 8u, &full[buf]);
+        bulk_load_1d(base + bs_bytes + he_bytes, a.htab + (int64_t)c * kHtW, (unsigned)(kHtW * 4), &full[buf]);
+    };
+    float4 acc[kKPW];
+#pragma unroll
+    for (int kk = 0; kk < kKPW; ++kk) acc[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int c = hl;
+    if (c < a.n_chunks) {
+        int4 d_next = make_int4(0, 0, 0, 0);
+        if (tid == 0) {
+            issue(0, c, __ldg(a.cdesc + c));
+            if (c + a.hub_lanes < a.n_chunks) d_next = __ldg(a.cdesc + c + a.hub_lanes);
+        }
+        for (int it = 0; c < a.n_chunks; c += a.hub_lanes, ++it) {
+            const int buf = it & 1;
+            const int cn = c + a.hub_lanes;
+            if (tid == 0 && cn < a.n_chunks) {
+                issue(buf ^ 1, cn, d_next);
+                if (cn + a.hub_lanes < a.n_chunks) d_next = __ldg(a.cdesc + cn + a.hub_lanes);
+            }
+            mbar_wait(&full[buf], (unsigned)(it >> 1) & 1u);
+            const unsigned char* base = smem + (size_t)buf * st_bytes;
+            const unsigned char* Bl = base + lane * 16;
+            const int2* he = reinterpret_cast<const int2*>(base + bs_bytes);
+            const int32_t* ht = reinterpret_cast<const int32_t*>(base + bs_bytes + he_bytes);
+            const int32_t* htw = ht + warp * kKPW;
+#pragma unroll
+            for (int kk = 0; kk < kKPW; ++kk) {
+                int q = htw[kk];  // warp-uniform broadcast reads
+                const int h1 = htw[kk + 1];
+#pragma unroll 1
+                for (; q + 4 <= h1; q += 4) {
+                    const int2 e0 = he[q], e1 = he[q + 1], e2 = he[q + 2], e3 = he[q + 3];
+                    const float4 b0 = lds128(Bl + e0.x), b1 = lds128(Bl + e1.x), b2 = lds128(Bl + e2.x), b3 = lds128(Bl + e3.x);
+                    fma4p(acc[kk], __int_as_float(e0.y), b0);
+                    fma4p(acc[kk], __int_as_float(e1.y), b1);
+                    fma4p(acc[kk], __int_as_float(e2.y), b2);
+                    fma4p(acc[kk], __int_as_float(e3.y), b3);
+                }
+                if (q + 2 <= h1) {
+                    const int2 e0 = he[q], e1 = he[q + 1];
+                    const float4 b0 = lds128(Bl + e0.x), b1 = lds128(Bl + e1.x);
+                    fma4p(acc[kk], __int_as_float(e0.y), b0);
+                    fma4p(acc[kk], __int_as_float(e1.y), b1);
+                    q += 2;
+                }
+                if (q < h1) {
+                    const int2 e0 = he[q];
+                    fma4p(acc[kk], __int_as_float(e0.y), lds128(Bl + e0.x));
+                }
+            }
+            __syncthreads();
+        }
+    }
+    float* dst = a.partials + ((int64_t)hl * kKv + warp * kKPW) * a.ldp + (int64_t)(slice * 32 + lane) * 4;
+#pragma unroll
+    for (int kk = 0; kk < kKPW; ++kk) *reinterpret_cast<float4*>(dst + (int64_t)kk * a.ldp) = acc[kk];
+}
+
+// =============================================== document role ===========================================================
+__device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, const CUtensorMap* tmap_job, unsigned char* smem,
+                                         uint64_t* bars, int bid) {
+    const int tid = threadIdx.x, lane = tid & 31, gl = lane & 7, grp = tid >> 3;
+    const unsigned gmask = group_mask<8>(lane);
+    const int slice = bid % a.doc_slices, dl = bid / a.doc_slices;
+    const int q0 = slice * 32 + gl;  // this lane owns the float4 chunks q0 + 8u, u < 4
+    const size_t bh_bytes = align128((size_t)a.Kh * kRowBytes);
+    const size_t en_bytes = align128((size_t)a.cap_doc * 8);
+    const size_t st_bytes = en_bytes + (size_t)kJobRows * 8;
+    unsigned char* ring = smem + bh_bytes;
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kStages;
+    uint64_t* bhbar = bars + 2 * kStages;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kWarps);
+        }
+        mbar_init(bhbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bhbar, (unsigned)a.Kh * kRowBytes);
+    }
+    __syncthreads();
+    // the hub rows of B (this slice) stay resident for the whole kernel
+    for (int k = tid; k < a.Kh; k += kThreads)
+        bulk_load_1d(smem + (size_t)k * kRowBytes, a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb + (int64_t)slice * kFT, kRowBytes, bhbar);
+    auto issue = [&](int itn, int jobn) {
+        const int s = itn % kStages;
+        const int2 jd = __ldg(a.jdesc + jobn);
+        unsigned char* base = ring + (size_t)s * st_bytes;
+        fence_proxy_async();
+        mbar_expect_tx(&full[s], (unsigned)jd.y * 8u + (unsigned)(kJobRows * 8));
+        if (jd.y) bulk_load_1d(base, a.dent + jd.x, (unsigned)jd.y * 8u, &full[s]);
+        bulk_load_1d(base + en_bytes, a.rdesc + (int64_t)jobn * kJobRows, (unsigned)(kJobRows * 8), &full[s]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kPF; ++i)
+            if (dl + i * a.doc_lanes < a.n_jobs) issue(i, dl + i * a.doc_lanes);
+#pragma unroll
+        for (int i = 1; i < kL2PF; ++i)
+            if (dl + i * a.doc_lanes < a.n_jobs) tma_prefetch_l2_2d(tmap_job, slice * kFT, (dl + i * a.doc_lanes) * kJobRows);
+    }
+    auto load_self = [&](float4(&dst)[4], int jobx) {
+        const int64_t row = (int64_t)jobx * kJobRows + grp;
+        if (jobx < a.n_jobs && row < a.n) {
+            const float* p = a.B + row * a.ldb + (int64_t)q0 * 4;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dst[u] = ldg_f4_stream(p + u * 32);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dst[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    // per-thread constants of the epilogue: this lane's 16 bias values, the optional upstream scale, the Philox offset
+    float4 bias4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        bias4[u] = epi.bias ? __ldg(reinterpret_cast<const float4*>(epi.bias + (int64_t)(q0 + 8 * u) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float gscale = epi.out_scale ? __ldg(epi.out_scale) : 1.f;
+    const uint64_t rng_offset = (epi.drop_mode == 1 && epi.offset_dev) ? epi.offset + __ldg(epi.offset_dev) : epi.offset;
+    const int mask_words = a.n_chunks4 / 8;
+    auto load_bits = [&](int jobx) {
+        const int64_t row = (int64_t)jobx * kJobRows + grp;
+        if (a.keep_bits && jobx < a.n_jobs && row < a.n)
+            return __ldg(reinterpret_cast<const uint4*>(a.keep_bits + row * mask_words + slice * 4));
+        return make_uint4(0u, 0u, 0u, 0u);
+    };
+    float4 cur[4];
+    load_self(cur, dl);
+    uint4 kbits = load_bits(dl);
+    mbar_wait(bhbar, 0);
+    const unsigned char* BHl = smem + gl * 16;
+    int it = 0;
+    for (int job = dl; job < a.n_jobs; job += a.doc_lanes, ++it) {
+        if (tid == 0) {
+            const int itn = it + kPF, jobn = job + kPF * a.doc_lanes;
+            if (jobn < a.n_jobs) {
+                // the stage was last read by iteration itn - kStages
+                if (itn >= kStages) mbar_wait(&empty[itn % kStages], (unsigned)(itn / kStages - 1) & 1u);
+                issue(itn, jobn);
+            }
+            // the rows of B the self loops of a later job need: into L2 now, so that the register prefetch one job ahead
+            // sees L2 latency instead of HBM latency (bytes in flight per SM, not bandwidth, were the limit)
+            const int jobp = job + kL2PF * a.doc_lanes;
+            if (jobp < a.n_jobs) tma_prefetch_l2_2d(tmap_job, slice * kFT, jobp * kJobRows);
+        }
+        const int s = it % kStages;
+        mbar_wait(&full[s], (unsigned)(it / kStages) & 1u);
+        const unsigned char* base = ring + (size_t)s * st_bytes;
+        const int2 rd = reinterpret_cast<const int2*>(base + en_bytes)[grp];
+        const int n_tot = rd.y >> 16, n_nh = rd.y & 0xffff;
+        const int2* ent = reinterpret_cast<const int2*>(base) + rd.x;
+        const int64_t row = (int64_t)job * kJobRows + grp;
+        float4 acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < n_nh; ++p) {  // columns outside the hub set: the self loop (prefetched) or a global gather
+            const int2 en = ent[p];
+            const float v = __int_as_float(en.y);
+            if ((int64_t)en.x == row) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) fma4p(acc[u], v, cur[u]);
+            } else {
+                const float* src = a.B + (int64_t)en.x * a.ldb + (int64_t)q0 * 4;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) fma4p(acc[u], v, ldg_f4(src + u * 32));
+            }
+        }
+        load_self(cur, job + a.doc_lanes);  // next job's self-loop operand: in flight during the hub-column loop
+        int p = n_nh;
+#pragma unroll 1
+        for (; p + 2 <= n_tot; p += 2) {
+            const int2 e0 = ent[p], e1 = ent[p + 1];
+            const unsigned char* r0 = BHl + e0.x;
+            const unsigned char* r1 = BHl + e1.x;
+            const float4 b00 = lds128(r0), b01 = lds128(r0 + 128), b02 = lds128(r0 + 256), b03 = lds128(r0 + 384);
+            const float4 b10 = lds128(r1), b11 = lds128(r1 + 128), b12 = lds128(r1 + 256), b13 = lds128(r1 + 384);
+            const float v0 = __int_as_float(e0.y), v1 = __int_as_float(e1.y);
+            fma4p(acc[0], v0, b00); fma4p(acc[1], v0, b01); fma4p(acc[2], v0, b02); fma4p(acc[3], v0, b03);
+            fma4p(acc[0], v1, b10); fma4p(acc[1], v1, b11); fma4p(acc[2], v1, b12); fma4p(acc[3], v1, b13);
+        }
+        if (p < n_tot) {
+            const int2 e0 = ent[p];
+            const unsigned char* r0 = BHl + e0.x;
+            const float v0 = __int_as_float(e0.y);
+            fma4p(acc[0], v0, lds128(r0)); fma4p(acc[1], v0, lds128(r0 + 128));
+            fma4p(acc[2], v0, lds128(r0 + 256)); fma4p(acc[3], v0, lds128(r0 + 384));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads the stage
+        const uint4 kb = kbits;
+        kbits = load_bits(job + a.doc_lanes);
+        if (n_tot > 0) {
+            // fused epilogue (EpiStore semantics, tg_epilogue.cuh) with the per-thread constants held in registers
+            float* yrow = epi.Y + row * epi.ldy + (int64_t)q0 * 4;
+            if (row >= epi.raw_row_begin) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(yrow + u * 32) = acc[u];
+            } else {
+                Philox4 rnd = Philox4{0, 0, 0, 0};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float y[4] = {acc[u].x, acc[u].y, acc[u].z, acc[u].w};
+                    const float bb[4] = {bias4[u].x, bias4[u].y, bias4[u].z, bias4[u].w};
+                    if (epi.bias) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) y[k] += bb[k];
+                    }
+                    if (epi.relu) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) y[k] = fmaxf(y[k], 0.f);
+                    }
+                    if (epi.out_scale) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) y[k] *= gscale;
+                    }
+                    const int q = q0 + 8 * u;
+                    if (a.keep_bits) {
+                        const uint32_t w = (u == 0 ? kb.x : u == 1 ? kb.y : u == 2 ? kb.z : kb.w) >> (4 * gl);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) y[k] = ((w >> k) & 1u) ? y[k] * epi.scale : 0.f;
+                    } else if (epi.drop_mode == 1) {
+                        if (!(u & 1)) rnd = dropout_philox(row, (uint32_t)(q & 7), (uint32_t)(q >> 4), epi.seed, rng_offset);
+                        uint32_t r16[4];
+                        dropout_u16x4(rnd, (q >> 3) & 1, r16);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) y[k] = (r16[k] < epi.keep_thr) ? y[k] * epi.scale : 0.f;
+                    } else if (epi.drop_mode == 2) {
+                        const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(epi.keep_mask + row * (int64_t)epi.n_feat + (int64_t)q * 4));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) y[k] = ((m >> (8 * k)) & 0xffu) ? y[k] * epi.scale : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(yrow + u * 32) = make_float4(y[0], y[1], y[2], y[3]);
+                }
+            }
+        }
+    }
+}
+
+// Bit-packed keep mask of the Philox dropout (definition: tg_common.cuh).  One thread per Philox call = (row, 64-column
+// block, lane8): its eight 16-bit draws are the columns 64 blk + 32 half + 4 lane8 + k, i.e. bits 4 lane8 + k of the words
+// 2 blk + half; the eight lanes of a block OR their nibbles together and lane 0 writes the two words.
+__global__ void __launch_bounds__(256) r2_keep_bits_kernel(uint32_t* __restrict__ out, int64_t n_rows, int n_blk, int blk_shift, uint32_t thr,
+                                                            uint64_t seed, uint64_t offset,
+                                                            const unsigned long long* __restrict__ offset_dev) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = n_rows * (int64_t)n_blk * 8;
+    const bool live = idx < total;
+    const int lane8 = (int)(idx & 7);
+    const int64_t rb = idx >> 3;
+    // n_blk = n_feat / 64 is 2, 4 or 8 for the usual widths: a shift instead of a 64-bit division
+    const int64_t row = blk_shift >= 0 ? (rb >> blk_shift) : rb / n_blk;
+    const int blk = (int)(rb - row * n_blk);
+    uint32_t w0 = 0, w1 = 0;
+    if (live) {
+        const uint64_t off = offset_dev ? offset + __ldg(offset_dev) : offset;
+        const Philox4 r = dropout_philox(row, (uint32_t)lane8, (uint32_t)blk, seed, off);
+        uint32_t u[4];
+        dropout_u16x4(r, 0, u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w0 |= (u[k] < thr ? 1u : 0u) << k;
+        dropout_u16x4(r, 1, u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w1 |= (u[k] < thr ? 1u : 0u) << k;
+        w0 <<= 4 * lane8;
+        w1 <<= 4 * lane8;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        w0 |= __shfl_xor_sync(0xffffffffu, w0, o);
+        w1 |= __shfl_xor_sync(0xffffffffu, w1, o);
+    }
+    if (live && lane8 == 0) *reinterpret_cast<uint2*>(out + (row * n_blk + blk) * 2) = make_uint2(w0, w1);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) roles2_kernel(const R2Args a, const EpiStore epi, const __grid_constant__ CUtensorMap tmapB,
+                                                            const __grid_constant__ CUtensorMap tmapJob) {
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 2];
+    // TMA destinations must be 128-byte aligned: align the dynamic base by hand (the launch requests 128 spare bytes)
+    unsigned char* smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    const int n_hub_ctas = a.hub_slices * a.hub_lanes;
+    const int bid = blockIdx.x;
+    if (bid < n_hub_ctas) {
+        if (a.only_role == 2) return;
+        hub_role(a, &tmapB, smem, bars, bid);
+    } else {
+        if (a.only_role == 1) return;
+        doc_role(a, epi, &tmapJob, smem, bars, bid - n_hub_ctas);
+    }
+}
+
+// =============================================== plan build =============================================================
+// number of hub-row entries in every column (= entries the hub role processes for that node)
+__global__ void r2_hub_deg_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                  const int32_t* __restrict__ hub_rows, int32_t* __restrict__ deg) {
+    const int r = hub_rows[blockIdx.x];
+    const int s = rowptr[r], e = rowptr[r + 1];
+    for (int p = s + threadIdx.x; p < e; p += blockDim.x) atomicAdd(deg + colidx[p], 1);
+}
+
+// one block per hub row: key = chunk * 256 + slot for each of its entries, in storage (column) order
+__global__ void r2_hub_keys_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                   const int32_t* __restrict__ hub_rows, const int64_t* __restrict__ hub_ofs,
+                                   const int32_t* __restrict__ node_chunk, const int32_t* __restrict__ vmap,
+                                   const int32_t* __restrict__ vcnt, uint32_t* __restrict__ keys, int32_t* __restrict__ src) {
+    const int k = blockIdx.x;
+    const int r = hub_rows[k];
+    const int s = rowptr[r], e = rowptr[r + 1];
+    const int64_t o = hub_ofs[k];
+    const int nv = vcnt[k];
+    for (int p = s + threadIdx.x; p < e; p += blockDim.x) {
+        const int c = colidx[p];
+        keys[o + (p - s)] = (uint32_t)node_chunk[c] * (uint32_t)kKv + (uint32_t)vmap[k * 8 + (c % nv)];
+        src[o + (p - s)] = p;
+    }
+}
+
+__global__ void r2_hub_gather_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ src,
+                                     const int32_t* __restrict__ colidx, const float* __restrict__ vals, int64_t hub_nnz,
+                                     const int32_t* __restrict__ cstart, int2* __restrict__ hent) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hub_nnz) return;
+    const int p = src[i];
+    const int c = (int)(keys[i] / (uint32_t)kKv);
+    hent[i] = make_int2((colidx[p] - cstart[c]) * kRowBytes, __float_as_int(vals[p]));
+}
+
+// tab[c][s] = first sorted position with key >= c*256 + s   (s = 256 gives the start of chunk c+1)
+__global__ void r2_hub_table_kernel(const uint32_t* __restrict__ keys, int64_t hub_nnz, int n_chunks, int32_t* __restrict__ tab) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_chunks * kHtW) return;
+    const int c = (int)(i / kHtW);
+    int s = (int)(i % kHtW);
+    if (s > kKv) s = kKv;
+    const uint64_t want = (uint64_t)c * kKv + s;
+    int64_t lo = 0, hi = hub_nnz;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((uint64_t)keys[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    tab[i] = (int32_t)lo;
+}
+
+// offsets relative to the chunk's even-aligned base (16-byte aligned bulk copies) + chunk descriptors
+__global__ void r2_hub_rel_kernel(const int32_t* __restrict__ tab_abs, int n_chunks, const int32_t* __restrict__ cstart,
+                                  int32_t* __restrict__ tab, int4* __restrict__ cdesc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_chunks * kHtW) return;
+    const int c = (int)(i / kHtW), s = (int)(i % kHtW);
+    const int base = tab_abs[(int64_t)c * kHtW] & ~1;
+    tab[i] = tab_abs[i] - base;
+    if (s == 0) cdesc[c] = make_int4(base, ((tab_abs[(int64_t)c * kHtW + kKv] - base) + 1) & ~1, cstart[c], 0);
+}
+
+__global__ void r2_row_len_kernel(const int32_t* __restrict__ rowptr, int64_t n, int64_t n_pad, int hub_threshold, int32_t* __restrict__ len) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_pad) return;
+    int l = 0;
+    if (r < n) {
+        l = rowptr[r + 1] - rowptr[r];
+        if (l > hub_threshold) l = 0;
+    }
+    len[r] = l;
+}
+
+// compact copy of the short rows' entries (already reordered: other columns | hub columns) + row / job descriptors
+__global__ void r2_doc_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rsplit,
+                                   const int2* __restrict__ dent, const int32_t* __restrict__ start, int64_t n, int64_t n_pad,
+                                   int hub_threshold, int2* __restrict__ dent2, int2* __restrict__ rdesc, int2* __restrict__ jdesc) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    const int64_t j0 = r / kJobRows * kJobRows;
+    const int jbase = start[j0] & ~1;
+    int2 rd = make_int2(0, 0);
+    if (r < n) {
+        const int s = rowptr[r], e = rowptr[r + 1];
+        const int len = e - s;
+        if (len > 0 && len <= hub_threshold) {
+            const int n_other = rsplit[r] - s;
+            const int o = start[r];
+            for (int p = 0; p < len; ++p) {
+                const int2 en = dent[s + p];
+                dent2[o + p] = make_int2(p < n_other ? en.x : en.x * kRowBytes, en.y);
+            }
+            rd = make_int2(o - jbase, (len << 16) | n_other);
+        }
+    }
+    rdesc[r] = rd;
+    if (r == j0) {
+        const int64_t j1 = (j0 + kJobRows < n_pad) ? j0 + kJobRows : n_pad;
+        jdesc[r / kJobRows] = make_int2(jbase, ((start[j1] - jbase) + 1) & ~1);
+    }
+}
+
+int env_int2(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+size_t hub_smem(int T, int cap_hub) {
+    return 2 * ((size_t)T * kRowBytes + align128((size_t)cap_hub * 8) + align128((size_t)kHtW * 4));
+}
+size_t doc_smem(int Kh, int cap_doc) {
+    return align128((size_t)Kh * kRowBytes) + (size_t)kStages * (align128((size_t)cap_doc * 8) + (size_t)kJobRows * 8);
+}
+
+}  // namespace
+
+void roles2_plan_free(tg_plan* pl) {
+    if (!pl) return;
+    cudaFree(pl->r2_hent); cudaFree(pl->r2_htab); cudaFree(pl->r2_cdesc); cudaFree(pl->r2_vmap); cudaFree(pl->r2_vcnt);
+    cudaFree(pl->r2_dent); cudaFree(pl->r2_rdesc); cudaFree(pl->r2_jdesc);
+    pl->r2_hent = nullptr; pl->r2_htab = nullptr; pl->r2_cdesc = nullptr; pl->r2_vmap = nullptr; pl->r2_vcnt = nullptr;
+    pl->r2_dent = nullptr; pl->r2_rdesc = nullptr; pl->r2_jdesc = nullptr;
+    pl->r2_ok = false;
+}
+
+// Builds the sub-plan of the warp-per-slot kernels on top of the streaming sub-plan (which provides colidx2 / rsplit, the
+// per-row reordered entry copy).  d_slot_of: device [n] hub index of every node or -1; h_hub_rows: host [n_hub].
+int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx, const float* vals, const int32_t* h_rowptr,
+                      const int32_t* d_slot_of, const int32_t* h_hub_rows, cudaStream_t st) {
+    (void)d_slot_of;
+    pl->r2_ok = false;
+    if (env_int2("TG_ROLES2", 1) == 0) return TG_OK;
+    if (!pl->stream_ok || pl->n_hub < 1 || pl->n_hub > kKv || !pl->colidx2 || !pl->rsplit) return TG_OK;
+    const int64_t n = pl->n_rows;
+    const int Kh = pl->n_hub;
+    const int64_t hub_nnz = pl->hub_nnz;
+    if (hub_nnz >= (int64_t)0x7fffffff) return TG_OK;
+
+    // ---- slots: split the heaviest hub rows into the spare slots, deal the pieces to the 16 warps longest-first ----
+    std::vector<int32_t> vcnt((size_t)Kh, 1), vmap((size_t)Kh * 8, 0);
+    std::vector<int64_t> hub_ofs((size_t)Kh);
+    {
+        std::vector<double> len((size_t)Kh);
+        int64_t run = 0;
+        for (int k = 0; k < Kh; ++k) {
+            const int32_t r = h_hub_rows[k];
+            hub_ofs[(size_t)k] = run;
+            len[(size_t)k] = (double)(h_rowptr[(size_t)r + 1] - h_rowptr[(size_t)r]);
+            run += h_rowptr[(size_t)r + 1] - h_rowptr[(size_t)r];
+        }
+        int spare = kKv - Kh;
+        while (spare > 0) {
+            int best = -1;
+            for (int k = 0; k < Kh; ++k)
+                if (vcnt[(size_t)k] < 8 && (best < 0 || len[(size_t)k] / vcnt[(size_t)k] > len[(size_t)best] / vcnt[(size_t)best])) best = k;
+            if (best < 0) break;
+            vcnt[(size_t)best] += 1;
+            --spare;
+        }
+        struct Piece { double w; int k, j; };
+        std::vector<Piece> pieces;
+        for (int k = 0; k < Kh; ++k)
+            for (int j = 0; j < vcnt[(size_t)k]; ++j) pieces.push_back(Piece{len[(size_t)k] / vcnt[(size_t)k], k, j});
+        std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) { return x.w > y.w; });
+        double load[kWarps] = {0};
+        int used[kWarps] = {0};
+        for (const Piece& pc : pieces) {
+            int best = -1;
+            for (int w = 0; w < kWarps; ++w)
+                if (used[w] < kKPW && (best < 0 || load[w] < load[best])) best = w;
+            vmap[(size_t)pc.k * 8 + pc.j] = best * kKPW + used[best];
+            used[best] += 1;
+            load[best] += pc.w;
+        }
+    }
+
+    int64_t* d_ofs = nullptr;
+    uint32_t *keys_a = nullptr, *keys_b = nullptr;
+    int32_t *src_a = nullptr, *src_b = nullptr, *tab_abs = nullptr, *d_len = nullptr, *d_start = nullptr;
+    void* tmp = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto release_tmp = [&]() {
+        cudaFree(d_ofs); cudaFree(keys_a); cudaFree(keys_b); cudaFree(src_a); cudaFree(src_b); cudaFree(tab_abs);
+        cudaFree(d_len); cudaFree(d_start); cudaFree(tmp);
+        d_ofs = nullptr; keys_a = keys_b = nullptr; src_a = src_b = tab_abs = d_len = d_start = nullptr; tmp = nullptr;
+    };
+    auto fail = [&](cudaError_t err, const char* what) {
+        release_tmp();
+        roles2_plan_free(pl);
+        return cuda_fail(err, what, __FILE__, __LINE__);
+    };
+#define TG_TRY(call) do { e = (call); if (e != cudaSuccess) return fail(e, #call); } while (0)
+    TG_TRY(cudaMalloc((void**)&d_ofs, (size_t)Kh * sizeof(int64_t)));
+    TG_TRY(cudaMemcpyAsync(d_ofs, hub_ofs.data(), (size_t)Kh * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    TG_TRY(cudaMalloc((void**)&pl->r2_vmap, (size_t)Kh * 8 * sizeof(int32_t)));
+    TG_TRY(cudaMemcpyAsync(pl->r2_vmap, vmap.data(), (size_t)Kh * 8 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    TG_TRY(cudaMalloc((void**)&pl->r2_vcnt, (size_t)Kh * sizeof(int32_t)));
+    TG_TRY(cudaMemcpyAsync(pl->r2_vcnt, vcnt.data(), (size_t)Kh * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    TG_TRY(cudaMalloc((void**)&keys_a, (size_t)hub_nnz * sizeof(uint32_t)));
+    TG_TRY(cudaMalloc((void**)&keys_b, (size_t)hub_nnz * sizeof(uint32_t)));
+    TG_TRY(cudaMalloc((void**)&src_a, (size_t)hub_nnz * sizeof(int32_t)));
+    TG_TRY(cudaMalloc((void**)&src_b, (size_t)hub_nnz * sizeof(int32_t)));
+    TG_TRY(cudaMalloc((void**)&pl->r2_hent, ((size_t)hub_nnz + 2) * sizeof(int2)));
+
+    // ---- hub side: variable-height chunks ------------------------------------------------------------------------------
+    // A chunk is a run of consecutive nodes with at most T rows AND at most `cap` hub entries, so that its tile of B and
+    // its entries always fit one shared-memory stage: document ranges are cut by the row limit, the dense topic-topic
+    // block (every hub node carries Kh entries) by the entry limit.
+    const double avg_deg = (double)hub_nnz / (double)n;
+    static const int kTs[] = {192, 176, 160, 144, 128, 96, 64, 32};
+    const int t_first = env_int2("TG_ROLES2_T", 192);
+    int T = 0, cap = 0;
+    for (int t : kTs) {
+        if (t > t_first) continue;
+        const int64_t room = (int64_t)(kSmemMax - 256) / 2 - (int64_t)t * kRowBytes - (int64_t)align128((size_t)kHtW * 4);
+        const int cap_fit = (int)std::min<int64_t>(room / 8, 1 << 20) & ~1;
+        if (cap_fit < Kh + 2 || (double)cap_fit < 1.25 * avg_deg * t + 32) continue;
+        T = t;
+        cap = cap_fit;
+        break;
+    }
+    if (T == 0) {
+        release_tmp();
+        roles2_plan_free(pl);
+        return TG_OK;
+    }
+    std::vector<int32_t> h_deg((size_t)n), node_chunk((size_t)n), cstart;
+    {
+        int32_t* d_deg = nullptr;
+        TG_TRY(cudaMalloc((void**)&d_deg, (size_t)n * sizeof(int32_t)));
+        e = cudaMemsetAsync(d_deg, 0, (size_t)n * sizeof(int32_t), st);
+        if (e == cudaSuccess) {
+            r2_hub_deg_kernel<<<Kh, 256, 0, st>>>(rowptr, colidx, pl->hub_rows, d_deg);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_deg.data(), d_deg, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(d_deg);
+        if (e != cudaSuccess) return fail(e, "hub degree histogram");
+    }
+    {
+        int rows = 0, ents = 0;
+        cstart.push_back(0);
+        for (int64_t j = 0; j < n; ++j) {
+            const int d = h_deg[(size_t)j];
+            if (rows == T || ents + d > cap - 2) {  // -2: the staged run starts at an even entry and has even length
+                cstart.push_back((int32_t)j);
+                rows = 0;
+                ents = 0;
+            }
+            node_chunk[(size_t)j] = (int32_t)cstart.size() - 1;
+            rows += 1;
+            ents += d;
+        }
+    }
+    const int n_chunks = (int)cstart.size();
+    cstart.push_back((int32_t)n);
+    if ((uint64_t)n_chunks * (uint64_t)kKv >= 0xFFFFFFFFull) {
+        release_tmp();
+        roles2_plan_free(pl);
+        return TG_OK;
+    }
+    {
+        int32_t *d_node_chunk = nullptr, *d_cstart = nullptr;
+        auto drop = [&]() { cudaFree(d_node_chunk); cudaFree(d_cstart); };
+#define TG_TRY2(call) do { e = (call); if (e != cudaSuccess) { drop(); return fail(e, #call); } } while (0)
+        TG_TRY2(cudaMalloc((void**)&d_node_chunk, (size_t)n * sizeof(int32_t)));
+        TG_TRY2(cudaMalloc((void**)&d_cstart, (size_t)(n_chunks + 1) * sizeof(int32_t)));
+        TG_TRY2(cudaMemcpyAsync(d_node_chunk, node_chunk.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        TG_TRY2(cudaMemcpyAsync(d_cstart, cstart.data(), (size_t)(n_chunks + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        r2_hub_keys_kernel<<<Kh, 256, 0, st>>>(rowptr, colidx, pl->hub_rows, d_ofs, d_node_chunk, pl->r2_vmap, pl->r2_vcnt, keys_a, src_a);
+        TG_TRY2(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        int end_bit = 1;
+        while (end_bit < 32 && (1ull << end_bit) < (uint64_t)n_chunks * kKv) ++end_bit;
+        TG_TRY2(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, src_a, src_b, (int)hub_nnz, 0, end_bit, st));
+        TG_TRY2(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+        // stable: inside a (chunk, slot) run the entries keep their column order
+        TG_TRY2(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_a, keys_b, src_a, src_b, (int)hub_nnz, 0, end_bit, st));
+        const int64_t tab_n = (int64_t)n_chunks * kHtW;
+        TG_TRY2(cudaMalloc((void**)&tab_abs, (size_t)tab_n * sizeof(int32_t)));
+        TG_TRY2(cudaMalloc((void**)&pl->r2_htab, (size_t)tab_n * sizeof(int32_t)));
+        TG_TRY2(cudaMalloc((void**)&pl->r2_cdesc, (size_t)n_chunks * sizeof(int4)));
+        r2_hub_table_kernel<<<(unsigned)ceil_div64(tab_n, 256), 256, 0, st>>>(keys_b, hub_nnz, n_chunks, tab_abs);
+        TG_TRY2(cudaGetLastError());
+        r2_hub_rel_kernel<<<(unsigned)ceil_div64(tab_n, 256), 256, 0, st>>>(tab_abs, n_chunks, d_cstart, pl->r2_htab, pl->r2_cdesc);
+        TG_TRY2(cudaGetLastError());
+        TG_TRY2(cudaMemsetAsync(pl->r2_hent, 0, ((size_t)hub_nnz + 2) * sizeof(int2), st));
+        r2_hub_gather_kernel<<<(unsigned)ceil_div64(hub_nnz, 256), 256, 0, st>>>(keys_b, src_b, colidx, vals, hub_nnz, d_cstart, pl->r2_hent);
+        TG_TRY2(cudaGetLastError());
+        TG_TRY2(cudaStreamSynchronize(st));
+#undef TG_TRY2
+        drop();
+        pl->r2_T = T;
+        pl->r2_n_chunks = n_chunks;
+        pl->r2_cap_hub = cap;
+    }
+
+    // ---- document side: compact entry copy, row descriptors, job descriptors --------------------------------------------------
+    const int64_t n_jobs = ceil_div64(n, kJobRows);
+    const int64_t n_pad = n_jobs * kJobRows;
+    const int64_t doc_nnz = pl->nnz - hub_nnz;
+    TG_TRY(cudaMalloc((void**)&d_len, (size_t)(n_pad + 1) * sizeof(int32_t)));
+    TG_TRY(cudaMalloc((void**)&d_start, (size_t)(n_pad + 1) * sizeof(int32_t)));
+    r2_row_len_kernel<<<(unsigned)ceil_div64(n_pad + 1, 256), 256, 0, st>>>(rowptr, n, n_pad, pl->hub_threshold, d_len);
+    TG_TRY(cudaGetLastError());
+    size_t scan_bytes = 0;
+    TG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_len, d_start, (int)(n_pad + 1), st));
+    cudaFree(tmp); tmp = nullptr;
+    TG_TRY(cudaMalloc(&tmp, scan_bytes ? scan_bytes : 1));
+    TG_TRY(cub::DeviceScan::ExclusiveSum(tmp, scan_bytes, d_len, d_start, (int)(n_pad + 1), st));
+    TG_TRY(cudaMalloc((void**)&pl->r2_dent, ((size_t)doc_nnz + 2) * sizeof(int2)));
+    TG_TRY(cudaMemsetAsync(pl->r2_dent, 0, ((size_t)doc_nnz + 2) * sizeof(int2), st));
+    TG_TRY(cudaMalloc((void**)&pl->r2_rdesc, (size_t)n_pad * sizeof(int2)));
+    TG_TRY(cudaMalloc((void**)&pl->r2_jdesc, (size_t)n_jobs * sizeof(int2)));
+    r2_doc_fill_kernel<<<(unsigned)ceil_div64(n_pad, 256), 256, 0, st>>>(rowptr, pl->rsplit, reinterpret_cast<const int2*>(pl->colidx2),
+                                                                          d_start, n, n_pad, pl->hub_threshold, pl->r2_dent,
+                                                                          pl->r2_rdesc, pl->r2_jdesc);
+    TG_TRY(cudaGetLastError());
+    std::vector<int2> h_jdesc((size_t)n_jobs);
+    TG_TRY(cudaMemcpyAsync(h_jdesc.data(), pl->r2_jdesc, (size_t)n_jobs * sizeof(int2), cudaMemcpyDeviceToHost, st));
+    TG_TRY(cudaStreamSynchronize(st));
+#undef TG_TRY
+    int cap_doc = 2;
+    for (const int2& d : h_jdesc) cap_doc = std::max(cap_doc, d.y);
+    release_tmp();
+    pl->r2_n_jobs = (int32_t)n_jobs;
+    pl->r2_cap_doc = cap_doc;
+    if (doc_smem(Kh, cap_doc) + 256 > kSmemMax) {
+        roles2_plan_free(pl);
+        return TG_OK;
+    }
+    pl->r2_ok = true;
+    return TG_OK;
+}
+
+bool roles2_applicable(const tg_plan* pl, const StreamCall& c) {
+    if (!pl || !pl->r2_ok) return false;
+    if (env_int2("TG_ROLES2", 1) == 0) return false;
+    if (c.n_feat < kFT || c.n_feat % kFT != 0 || c.n_feat > 1024) return false;
+    if (c.ldb % 4 != 0 || !aligned16(c.B) || !encode_tiled_fn()) return false;
+    return true;
+}
+
+size_t roles2_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
+    if (!pl || !pl->r2_ok) return 0;
+    const size_t ld = (size_t)((n_feat + 3) / 4) * 4;
+    // per-CTA hub partials + the bit-packed dropout keep mask (n x n_feat / 8 bytes)
+    return (size_t)kNumSM * kKv * ld * sizeof(float) + 16 + (size_t)pl->n_rows * (ld / 8) + 256;
+}
+
+int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st) {
+    R2Args a;
+    a.hent = pl->r2_hent; a.htab = pl->r2_htab; a.cdesc = pl->r2_cdesc;
+    a.T = pl->r2_T; a.n_chunks = pl->r2_n_chunks; a.cap_hub = pl->r2_cap_hub;
+    a.dent = pl->r2_dent; a.rdesc = pl->r2_rdesc; a.jdesc = pl->r2_jdesc;
+    a.n_jobs = pl->r2_n_jobs; a.cap_doc = pl->r2_cap_doc;
+    a.hub_rows = pl->hub_rows; a.Kh = pl->n_hub;
+    a.B = c.B; a.ldb = c.ldb; a.n = pl->n_rows; a.n_chunks4 = c.n_feat / 4;
+    a.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(c.workspace) + 15u) & ~(uintptr_t)15u);
+    a.ldp = (int64_t)((c.n_feat + 3) / 4) * 4;
+    const int slices = c.n_feat / kFT;
+    a.hub_slices = a.doc_slices = slices;
+    // Philox dropout: the keep mask is drawn by a separate ALU-bound kernel into a bit-packed side buffer (1 bit per
+    // element) instead of inside the document role, whose CTAs have no issue slots to spare (ncu: the in-kernel RNG
+    // cost 0.4 ms at 1M x 256).  Same mask, bit for bit, as the in-kernel definition (tg_common.cuh).
+    a.keep_bits = nullptr;
+    if (epi.drop_mode == 1 && env_int2("TG_ROLES2_BITMASK", 1) != 0) {
+        const size_t part_bytes = ((size_t)kNumSM * kKv * a.ldp * sizeof(float) + 16 + 255) & ~(size_t)255;
+        const size_t mask_bytes = (size_t)pl->n_rows * (size_t)(c.n_feat / 8);
+        if (c.workspace_bytes >= part_bytes + mask_bytes + 16) {
+            uint32_t* bits = reinterpret_cast<uint32_t*>(
+                (reinterpret_cast<uintptr_t>(c.workspace) + part_bytes + 15u) & ~(uintptr_t)15u);
+            const int n_blk = c.n_feat / 64;
+            const int64_t threads = pl->n_rows * (int64_t)n_blk * 8;
+            int blk_shift = -1;
+            for (int sh = 0; sh < 8; ++sh)
+                if ((1 << sh) == n_blk) blk_shift = sh;
+            r2_keep_bits_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, st>>>(bits, pl->n_rows, n_blk, blk_shift, epi.keep_thr, epi.seed,
+                                                                                    epi.offset, epi.offset_dev);
+            TG_LAUNCH_CHECK();
+            a.keep_bits = bits;
+        }
+    }
+    // share of the SMs given to the hub role (both fronts must advance together so that the second reader of a row of B
+    // hits L2); the document role also runs the Philox dropout when the epilogue draws the mask itself
+    const int hub_pct = env_int2("TG_ROLES2_HUB_PCT", (epi.drop_mode == 1 && !a.keep_bits) ? 38 : 44);
+    int hub_lanes = (kNumSM * hub_pct / 100) / slices;
+    if (hub_lanes < 1) hub_lanes = 1;
+    if (hub_lanes > a.n_chunks) hub_lanes = a.n_chunks;
+    int doc_lanes = (kNumSM - hub_lanes * slices) / slices;
+    if (doc_lanes < 1) doc_lanes = 1;
+    if (doc_lanes > a.n_jobs) doc_lanes = a.n_jobs;
+    a.hub_lanes = hub_lanes;
+    a.doc_lanes = doc_lanes;
+    a.only_role = env_int2("TG_ROLES_ONLY", 0);
+    const size_t need = (size_t)hub_lanes * kKv * a.ldp * sizeof(float);
+    TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
+               c.workspace_bytes, need + 16);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    TG_REQUIRE(make_tensor_map(&tmap, a.B, a.n, c.n_feat, a.ldb, a.T, kFT), TG_ERR_UNSUPPORTED,
+               "cuTensorMapEncodeTiled failed (TMA tile of the dense operand)");
+    CUtensorMap tmap_job;
+    memset(&tmap_job, 0, sizeof(tmap_job));
+    TG_REQUIRE(make_tensor_map(&tmap_job, a.B, a.n, c.n_feat, a.ldb, kJobRows, kFT), TG_ERR_UNSUPPORTED,
+               "cuTensorMapEncodeTiled failed (L2 prefetch tile of the dense operand)");
+    size_t smem = std::max(hub_smem(a.T, a.cap_hub), doc_smem(a.Kh, a.cap_doc)) + 128;
+    TG_CUDA(cudaFuncSetAttribute(roles2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((hub_lanes + doc_lanes) * slices);
+    roles2_kernel<<<grid, kThreads, smem, st>>>(a, epi, tmap, tmap_job);
+    TG_LAUNCH_CHECK();
+    FinishArgs f{a.partials, a.ldp, hub_lanes, a.Kh, kKv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
+    return finish_run(f, epi, st);
+}
+
+}  // namespace tg

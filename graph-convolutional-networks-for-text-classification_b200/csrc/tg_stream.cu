@@ -22,9 +22,12 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "tg_stream.cuh"
+#include "tg_async.cuh"
+#include "tg_finish.cuh"
 
 namespace tg {
 
@@ -58,63 +61,6 @@ struct StreamArgs {
     int64_t ldp;
 };
 
-// ---- cp.async helpers ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    const int bytes = valid ? 16 : 0;  // src-size 0 -> 16 bytes of zeros
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, bool valid) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    const int bytes = valid ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// ---- TMA (bulk async copy) + mbarrier helpers: one elected thread moves a whole stage -----------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// 2-D tile [box rows x box cols] of a row-major matrix described by a tensor map -> shared memory (zero fill outside)
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int col, int row, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(col), "r"(row), "r"(smem_u32(bar))
-        : "memory");
-}
-// contiguous run global -> shared memory (16-byte aligned, size multiple of 16)
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__host__ __device__ inline size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
-
 struct StageView {
     float* Bs;       // [T][FT]
     int32_t* rp;     // [T+1]
@@ -123,8 +69,6 @@ struct StageView {
     int2* hent;      // [cap_hub]
     int32_t* htab;   // [Kh+1]
 };
-
-__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 __host__ __device__ inline size_t stage_bytes(int T, int FT, int cap_doc, int cap_hub, int Kh) {
     return align16((size_t)T * FT * 4) + align16((size_t)(T + 1) * 4) + align16((size_t)T * 4) +
@@ -710,90 +654,10 @@ __global__ void __launch_bounds__(kNThreads) stream_narrow_kernel(const StreamAr
     }
 }
 
-// ---- finishing kernel: hub row k = sum over CTA groups (fixed order) + epilogue --------------------------------------
-template <int VEC, int G, int CPL, class Epi>
-__global__ void __launch_bounds__(256) stream_finish_kernel(const float* __restrict__ partials, int64_t ldp, int n_groups,
-                                                            int Kh, int Kv, const int32_t* __restrict__ vmap,
-                                                            const int32_t* __restrict__ vcnt,
-                                                            const int32_t* __restrict__ hub_rows, int n_chunks,
-                                                            const Epi epi) {
-    // One block row-group per hub row; the 8 warps of a block take the CTA partials g = w, w+8, ... (each warp in
-    // ascending order), deposit their sums in shared memory and warp 0 adds the 8 deposits in warp order: a fixed tree.
-    constexpr int GPW = 32 / G;
-    extern __shared__ __align__(16) float fin_s[];  // [8 warps][GPW groups][G*CPL*VEC]
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int gl = lane & (G - 1);
-    const int gw = lane / G;
-    const unsigned gmask = group_mask<G>(lane);
-    const int k = blockIdx.x * GPW + gw;
-    Chunk<VEC> acc[CPL];
-#pragma unroll
-    for (int i = 0; i < CPL; ++i) acc[i] = chunk_zero<VEC>();
-    if (k < Kh) {
-        const int nv = __ldg(vcnt + k);
-        for (int j = 0; j < nv; ++j) {
-            const int v = __ldg(vmap + k * 8 + j);
-            for (int g = warp; g < n_groups; g += 8) {
-                const float* src = partials + ((int64_t)g * Kv + v) * ldp;
-#pragma unroll
-                for (int i = 0; i < CPL; ++i) {
-                    const int chunk = gl + i * G;
-                    if (chunk < n_chunks) {
-                        const Chunk<VEC> t = chunk_ldg<VEC>(src + (int64_t)chunk * VEC);
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) acc[i].v[e] += t.v[e];
-                    }
-                }
-            }
-        }
-    }
-    constexpr int ROWF = G * CPL * VEC;
-    float* mine = fin_s + ((size_t)warp * GPW + gw) * ROWF;
-#pragma unroll
-    for (int i = 0; i < CPL; ++i)
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) mine[(gl + i * G) * VEC + e] = acc[i].v[e];
-    __syncthreads();
-    if (warp != 0 || k >= Kh) return;
-#pragma unroll
-    for (int i = 0; i < CPL; ++i) acc[i] = chunk_zero<VEC>();
-    for (int w = 0; w < 8; ++w) {
-        const float* src = fin_s + ((size_t)w * GPW + gw) * ROWF;
-#pragma unroll
-        for (int i = 0; i < CPL; ++i)
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[i].v[e] += src[(gl + i * G) * VEC + e];
-    }
-    epi.template apply<VEC, G, CPL>((int64_t)__ldg(hub_rows + k), gl, gmask, n_chunks, acc);
-}
-
-struct FinishArgs {
-    const float* partials;
-    int64_t ldp;
-    int n_groups, Kh, Kv;
-    const int32_t *vmap, *vcnt, *hub_rows;
-    int n_chunks;
-};
-
-template <int VEC, int G, int CPL, class Epi>
-static int launch_finish(const FinishArgs& f, const Epi& epi, cudaStream_t st) {
-    constexpr int GPW = 32 / G;
-    const size_t smem = (size_t)8 * GPW * G * CPL * VEC * sizeof(float);
-    stream_finish_kernel<VEC, G, CPL, Epi><<<(unsigned)ceil_div64(f.Kh, GPW), 256, smem, st>>>(
-        f.partials, f.ldp, f.n_groups, f.Kh, f.Kv, f.vmap, f.vcnt, f.hub_rows, f.n_chunks, epi);
-    TG_LAUNCH_CHECK();
-    return TG_OK;
-}
-
 template <class Epi>
 static int finish_dispatch(const StreamArgs& a, const float* partials, int n_groups, const Epi& epi, cudaStream_t st) {
     FinishArgs f{partials, a.ldp, n_groups, a.Kh, a.Kv, a.vmap, a.vcnt, a.hub_rows, a.n_chunks4};
-#define TG_LAUNCH_FIN(V, G, C) launch_finish<V, G, C>(f, epi, st)
-    TG_SHAPE_SWITCH(4, f.n_chunks, TG_LAUNCH_FIN);
-#undef TG_LAUNCH_FIN
-    set_error("n_feat too wide for the streaming finish kernel");
-    return TG_ERR_UNSUPPORTED;
+    return finish_run(f, epi, st);
 }
 
 // ---- launch ------------------------------------------------------------------------------------------------------------------
@@ -827,38 +691,6 @@ static size_t roles_hub_smem(const tg_plan* pl) {
                 align128((size_t)(pl->n_vslot + kHtabPad) * 4));
 }
 
-// ---- tensor map for the TMA tile loads of B (driver entry point fetched at run time: no libcuda link dependency) ----
-typedef CUresult (*tg_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static tg_encode_tiled_fn encode_tiled_fn() {
-    static tg_encode_tiled_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<tg_encode_tiled_fn>(p);
-        else
-            (void)cudaGetLastError();
-    }
-    return fn;
-}
-
-// [rows x cols] fp32 row-major with leading dimension ldb, tiles of box_rows x 64 columns, no swizzle, zero OOB fill
-static bool make_tensor_map(CUtensorMap* map, const float* B, int64_t rows, int64_t cols, int64_t ldb, int box_rows) {
-    tg_encode_tiled_fn fn = encode_tiled_fn();
-    if (!fn || box_rows > 256 || (ldb * 4) % 16 != 0) return false;
-    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t gstr[1] = {(cuuint64_t)ldb * 4};
-    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1u, 1u};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(B), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 static size_t roles_doc_smem(const tg_plan* pl, int CPLD) { return align16((size_t)pl->n_hub * 32 * CPLD * 4); }
 
 static int roles_cpld(const tg_plan* pl, int n_feat) {
@@ -901,7 +733,7 @@ static int launch_roles(const tg_plan* pl, const StreamCall& c, RolesArgs ra, co
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     ra.use_tma = 1;
-    TG_REQUIRE(make_tensor_map(&tmap, a.B, a.n, c.n_feat, a.ldb, a.T), TG_ERR_UNSUPPORTED,
+    TG_REQUIRE(make_tensor_map(&tmap, a.B, a.n, c.n_feat, a.ldb, a.T, 64), TG_ERR_UNSUPPORTED,
                "cuTensorMapEncodeTiled failed (TMA tile of the dense operand)");
     ra.n_doc_jobs = (int)ceil_div64(a.n, ra.doc_job_rows);
     a.n_groups = hub_lanes;
@@ -972,7 +804,8 @@ bool stream_applicable(const tg_plan* pl, const StreamCall& c, bool out_vec4_ok,
 size_t stream_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
     if (!pl || !pl->stream_ok) return 0;
     const size_t ld = (size_t)((n_feat + 3) / 4) * 4;
-    return (size_t)kNumSM * (n_feat <= 32 ? 4 : 1) * pl->n_vslot * ld * sizeof(float) + 16;
+    const size_t ws = (size_t)kNumSM * (n_feat <= 32 ? 4 : 1) * pl->n_vslot * ld * sizeof(float) + 16;
+    return std::max(ws, roles2_workspace_bytes(pl, n_feat));
 }
 
 template <int CPL, int KPG, class Epi>
@@ -1030,6 +863,9 @@ static int run_stream(const tg_plan* pl, const StreamCall& c, const Epi& epi, bo
         TG_NARROW_CASE(1) TG_NARROW_CASE(2) TG_NARROW_CASE(3) TG_NARROW_CASE(4)
         TG_NARROW_CASE(5) TG_NARROW_CASE(6) TG_NARROW_CASE(7) TG_NARROW_CASE(8)
 #undef TG_NARROW_CASE
+    }
+    if constexpr (std::is_same<Epi, EpiStore>::value) {
+        if (!whole_row && roles2_applicable(pl, c)) return roles2_run(pl, c, epi, st);
     }
     if (!whole_row && roles_applicable(pl, c.n_feat)) return run_roles(pl, c, epi, st);
     const int CPL = pick_cpl(pl, c.n_feat, whole_row);
@@ -1150,6 +986,7 @@ __global__ void chunk_desc_kernel(const int32_t* __restrict__ rowptr, const int3
 
 void stream_plan_free(tg_plan* pl) {
     if (!pl) return;
+    roles2_plan_free(pl);
     cudaFree(pl->colidx2); cudaFree(pl->hcol); cudaFree(pl->htab); cudaFree(pl->cdesc); cudaFree(pl->rsplit);
     cudaFree(pl->vmap); cudaFree(pl->vcnt);
     pl->colidx2 = nullptr; pl->hcol = nullptr; pl->hval = nullptr; pl->htab = nullptr; pl->cdesc = nullptr;
@@ -1297,6 +1134,7 @@ int stream_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     pl->stream_ok = true;
     // the kernel must fit at least the narrow configuration
     if (stream_smem_bytes(pl, 1) > kSmemBudget) stream_plan_free(pl);
+    if (pl->stream_ok) return roles2_plan_build(pl, rowptr, colidx, vals, h_rowptr, nullptr, hub_rows.data(), st);
     return TG_OK;
 }
 

@@ -25,6 +25,14 @@ size_t stream_workspace_bytes(const tg_plan* pl, int32_t n_feat);
 // true when the streaming kernel can run this call (plan has the sub-plan, vec4-aligned operands, width supported)
 bool stream_applicable(const tg_plan* pl, const StreamCall& c, bool out_vec4_ok, bool whole_row_epilogue);
 
+// warp-per-slot role kernels (tg_roles2.cu)
+int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx, const float* vals, const int32_t* h_rowptr,
+                      const int32_t* d_slot_of, const int32_t* h_hub_rows, cudaStream_t st);
+void roles2_plan_free(tg_plan* pl);
+bool roles2_applicable(const tg_plan* pl, const StreamCall& c);
+size_t roles2_workspace_bytes(const tg_plan* pl, int32_t n_feat);
+int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st);
+
 int stream_spmm_store(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st);
 int stream_spmm_loss(const tg_plan* pl, const StreamCall& c, const EpiLoss& epi, cudaStream_t st);
 

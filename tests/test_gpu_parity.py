@@ -482,3 +482,51 @@ def test_captured_train_step_matches_eager(tg, small_golden):
     mask = O.philox_keep_mask(n, int(g["nhid"]), 0.5, 77, 2 + 3)
     ref_loss, _, _ = O.gcn_loss_and_grads(None, coo, params, g["target"], g["index"], p=0.5, training=True, keep_mask=mask)
     assert abs(losses[3] - float(ref_loss)) <= 1e-5 * max(1.0, abs(float(ref_loss)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# warp-per-slot role kernels (tg_roles2.cu): F % 128 == 0, <= 256 hub rows
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_docs,n_topics,F,thr", [(3000, 64, 128, 64), (9000, 256, 256, 48), (777, 37, 384, 24),
+                                                    (20000, 100, 256, 256)])
+def test_roles2_kernel_parity(tg, monkeypatch, n_docs, n_topics, F, thr):
+    """Plain product, fused layer-1 epilogue (eval / explicit mask / Philox via the bit-packed side mask / in-kernel
+    Philox) and the raw-row (document-sharded) mode of the warp-per-slot kernels against the oracle; bitwise
+    reproducible; agrees with the first-generation role kernel."""
+    from topicgcn_b200 import graphgen, ops
+    g = graphgen.doc_topic_topic_graph(n_docs, n_topics, deg_lo=2, deg_hi=13, dense_topics=True, seed=3, device="cuda:0")
+    csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n, hub_threshold=thr, segment_nnz=max(8, thr // 2))
+    assert csr.streaming and csr.roles2 and csr.n_hub_rows == n_topics
+    gen = torch.Generator(device="cuda:0").manual_seed(5)
+    B = torch.randn(g.n, F, device=dev(), generator=gen)
+    bias = torch.randn(F, device=dev(), generator=gen)
+    coo = O.Coo(g.rows.cpu().numpy(), g.cols.cpu().numpy(), g.vals.cpu().numpy(), (g.n, g.n))
+    ref = O.spmm(coo, B.cpu().numpy())
+    y = tg.spmm(csr, B)
+    assert rel_err(y.cpu().numpy(), ref) <= SPMM_RTOL
+    assert rel_err(y.cpu().numpy()[n_docs:], ref[n_docs:]) <= SPMM_RTOL      # hub rows on their own scale
+    assert torch.equal(y, tg.spmm(csr, B))                                    # deterministic
+    z = ref + bias.cpu().numpy()
+    h_eval = ops.gc1_forward(csr, B, bias, 0.5, False).cpu().numpy()
+    assert rel_err(h_eval, np.maximum(z, 0)) <= SPMM_RTOL
+    mask = (torch.rand(g.n, F, device=dev(), generator=gen) < 0.5).to(torch.uint8)
+    h_m = ops.gc1_forward(csr, B, bias, 0.5, True, keep_mask=mask).cpu().numpy()
+    assert rel_err(h_m, np.maximum(z, 0) * mask.cpu().numpy() * 2.0) <= SPMM_RTOL
+    pm = O.philox_keep_mask(g.n, F, 0.3, 42, 9)
+    want = np.maximum(z, 0) * pm / 0.7
+    h_bits = ops.gc1_forward(csr, B, bias, 0.3, True, seed=42, offset=9)
+    assert rel_err(h_bits.cpu().numpy(), want) <= SPMM_RTOL
+    assert np.array_equal(h_bits.cpu().numpy() != 0, want != 0)
+    monkeypatch.setenv("TG_ROLES2_BITMASK", "0")                               # Philox drawn inside the kernel
+    h_in = ops.gc1_forward(csr, B, bias, 0.3, True, seed=42, offset=9)
+    assert torch.equal(h_in[:n_docs], h_bits[:n_docs])    # hub rows: the SM split (hence the partial grouping) differs
+    assert torch.equal(h_in != 0, h_bits != 0)
+    assert float((h_in - h_bits).abs().max() / h_bits.abs().max()) <= SPMM_RTOL
+    monkeypatch.delenv("TG_ROLES2_BITMASK")
+    h_raw = ops.gc1_forward(csr, B, bias, 0.5, False, raw_row_begin=n_docs).cpu().numpy()   # document-sharded mode
+    assert rel_err(h_raw[:n_docs], np.maximum(z[:n_docs], 0)) <= SPMM_RTOL
+    assert rel_err(h_raw[n_docs:], ref[n_docs:]) <= SPMM_RTOL
+    monkeypatch.setenv("TG_ROLES2", "0")                                       # first-generation role kernel
+    y_old = tg.spmm(csr, B)
+    monkeypatch.delenv("TG_ROLES2")
+    assert float((y_old - y).abs().max() / y.abs().max()) <= SPMM_RTOL
