@@ -392,19 +392,21 @@ __global__ void __launch_bounds__(TB, (TB == 256 ? 2 : 1)) hidden_bwd_kernel(con
             mask &= mask - 1;  // (0 stays 0)
             const float a = act ? acol[u * hp4] : 0.f;
             const float* dr = dsm + u * CP;  // lane-private row of the dS2 tile
-            float dh0 = 0.f, dh1 = 0.f, dh2 = 0.f, dh3 = 0.f;
+            // packed fp32 FMAs (FFMA2): the products of two adjacent classes per instruction — half the issue slots of the
+            // arithmetic that bounds this kernel; every lane of a pair is an IEEE fma, the sums keep their order
+            float2 dh01 = make_float2(0.f, 0.f), dh23 = make_float2(0.f, 0.f);
+            const float2 aa = make_float2(a, a);
 #pragma unroll
             for (int q4 = 0; q4 < NC4; ++q4) {
                 const float4 d = *reinterpret_cast<const float4*>(dr + q4 * 4);
-                dh0 = fmaf(d.x, w[q4 * 4 + 0], dh0);
-                dh1 = fmaf(d.y, w[q4 * 4 + 1], dh1);
-                dh2 = fmaf(d.z, w[q4 * 4 + 2], dh2);
-                dh3 = fmaf(d.w, w[q4 * 4 + 3], dh3);
-                gw[q4 * 4 + 0] = fmaf(a, d.x, gw[q4 * 4 + 0]);
-                gw[q4 * 4 + 1] = fmaf(a, d.y, gw[q4 * 4 + 1]);
-                gw[q4 * 4 + 2] = fmaf(a, d.z, gw[q4 * 4 + 2]);
-                gw[q4 * 4 + 3] = fmaf(a, d.w, gw[q4 * 4 + 3]);
+                dh01 = __ffma2_rn(make_float2(d.x, d.y), make_float2(w[q4 * 4 + 0], w[q4 * 4 + 1]), dh01);
+                dh23 = __ffma2_rn(make_float2(d.z, d.w), make_float2(w[q4 * 4 + 2], w[q4 * 4 + 3]), dh23);
+                const float2 g01 = __ffma2_rn(aa, make_float2(d.x, d.y), make_float2(gw[q4 * 4 + 0], gw[q4 * 4 + 1]));
+                const float2 g23 = __ffma2_rn(aa, make_float2(d.z, d.w), make_float2(gw[q4 * 4 + 2], gw[q4 * 4 + 3]));
+                gw[q4 * 4 + 0] = g01.x; gw[q4 * 4 + 1] = g01.y;
+                gw[q4 * 4 + 2] = g23.x; gw[q4 * 4 + 3] = g23.y;
             }
+            const float dh0 = dh01.x, dh1 = dh01.y, dh2 = dh23.x, dh3 = dh23.y;
             if (act) {
                 const float dz = ((dh0 + dh1) + (dh2 + dh3)) * scale;
                 acol[u * hp4] = dz;  // in place: the tile turns into dZ1

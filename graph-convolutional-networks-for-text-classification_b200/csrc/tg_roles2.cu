@@ -45,6 +45,9 @@ constexpr int kJobRows = 64;          // document role: rows per job = row group
 constexpr int kStages = 4;            // document role: entry ring depth
 constexpr int kPF = 2;                // ... jobs issued ahead
 constexpr int kL2PF = 4;              // document role: jobs whose self-loop rows of B are prefetched into L2 ahead
+constexpr int kNStages = 4;            // narrow kernels: hub stages
+constexpr int kNRing = 8;              // narrow kernels: document ring depth
+constexpr int kNPF = 6;                // ... jobs issued ahead
 constexpr size_t kSmemMax = 227 * 1024;
 
 struct R2Args {
@@ -405,6 +408,386 @@ __global__ void __launch_bounds__(kThreads, 1) roles2_kernel(const R2Args a, con
     }
 }
 
+// =============================================== narrow operands (F <= 32) ===============================================
+// The class-sized products (F = number of classes: 8, 20) of layer 2 use the same plan and the same two roles with a row
+// of F floats covered by the 8 lanes of a group (lane gl owns float4 chunk gl when gl < F/4):
+//   hub role: a warp still owns 16 slots and walks one slot at a time, but the four groups of the warp take every fourth
+//             entry of the slot's run (trip counts differ by at most one), so one warp instruction covers four entries;
+//             the four group accumulators are added once, at the end, by a fixed shuffle butterfly (deterministic);
+//   doc role: identical ring / prefetch structure, one float4 accumulator per lane, whole-row epilogues (EpiLoss) work
+//             because a group holds the whole row.
+// Entry offsets were precomputed for 512-byte rows (x = local row * 512): rescaled here to the F*4-byte rows.
+__device__ __forceinline__ void hub_role_narrow(const R2Args& a, const CUtensorMap* tmap, unsigned char* smem, uint64_t* bars,
+                                                int hl) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane & 7, g = lane >> 3;
+    const int n4 = a.n_chunks4;
+    const int rowb = n4 * 16;
+    const bool act = gl < n4;
+    const int lane_off = (act ? gl : 0) * 16;
+    const size_t tile_bytes = (size_t)a.T * rowb;
+    const size_t bs_bytes = align128(tile_bytes);
+    const size_t he_bytes = align128((size_t)a.cap_hub * 8);
+    const size_t st_bytes = bs_bytes + he_bytes + align128((size_t)kHtW * 4);
+    uint64_t* full = bars;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kNStages; ++i) mbar_init(&full[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const bool contiguous = a.ldb == (int64_t)n4 * 4;  // rows of B back to back: one bulk copy instead of a 2-D tile
+    auto issue = [&](int buf, int c, const int4 d) {
+        unsigned char* base = smem + (size_t)buf * st_bytes;
+        fence_proxy_async();
+        if (contiguous) {
+            const int64_t rows = (a.n - d.z < a.T) ? a.n - d.z : a.T;
+            mbar_expect_tx(&full[buf], (unsigned)(rows * rowb) + (unsigned)d.y * 8u + (unsigned)(kHtW * 4));
+            bulk_load_1d(base, a.B + (int64_t)d.z * a.ldb, (unsigned)(rows * rowb), &full[buf]);
+        } else {
+            mbar_expect_tx(&full[buf], (unsigned)tile_bytes + (unsigned)d.y * 8u + (unsigned)(kHtW * 4));
+            tma_load_2d(base, tmap, 0, d.z, &full[buf]);
+        }
+        if (d.y) bulk_load_1d(base + bs_bytes, a.hent + d.x, (unsigned)d.y * 8u, &full[buf]);
+        bulk_load_1d(base + bs_bytes + he_bytes, a.htab + (int64_t)c * kHtW, (unsigned)(kHtW * 4), &full[buf]);
+    };
+    // The slots of a warp are in descending weight order (plan: longest-first dealing).  The four heaviest are walked by the
+    // whole warp, every group taking each fourth entry of the run; the other twelve are walked four at a time, one slot per
+    // group — a quarter of the loop set-ups, at the price of lock-stepping four short runs of slightly different lengths.
+    float4 accS[4], accG[3];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) accS[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) accG[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int c = hl;
+    if (c < a.n_chunks) {
+        // a chunk of a narrow operand is little work: keep kNStages - 1 chunks in flight to cover the HBM latency
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < kNStages - 1; ++i)
+                if (c + i * a.hub_lanes < a.n_chunks) issue(i, c + i * a.hub_lanes, __ldg(a.cdesc + c + i * a.hub_lanes));
+        }
+        for (int it = 0; c < a.n_chunks; c += a.hub_lanes, ++it) {
+            const int buf = it % kNStages;
+            const int cn = c + (kNStages - 1) * a.hub_lanes;  // its buffer was released by the barrier of iteration it - 1
+            if (tid == 0 && cn < a.n_chunks) issue((it + kNStages - 1) % kNStages, cn, __ldg(a.cdesc + cn));
+            mbar_wait(&full[buf], (unsigned)(it / kNStages) & 1u);
+            const unsigned char* base = smem + (size_t)buf * st_bytes;
+            const unsigned char* Bl = base + lane_off;
+            const int2* he = reinterpret_cast<const int2*>(base + bs_bytes);
+            const int32_t* htw = reinterpret_cast<const int32_t*>(base + bs_bytes + he_bytes) + warp * kKPW;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                int q = htw[kk] + g;
+                const int h1 = htw[kk + 1];
+#pragma unroll 1
+                for (; q + 4 < h1; q += 8) {
+                    const int2 e0 = he[q], e1 = he[q + 4];
+                    const float4 b0 = lds128(Bl + ((e0.x * n4) >> 5)), b1 = lds128(Bl + ((e1.x * n4) >> 5));
+                    fma4p(accS[kk], __int_as_float(e0.y), b0);
+                    fma4p(accS[kk], __int_as_float(e1.y), b1);
+                }
+                if (q < h1) {
+                    const int2 e0 = he[q];
+                    fma4p(accS[kk], __int_as_float(e0.y), lds128(Bl + ((e0.x * n4) >> 5)));
+                }
+            }
+#pragma unroll
+            for (int sx = 0; sx < 3; ++sx) {
+                const int slot = 4 + 4 * sx + g;
+                int q = htw[slot];
+                const int h1 = htw[slot + 1];
+#pragma unroll 1
+                for (; q + 2 <= h1; q += 2) {
+                    const int2 e0 = he[q], e1 = he[q + 1];
+                    const float4 b0 = lds128(Bl + ((e0.x * n4) >> 5)), b1 = lds128(Bl + ((e1.x * n4) >> 5));
+                    fma4p(accG[sx], __int_as_float(e0.y), b0);
+                    fma4p(accG[sx], __int_as_float(e1.y), b1);
+                }
+                if (q < h1) {
+                    const int2 e0 = he[q];
+                    fma4p(accG[sx], __int_as_float(e0.y), lds128(Bl + ((e0.x * n4) >> 5)));
+                }
+            }
+            __syncthreads();
+        }
+    }
+    float* dst = a.partials + ((int64_t)hl * kKv + warp * kKPW) * a.ldp + (int64_t)gl * 4;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        float4 v = accS[kk];
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {  // groups (0+1), (2+3), then the two pairs: a fixed tree
+            v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+            v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+            v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+            v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+        }
+        if (g == 0 && act) *reinterpret_cast<float4*>(dst + (int64_t)kk * a.ldp) = v;
+    }
+#pragma unroll
+    for (int sx = 0; sx < 3; ++sx)
+        if (act) *reinterpret_cast<float4*>(dst + (int64_t)(4 + 4 * sx + g) * a.ldp) = accG[sx];
+}
+
+template <class Epi>
+__device__ __forceinline__ void doc_role_narrow(const R2Args& a, const Epi& epi, unsigned char* smem, uint64_t* bars, int dl) {
+    const int tid = threadIdx.x, lane = tid & 31, gl = lane & 7, grp = tid >> 3;
+    const unsigned gmask = group_mask<8>(lane);
+    const int n4 = a.n_chunks4;
+    const int rowb = n4 * 16;
+    const bool act = gl < n4;
+    const int lane_off = (act ? gl : 0) * 16;
+    const size_t bh_bytes = align128((size_t)a.Kh * rowb);
+    const size_t en_bytes = align128((size_t)a.cap_doc * 8);
+    const size_t self_bytes = align128((size_t)kJobRows * rowb);
+    const size_t st_bytes = en_bytes + (size_t)kJobRows * 8 + self_bytes;
+    unsigned char* ring = smem + bh_bytes;
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kNRing;
+    uint64_t* bhbar = bars + 2 * kNRing;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kNRing; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kWarps);
+        }
+        mbar_init(bhbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bhbar, (unsigned)a.Kh * rowb);
+    }
+    __syncthreads();
+    for (int k = tid; k < a.Kh; k += kThreads)
+        bulk_load_1d(smem + (size_t)k * rowb, a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb, rowb, bhbar);
+    // a job of a narrow operand is a few hundred cycles of work: everything it reads — entries, row descriptors AND the
+    // rows of B for the self loops — arrives through the ring, issued kNPF jobs ahead
+    const bool contiguous = a.ldb == (int64_t)n4 * 4;
+    auto issue = [&](int itn, int jobn) {
+        const int s = itn % kNRing;
+        const int2 jd = __ldg(a.jdesc + jobn);
+        unsigned char* base = ring + (size_t)s * st_bytes;
+        const int64_t r0 = (int64_t)jobn * kJobRows;
+        const int rows = (int)((a.n - r0 < kJobRows) ? a.n - r0 : kJobRows);
+        fence_proxy_async();
+        mbar_expect_tx(&full[s], (unsigned)jd.y * 8u + (unsigned)(kJobRows * 8) + (unsigned)(rows * rowb));
+        if (jd.y) bulk_load_1d(base, a.dent + jd.x, (unsigned)jd.y * 8u, &full[s]);
+        bulk_load_1d(base + en_bytes, a.rdesc + r0, (unsigned)(kJobRows * 8), &full[s]);
+        unsigned char* selfs = base + en_bytes + kJobRows * 8;
+        if (contiguous) {
+            bulk_load_1d(selfs, a.B + r0 * a.ldb, (unsigned)(rows * rowb), &full[s]);
+        } else {
+            for (int r = 0; r < rows; ++r) bulk_load_1d(selfs + (size_t)r * rowb, a.B + (r0 + r) * a.ldb, (unsigned)rowb, &full[s]);
+        }
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kNPF; ++i)
+            if (dl + i * a.doc_lanes < a.n_jobs) issue(i, dl + i * a.doc_lanes);
+    }
+    mbar_wait(bhbar, 0);
+    const unsigned char* BHl = smem + lane_off;
+    int it = 0;
+    for (int job = dl; job < a.n_jobs; job += a.doc_lanes, ++it) {
+        if (tid == 0) {
+            const int itn = it + kNPF, jobn = job + kNPF * a.doc_lanes;
+            if (jobn < a.n_jobs) {
+                if (itn >= kNRing) mbar_wait(&empty[itn % kNRing], (unsigned)(itn / kNRing - 1) & 1u);
+                issue(itn, jobn);
+            }
+        }
+        const int s = it % kNRing;
+        mbar_wait(&full[s], (unsigned)(it / kNRing) & 1u);
+        const unsigned char* base = ring + (size_t)s * st_bytes;
+        const int2 rd = reinterpret_cast<const int2*>(base + en_bytes)[grp];
+        const int n_tot = rd.y >> 16, n_nh = rd.y & 0xffff;
+        const int2* ent = reinterpret_cast<const int2*>(base) + rd.x;
+        const int64_t row = (int64_t)job * kJobRows + grp;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < n_nh; ++p) {
+            const int2 en = ent[p];
+            const float v = __int_as_float(en.y);
+            if ((int64_t)en.x == row) fma4p(acc, v, lds128(base + en_bytes + kJobRows * 8 + (size_t)grp * rowb + lane_off));
+            else fma4p(acc, v, act ? ldg_f4(a.B + (int64_t)en.x * a.ldb + gl * 4) : make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        int p = n_nh;
+#pragma unroll 1
+        for (; p + 4 <= n_tot; p += 4) {
+            const int2 e0 = ent[p], e1 = ent[p + 1], e2 = ent[p + 2], e3 = ent[p + 3];
+            const float4 b0 = lds128(BHl + ((e0.x * n4) >> 5)), b1 = lds128(BHl + ((e1.x * n4) >> 5));
+            const float4 b2 = lds128(BHl + ((e2.x * n4) >> 5)), b3 = lds128(BHl + ((e3.x * n4) >> 5));
+            fma4p(acc, __int_as_float(e0.y), b0);
+            fma4p(acc, __int_as_float(e1.y), b1);
+            fma4p(acc, __int_as_float(e2.y), b2);
+            fma4p(acc, __int_as_float(e3.y), b3);
+        }
+        for (; p < n_tot; ++p) {
+            const int2 e0 = ent[p];
+            fma4p(acc, __int_as_float(e0.y), lds128(BHl + ((e0.x * n4) >> 5)));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (n_tot > 0) {
+            Chunk<4> out[1];
+            out[0].v[0] = acc.x; out[0].v[1] = acc.y; out[0].v[2] = acc.z; out[0].v[3] = acc.w;
+            epi.template apply<4, 8, 1>(row, gl, gmask, n4, out);
+        }
+    }
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(kThreads, 1) roles2n_kernel(const R2Args a, const Epi epi, const __grid_constant__ CUtensorMap tmapB) {
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t bars[2 * kNRing + 2];
+    unsigned char* smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    const int bid = blockIdx.x;
+    if (bid < a.hub_lanes) {
+        if (a.only_role == 2) return;
+        hub_role_narrow(a, &tmapB, smem, bars, bid);
+    } else {
+        if (a.only_role == 1) return;
+        doc_role_narrow(a, epi, smem, bars, bid - a.hub_lanes);
+    }
+}
+
+// Lane-per-row document role for narrow operands whose rows lie back to back (ldb == n_feat): a row is NV float4 chunks
+// held by ONE lane, so a warp covers 32 rows per instruction instead of 4 and the per-entry bookkeeping is amortised over
+// the whole row (ncu on the group-per-row variant: 106 M warp instructions for 16 M entries at F = 20).  A stage carries a
+// "super job" of 8 consecutive jobs (512 rows, one per thread): their entries (one contiguous run), row descriptors,
+// job descriptors and the 512 rows of B for the self loops, as four bulk copies; two stages.
+constexpr int kTeams = 8;       // lane-per-row document role: teams of two warps, one job (64 rows) per team and stage
+constexpr int kTeamStages = 2;
+template <int NV, class Epi>
+__device__ __forceinline__ void doc_role_narrow_lane(const R2Args& a, const Epi& epi, unsigned char* smem, uint64_t* bars, int dl) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int team = tid >> 6, tl = tid & 63;
+    const int n4 = a.n_chunks4;
+    const int rowb = n4 * 16;
+    const size_t bh_bytes = align128((size_t)a.Kh * rowb);
+    const size_t en_bytes = align128((size_t)a.cap_doc * 8);
+    const size_t rd_bytes = (size_t)kJobRows * 8;
+    const size_t self_bytes = align128((size_t)kJobRows * rowb);
+    const size_t st_bytes = en_bytes + rd_bytes + self_bytes;
+    unsigned char* ring = smem + bh_bytes + (size_t)team * kTeamStages * st_bytes;
+    uint64_t* full = bars + team * 2 * kTeamStages;
+    uint64_t* empty = full + kTeamStages;
+    uint64_t* bhbar = bars + kTeams * 2 * kTeamStages;
+    if (tid == 0) {
+        for (int i = 0; i < kTeams; ++i)
+            for (int s = 0; s < kTeamStages; ++s) {
+                mbar_init(&bars[i * 2 * kTeamStages + s], 1);
+                mbar_init(&bars[i * 2 * kTeamStages + kTeamStages + s], 2);  // the two warps of the team
+            }
+        mbar_init(bhbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bhbar, (unsigned)a.Kh * rowb);
+    }
+    __syncthreads();
+    for (int k = tid; k < a.Kh; k += kThreads)
+        bulk_load_1d(smem + (size_t)k * rowb, a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb, rowb, bhbar);
+    // every team runs its own two-stage ring over its own job sequence: 8 teams x 1 job in flight per CTA keep enough
+    // bytes in flight to cover the HBM latency (one 82 KB stage per CTA did not: 4.8 us per stage, ncu/ROLE=2 timing)
+    const int job_stride = a.doc_lanes * kTeams;
+    auto issue = [&](int itn, int jobn) {
+        const int s = itn % kTeamStages;
+        const int2 jd = __ldg(a.jdesc + jobn);
+        const int64_t r0 = (int64_t)jobn * kJobRows;
+        const unsigned rows = (unsigned)((a.n - r0 < kJobRows) ? a.n - r0 : kJobRows);
+        unsigned char* base = ring + (size_t)s * st_bytes;
+        fence_proxy_async();
+        mbar_expect_tx(&full[s], (unsigned)jd.y * 8u + (unsigned)rd_bytes + rows * (unsigned)rowb);
+        if (jd.y) bulk_load_1d(base, a.dent + jd.x, (unsigned)jd.y * 8u, &full[s]);
+        bulk_load_1d(base + en_bytes, a.rdesc + r0, (unsigned)rd_bytes, &full[s]);
+        bulk_load_1d(base + en_bytes + rd_bytes, a.B + r0 * a.ldb, rows * (unsigned)rowb, &full[s]);
+    };
+    const int job0 = dl * kTeams + team;
+    if (tl == 0) {
+#pragma unroll
+        for (int i = 0; i < kTeamStages - 1; ++i)
+            if (job0 + i * job_stride < a.n_jobs) issue(i, job0 + i * job_stride);
+    }
+    mbar_wait(bhbar, 0);
+    int it = 0;
+    for (int job = job0; job < a.n_jobs; job += job_stride, ++it) {
+        if (tl == 0) {
+            const int itn = it + kTeamStages - 1, jobn = job + (kTeamStages - 1) * job_stride;
+            if (jobn < a.n_jobs) {
+                if (itn >= kTeamStages) mbar_wait(&empty[itn % kTeamStages], (unsigned)(itn / kTeamStages - 1) & 1u);
+                issue(itn, jobn);
+            }
+        }
+        const int s = it % kTeamStages;
+        mbar_wait(&full[s], (unsigned)(it / kTeamStages) & 1u);
+        const unsigned char* base = ring + (size_t)s * st_bytes;
+        const int2 rd = reinterpret_cast<const int2*>(base + en_bytes)[tl];
+        const int n_tot = rd.y >> 16, n_nh = rd.y & 0xffff;
+        const int2* ent = reinterpret_cast<const int2*>(base) + rd.x;
+        const int64_t row = (int64_t)job * kJobRows + tl;
+        float4 acc[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < n_nh; ++p) {
+            const int2 en = ent[p];
+            const float v = __int_as_float(en.y);
+            if ((int64_t)en.x == row) {
+                const unsigned char* sr = base + en_bytes + rd_bytes + (size_t)tl * rowb;
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+                    if (i < n4) fma4p(acc[i], v, lds128(sr + i * 16));
+            } else {
+                const float* src = a.B + (int64_t)en.x * a.ldb;
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+                    if (i < n4) fma4p(acc[i], v, ldg_f4(src + i * 4));
+            }
+        }
+        int p = n_nh;
+#pragma unroll 1
+        for (; p + 2 <= n_tot; p += 2) {
+            const int2 e0 = ent[p], e1 = ent[p + 1];
+            const unsigned char* r0 = smem + ((e0.x * n4) >> 5);
+            const unsigned char* r1 = smem + ((e1.x * n4) >> 5);
+            const float v0 = __int_as_float(e0.y), v1 = __int_as_float(e1.y);
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (i < n4) {
+                    const float4 b0 = lds128(r0 + i * 16), b1 = lds128(r1 + i * 16);
+                    fma4p(acc[i], v0, b0);
+                    fma4p(acc[i], v1, b1);
+                }
+        }
+        if (p < n_tot) {
+            const int2 e0 = ent[p];
+            const unsigned char* r0 = smem + ((e0.x * n4) >> 5);
+            const float v0 = __int_as_float(e0.y);
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (i < n4) fma4p(acc[i], v0, lds128(r0 + i * 16));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (n_tot > 0) {
+            Chunk<4> out[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) { out[i].v[0] = acc[i].x; out[i].v[1] = acc[i].y; out[i].v[2] = acc[i].z; out[i].v[3] = acc[i].w; }
+            epi.template apply<4, 1, NV>(row, 0, 1u << lane, n4, out);
+        }
+    }
+}
+
+template <int NV, class Epi>
+__global__ void __launch_bounds__(kThreads, 1) roles2nl_kernel(const R2Args a, const Epi epi, const __grid_constant__ CUtensorMap tmapB) {
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t bars[kTeams * 2 * kTeamStages + 2];
+    unsigned char* smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    const int bid = blockIdx.x;
+    if (bid < a.hub_lanes) {
+        if (a.only_role == 2) return;
+        hub_role_narrow(a, &tmapB, smem, bars, bid);
+    } else {
+        if (a.only_role == 1) return;
+        doc_role_narrow_lane<NV>(a, epi, smem, bars, bid - a.hub_lanes);
+    }
+}
+
 // =============================================== plan build =============================================================
 // number of hub-row entries in every column (= entries the hub role processes for that node)
 __global__ void r2_hub_deg_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
@@ -721,7 +1104,8 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     TG_TRY(cudaMalloc((void**)&pl->r2_dent, ((size_t)doc_nnz + 2) * sizeof(int2)));
     TG_TRY(cudaMemsetAsync(pl->r2_dent, 0, ((size_t)doc_nnz + 2) * sizeof(int2), st));
     TG_TRY(cudaMalloc((void**)&pl->r2_rdesc, (size_t)n_pad * sizeof(int2)));
-    TG_TRY(cudaMalloc((void**)&pl->r2_jdesc, (size_t)n_jobs * sizeof(int2)));
+    TG_TRY(cudaMalloc((void**)&pl->r2_jdesc, (size_t)(n_jobs + 8) * sizeof(int2)));  // padded: the lane-per-row kernel copies 8 at a time
+    TG_TRY(cudaMemsetAsync(pl->r2_jdesc, 0, (size_t)(n_jobs + 8) * sizeof(int2), st));
     r2_doc_fill_kernel<<<(unsigned)ceil_div64(n_pad, 256), 256, 0, st>>>(rowptr, pl->rsplit, reinterpret_cast<const int2*>(pl->colidx2),
                                                                           d_start, n, n_pad, pl->hub_threshold, pl->r2_dent,
                                                                           pl->r2_rdesc, pl->r2_jdesc);
@@ -821,6 +1205,86 @@ int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cuda
     TG_LAUNCH_CHECK();
     FinishArgs f{a.partials, a.ldp, hub_lanes, a.Kh, kKv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
     return finish_run(f, epi, st);
+}
+
+static void narrow_smem(const tg_plan* pl, int n_feat, size_t* hub_s, size_t* doc_s, size_t* lane_s) {
+    const size_t rowb = (size_t)n_feat * 4;
+    *hub_s = (size_t)kNStages * (align128((size_t)pl->r2_T * rowb) + align128((size_t)pl->r2_cap_hub * 8) + align128((size_t)kHtW * 4));
+    const size_t job_s = align128((size_t)pl->r2_cap_doc * 8) + (size_t)kJobRows * 8 + align128((size_t)kJobRows * rowb);
+    *doc_s = align128((size_t)pl->n_hub * rowb) + (size_t)kNRing * job_s;
+    *lane_s = align128((size_t)pl->n_hub * rowb) + (size_t)kTeams * kTeamStages * job_s;
+}
+
+bool roles2_narrow_applicable(const tg_plan* pl, const StreamCall& c) {
+    if (!pl || !pl->r2_ok) return false;
+    if (env_int2("TG_ROLES2", 1) == 0 || env_int2("TG_ROLES2_NARROW", 1) == 0) return false;
+    if (c.n_feat < 4 || c.n_feat > 32 || c.n_feat % 4 != 0) return false;
+    if (c.ldb % 4 != 0 || !aligned16(c.B) || !encode_tiled_fn()) return false;
+    size_t hub_s, doc_s, lane_s;
+    narrow_smem(pl, c.n_feat, &hub_s, &doc_s, &lane_s);
+    return std::max(hub_s, doc_s) + 256 <= kSmemMax;  // (the lane-per-row variant is chosen at launch when it fits too)
+}
+
+template <class Epi>
+static int roles2_narrow_run_t(const tg_plan* pl, const StreamCall& c, const Epi& epi, cudaStream_t st) {
+    R2Args a;
+    a.hent = pl->r2_hent; a.htab = pl->r2_htab; a.cdesc = pl->r2_cdesc;
+    a.T = pl->r2_T; a.n_chunks = pl->r2_n_chunks; a.cap_hub = pl->r2_cap_hub;
+    a.dent = pl->r2_dent; a.rdesc = pl->r2_rdesc; a.jdesc = pl->r2_jdesc;
+    a.n_jobs = pl->r2_n_jobs; a.cap_doc = pl->r2_cap_doc;
+    a.hub_rows = pl->hub_rows; a.Kh = pl->n_hub;
+    a.B = c.B; a.ldb = c.ldb; a.n = pl->n_rows; a.n_chunks4 = c.n_feat / 4;
+    a.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(c.workspace) + 15u) & ~(uintptr_t)15u);
+    a.ldp = (int64_t)((c.n_feat + 3) / 4) * 4;
+    a.hub_slices = a.doc_slices = 1;
+    a.keep_bits = nullptr;
+    const int hub_pct = env_int2("TG_ROLES2_NARROW_HUB_PCT", 52);
+    int hub_lanes = kNumSM * hub_pct / 100;
+    if (hub_lanes < 1) hub_lanes = 1;
+    if (hub_lanes > a.n_chunks) hub_lanes = a.n_chunks;
+    int doc_lanes = kNumSM - hub_lanes;
+    if (doc_lanes < 1) doc_lanes = 1;
+    if (doc_lanes > a.n_jobs) doc_lanes = a.n_jobs;
+    a.hub_lanes = hub_lanes;
+    a.doc_lanes = doc_lanes;
+    a.only_role = env_int2("TG_ROLES_ONLY", 0);
+    const size_t need = (size_t)hub_lanes * kKv * a.ldp * sizeof(float);
+    TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
+               c.workspace_bytes, need + 16);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    TG_REQUIRE(make_tensor_map(&tmap, a.B, a.n, c.n_feat, a.ldb, a.T, c.n_feat), TG_ERR_UNSUPPORTED,
+               "cuTensorMapEncodeTiled failed (TMA tile of the narrow dense operand)");
+    size_t hub_s, doc_s, lane_s;
+    narrow_smem(pl, c.n_feat, &hub_s, &doc_s, &lane_s);
+    const bool lane_rows = c.ldb == c.n_feat && std::max(hub_s, lane_s) + 256 <= kSmemMax && env_int2("TG_ROLES2_NARROW_LANE", 1) != 0;
+    const unsigned grid = (unsigned)(hub_lanes + doc_lanes);
+    if (lane_rows) {
+        const size_t smem = std::max(hub_s, lane_s) + 128;
+        const int n4 = a.n_chunks4;
+#define TG_R2NL(NVv)                                                                                                         \
+        if (n4 <= NVv) {                                                                                                     \
+            TG_CUDA(cudaFuncSetAttribute(roles2nl_kernel<NVv, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            roles2nl_kernel<NVv, Epi><<<grid, kThreads, smem, st>>>(a, epi, tmap);                                          \
+        } else
+        TG_R2NL(2) TG_R2NL(4) TG_R2NL(5) TG_R2NL(6) TG_R2NL(8) { set_error("narrow role kernels: n_feat > 32"); return TG_ERR_UNSUPPORTED; }
+#undef TG_R2NL
+    } else {
+        TG_REQUIRE(std::max(hub_s, doc_s) + 256 <= kSmemMax, TG_ERR_UNSUPPORTED, "narrow role kernels: shared memory budget exceeded");
+        const size_t smem = std::max(hub_s, doc_s) + 128;
+        TG_CUDA(cudaFuncSetAttribute(roles2n_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roles2n_kernel<Epi><<<grid, kThreads, smem, st>>>(a, epi, tmap);
+    }
+    TG_LAUNCH_CHECK();
+    FinishArgs f{a.partials, a.ldp, hub_lanes, a.Kh, kKv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
+    return finish_run(f, epi, st);
+}
+
+int roles2_narrow_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st) {
+    return roles2_narrow_run_t(pl, c, epi, st);
+}
+int roles2_narrow_run(const tg_plan* pl, const StreamCall& c, const EpiLoss& epi, cudaStream_t st) {
+    return roles2_narrow_run_t(pl, c, epi, st);
 }
 
 }  // namespace tg

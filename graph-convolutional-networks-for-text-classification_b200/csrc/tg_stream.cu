@@ -794,6 +794,7 @@ bool stream_applicable(const tg_plan* pl, const StreamCall& c, bool out_vec4_ok,
     if (!(c.n_feat % 4 == 0 && c.ldb % 4 == 0 && aligned16(c.B) && out_vec4_ok)) return false;
     if (c.n_feat > 1024) return false;
     if (narrow_applicable(pl, c.n_feat)) return true;
+    if (roles2_narrow_applicable(pl, c)) return true;
     // rows of <= 32 columns: at the single-GPU sizes B (N x F x 4 B, 80 MB at C3) stays in L2 and the gather kernel
     // (tg_spmm.cu, 8 lanes per row) is faster than streaming; TG_STREAM_NARROW=1 selects the lane-per-row streaming
     // kernel, which keeps DRAM traffic at the algorithmic minimum when B outgrows L2.
@@ -846,6 +847,7 @@ static int launch_narrow(const tg_plan* pl, const StreamCall& c, StreamArgs a, c
 
 template <class Epi>
 static int run_stream(const tg_plan* pl, const StreamCall& c, const Epi& epi, bool whole_row, cudaStream_t st) {
+    if (!narrow_applicable(pl, c.n_feat) && roles2_narrow_applicable(pl, c)) return roles2_narrow_run(pl, c, epi, st);
     if (narrow_applicable(pl, c.n_feat)) {
         StreamArgs a;
         a.rowptr = c.rowptr; a.rsplit = pl->rsplit; a.dent = reinterpret_cast<const int2*>(pl->colidx2);

@@ -32,6 +32,9 @@ void roles2_plan_free(tg_plan* pl);
 bool roles2_applicable(const tg_plan* pl, const StreamCall& c);
 size_t roles2_workspace_bytes(const tg_plan* pl, int32_t n_feat);
 int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st);
+bool roles2_narrow_applicable(const tg_plan* pl, const StreamCall& c);   // n_feat <= 32 (class-sized operands)
+int roles2_narrow_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st);
+int roles2_narrow_run(const tg_plan* pl, const StreamCall& c, const EpiLoss& epi, cudaStream_t st);
 
 int stream_spmm_store(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st);
 int stream_spmm_loss(const tg_plan* pl, const StreamCall& c, const EpiLoss& epi, cudaStream_t st);

@@ -530,3 +530,38 @@ def test_roles2_kernel_parity(tg, monkeypatch, n_docs, n_topics, F, thr):
     y_old = tg.spmm(csr, B)
     monkeypatch.delenv("TG_ROLES2")
     assert float((y_old - y).abs().max() / y.abs().max()) <= SPMM_RTOL
+
+
+@pytest.mark.parametrize("n_docs,n_topics,thr", [(3000, 64, 64), (9000, 256, 48), (20000, 100, 256)])
+@pytest.mark.parametrize("C", [8, 20, 32])
+def test_roles2_narrow_kernel_parity(tg, monkeypatch, n_docs, n_topics, thr, C):
+    """Class-sized operands (F <= 32) through the narrow variant of the warp-per-slot kernels: plain product and the fused
+    layer-2 epilogue (bias + log-softmax + masked cross-entropy + gradient) against the oracle; deterministic; agrees
+    with the gather kernel."""
+    from topicgcn_b200 import graphgen, ops
+    g = graphgen.doc_topic_topic_graph(n_docs, n_topics, deg_lo=2, deg_hi=13, dense_topics=True, seed=4, device="cuda:0")
+    csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n, hub_threshold=thr, segment_nnz=max(8, thr // 2))
+    assert csr.streaming and csr.roles2
+    rng = np.random.default_rng(C)
+    S2 = rng.normal(size=(g.n, C)).astype(np.float32)
+    b2 = rng.normal(size=C).astype(np.float32)
+    coo = O.Coo(g.rows.cpu().numpy(), g.cols.cpu().numpy(), g.vals.cpu().numpy(), (g.n, g.n))
+    ref = O.spmm(coo, S2)
+    S2d = torch.tensor(S2, device=dev())
+    y = tg.spmm(csr, S2d)
+    assert rel_err(y.cpu().numpy(), ref) <= SPMM_RTOL
+    assert rel_err(y.cpu().numpy()[n_docs:], ref[n_docs:]) <= SPMM_RTOL
+    assert torch.equal(y, tg.spmm(csr, S2d))
+    monkeypatch.setenv("TG_ROLES2_NARROW", "0")
+    y_g = tg.spmm(csr, S2d)
+    monkeypatch.delenv("TG_ROLES2_NARROW")
+    assert float((y_g - y).abs().max() / y.abs().max()) <= SPMM_RTOL
+    target = rng.integers(0, C, size=n_docs)
+    index = np.sort(rng.choice(n_docs, size=n_docs * 2 // 3, replace=False))
+    logits_ref = ref + b2
+    loss_ref, dz_ref = O.masked_cross_entropy(logits_ref, target, index)
+    row_label = ops.make_row_label(g.n, torch.tensor(target, device=dev()), torch.tensor(index, device=dev()))
+    loss, logits, dz = ops.gc2_loss_forward(csr, S2d, torch.tensor(b2, device=dev()), row_label, 1.0 / index.size)
+    assert rel_err(logits.cpu().numpy(), logits_ref) <= SPMM_RTOL
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    assert rel_err(dz.cpu().numpy(), dz_ref) <= 2e-5
