@@ -128,6 +128,23 @@ __host__ __device__ __forceinline__ Philox4 dropout_philox(int64_t row, uint32_t
                          (uint32_t)(seed >> 32));
 }
 
+// Exact-half mode: when keep_threshold(p) == 32768 (p = 0.5, the reference's setting, trainer.py:428) one random BIT per
+// element is an exact Bernoulli(1/2) draw, so a Philox call serves 128 consecutive columns instead of 8:
+//   element (row, col):  r = philox(counter = (row_lo, row_hi, (col / 128) | 0x80000000, offset_lo), same key)
+//   keep  <=>  bit (col % 128) of the 128-bit little-endian value (x | y << 32 | z << 64 | w << 96) is set.
+// Every other p keeps the 16-bit definition above.  (Both are restated in oracle/gcn_oracle.py.)
+constexpr uint32_t kDropoutHalfThr = 32768u;
+__host__ __device__ __forceinline__ Philox4 dropout_philox_half(int64_t row, uint32_t cidx, uint64_t seed, uint64_t offset) {
+    return philox4x32_10((uint32_t)(uint64_t)row, (uint32_t)((uint64_t)row >> 32), cidx | 0x80000000u,
+                         (uint32_t)offset, (uint32_t)seed ^ (uint32_t)(offset >> 32),
+                         (uint32_t)(seed >> 32));
+}
+// the 32-bit word of a half-mode result that holds float4 chunk q (columns 4q .. 4q+3): word (q / 8) % 4, bits 4 (q % 8) ..
+__host__ __device__ __forceinline__ uint32_t dropout_half_word(const Philox4& r, int q) {
+    const int w = (q >> 3) & 3;
+    return w == 0 ? r.x : w == 1 ? r.y : w == 2 ? r.z : r.w;
+}
+
 // the four u16 lanes that belong to chunk-half `half` (0/1) of a Philox result
 __host__ __device__ __forceinline__ void dropout_u16x4(const Philox4& r, int half, uint32_t u[4]) {
     const uint32_t a = half ? r.z : r.x, b = half ? r.w : r.y;

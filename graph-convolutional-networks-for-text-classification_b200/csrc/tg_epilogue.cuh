@@ -101,6 +101,7 @@ struct EpiStore {
             return;
         }
         Philox4 rnd = Philox4{0, 0, 0, 0};
+        int rnd_cidx = -1;  // exact-half mode: the 128-column block `rnd` was drawn for
         const uint64_t offset = (drop_mode == 1 && offset_dev) ? this->offset + __ldg(offset_dev) : this->offset;
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
@@ -122,7 +123,26 @@ struct EpiStore {
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) y.v[k] *= g;
             }
-            if (drop_mode == 1) {
+            if (drop_mode == 1 && keep_thr == kDropoutHalfThr) {
+                // exact-half mode (tg_common.cuh): one bit per element, one Philox call per 128 columns
+                if (VEC == 4) {
+                    const int q = chunk;
+                    if ((q >> 5) != rnd_cidx) {
+                        rnd_cidx = q >> 5;
+                        rnd = dropout_philox_half(row, (uint32_t)rnd_cidx, seed, offset);
+                    }
+                    const uint32_t w = dropout_half_word(rnd, q) >> (4 * (q & 7));
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) y.v[k] = ((w >> k) & 1u) ? y.v[k] * scale : 0.f;
+                } else {
+                    if ((col0 >> 7) != rnd_cidx) {
+                        rnd_cidx = col0 >> 7;
+                        rnd = dropout_philox_half(row, (uint32_t)rnd_cidx, seed, offset);
+                    }
+                    const uint32_t w = dropout_half_word(rnd, col0 >> 2) >> (col0 & 31);
+                    y.v[0] = (w & 1u) ? y.v[0] * scale : 0.f;
+                }
+            } else if (drop_mode == 1) {
                 if (VEC == 4) {
                     // chunk q: Philox call (q % 8, q / 16), half (q / 8) % 2 (see tg_common.cuh); with G == 8 the
                     // chunks (q, q + 8) of consecutive i share one call

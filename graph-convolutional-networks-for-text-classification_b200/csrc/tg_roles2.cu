@@ -337,6 +337,11 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
                         const uint32_t w = (u == 0 ? kb.x : u == 1 ? kb.y : u == 2 ? kb.z : kb.w) >> (4 * gl);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) y[k] = ((w >> k) & 1u) ? y[k] * epi.scale : 0.f;
+                    } else if (epi.drop_mode == 1 && epi.keep_thr == kDropoutHalfThr) {
+                        if (u == 0) rnd = dropout_philox_half(row, (uint32_t)(q >> 5), epi.seed, rng_offset);  // one call per slice
+                        const uint32_t w = dropout_half_word(rnd, q) >> (4 * (q & 7));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) y[k] = ((w >> k) & 1u) ? y[k] * epi.scale : 0.f;
                     } else if (epi.drop_mode == 1) {
                         if (!(u & 1)) rnd = dropout_philox(row, (uint32_t)(q & 7), (uint32_t)(q >> 4), epi.seed, rng_offset);
                         uint32_t r16[4];
@@ -389,6 +394,26 @@ __global__ void __launch_bounds__(256) r2_keep_bits_kernel(uint32_t* __restrict_
         w1 |= __shfl_xor_sync(0xffffffffu, w1, o);
     }
     if (live && lane8 == 0) *reinterpret_cast<uint2*>(out + (row * n_blk + blk) * 2) = make_uint2(w0, w1);
+}
+
+// Exact-half mode (p = 0.5): the 128 random bits of a call ARE the keep bits of 128 consecutive columns — one thread per
+// (row, 128-column block) writes four mask words, no comparisons, no shuffles.
+__global__ void __launch_bounds__(256) r2_keep_bits_half_kernel(uint32_t* __restrict__ out, int64_t n_rows, int n_words, uint64_t seed,
+                                                                 uint64_t offset, const unsigned long long* __restrict__ offset_dev) {
+    const int n_c = (n_words + 3) / 4;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * (int64_t)n_c) return;
+    const int64_t row = idx / n_c;
+    const int cidx = (int)(idx - row * n_c);
+    const uint64_t off = offset_dev ? offset + __ldg(offset_dev) : offset;
+    const Philox4 r = dropout_philox_half(row, (uint32_t)cidx, seed, off);
+    uint32_t* dst = out + row * n_words + cidx * 4;
+    if (cidx * 4 + 3 < n_words) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(r.x, r.y, r.z, r.w);
+    } else {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        for (int j = 0; cidx * 4 + j < n_words; ++j) dst[j] = w[j];
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) roles2_kernel(const R2Args a, const EpiStore epi, const __grid_constant__ CUtensorMap tmapB,
@@ -1166,11 +1191,18 @@ int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cuda
                 (reinterpret_cast<uintptr_t>(c.workspace) + part_bytes + 15u) & ~(uintptr_t)15u);
             const int n_blk = c.n_feat / 64;
             const int64_t threads = pl->n_rows * (int64_t)n_blk * 8;
+            if (epi.keep_thr == kDropoutHalfThr) {
+                const int n_words = c.n_feat / 32;
+                const int64_t th = pl->n_rows * (int64_t)((n_words + 3) / 4);
+                r2_keep_bits_half_kernel<<<(unsigned)ceil_div64(th, 256), 256, 0, st>>>(bits, pl->n_rows, n_words, epi.seed, epi.offset,
+                                                                                        epi.offset_dev);
+            } else {
             int blk_shift = -1;
             for (int sh = 0; sh < 8; ++sh)
                 if ((1 << sh) == n_blk) blk_shift = sh;
             r2_keep_bits_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, st>>>(bits, pl->n_rows, n_blk, blk_shift, epi.keep_thr, epi.seed,
                                                                                     epi.offset, epi.offset_dev);
+            }
             TG_LAUNCH_CHECK();
             a.keep_bits = bits;
         }

@@ -331,6 +331,11 @@ __global__ void keep_mask_kernel(uint8_t* __restrict__ out, int64_t n_rows, int3
     const int64_t row = idx / n_feat;
     const int col = (int)(idx % n_feat);
     const int q = col >> 2;
+    if (thr == kDropoutHalfThr) {  // exact-half mode: one bit per element
+        const Philox4 r = dropout_philox_half(row, (uint32_t)(col >> 7), seed, offset);
+        out[idx] = (dropout_half_word(r, q) >> (col & 31)) & 1u;
+        return;
+    }
     const Philox4 r = dropout_philox(row, (uint32_t)(q & 7), (uint32_t)(q >> 4), seed, offset);
     uint32_t u[4];
     dropout_u16x4(r, (q >> 3) & 1, u);

@@ -235,6 +235,15 @@ def philox_keep_mask(n_rows: int, n_feat: int, p: float, seed: int, offset: int)
     seed, offset = int(seed) & (2**64 - 1), int(offset) & (2**64 - 1)
     k0 = (seed & 0xFFFFFFFF) ^ (offset >> 32)
     k1 = seed >> 32
+    if thr == 32768:
+        # exact-half mode (p = 0.5): one random bit per element, one call per 128 columns (csrc/tg_common.cuh)
+        cidx = (col >> np.uint64(7)) | np.uint64(0x80000000)
+        x, y, z, w = _philox4x32_10(row & np.uint64(0xFFFFFFFF), row >> np.uint64(32), cidx,
+                                    np.full(row.shape, offset & 0xFFFFFFFF, dtype=np.uint64), k0, k1)
+        wsel = (col >> np.uint64(5)) & np.uint64(3)
+        word = np.where(wsel == 0, x, np.where(wsel == 1, y, np.where(wsel == 2, z, w)))
+        bit = (word >> (col & np.uint64(31))) & np.uint64(1)
+        return bit.astype(np.uint8).reshape(n_rows, n_feat)
     x, y, z, w = _philox4x32_10(row & np.uint64(0xFFFFFFFF), row >> np.uint64(32), slot | (j << np.uint64(8)),
                                 np.full(row.shape, offset & 0xFFFFFFFF, dtype=np.uint64), k0, k1)
     a = np.where(half == 1, z, x)

@@ -517,7 +517,15 @@ def test_roles2_kernel_parity(tg, monkeypatch, n_docs, n_topics, F, thr):
     h_bits = ops.gc1_forward(csr, B, bias, 0.3, True, seed=42, offset=9)
     assert rel_err(h_bits.cpu().numpy(), want) <= SPMM_RTOL
     assert np.array_equal(h_bits.cpu().numpy() != 0, want != 0)
+    pm5 = O.philox_keep_mask(g.n, F, 0.5, 7, 3)                                # exact-half mode: one bit per element
+    want5 = np.maximum(z, 0) * pm5 * 2.0
+    h5 = ops.gc1_forward(csr, B, bias, 0.5, True, seed=7, offset=3)
+    assert rel_err(h5.cpu().numpy(), want5) <= SPMM_RTOL
+    assert np.array_equal(h5.cpu().numpy() != 0, want5 != 0)
+    assert 0.49 < pm5.mean() < 0.51
     monkeypatch.setenv("TG_ROLES2_BITMASK", "0")                               # Philox drawn inside the kernel
+    h5_in = ops.gc1_forward(csr, B, bias, 0.5, True, seed=7, offset=3)
+    assert torch.equal(h5_in[:n_docs], h5[:n_docs]) and torch.equal(h5_in != 0, h5 != 0)
     h_in = ops.gc1_forward(csr, B, bias, 0.3, True, seed=42, offset=9)
     assert torch.equal(h_in[:n_docs], h_bits[:n_docs])    # hub rows: the SM split (hence the partial grouping) differs
     assert torch.equal(h_in != 0, h_bits != 0)
