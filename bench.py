@@ -367,9 +367,14 @@ def run_ours(args):
         tot_bytes = sum(v["algorithmic_GB"] * v["launches"] for _, v in dom)
         n_l = sum(v["launches"] for _, v in dom)
         achieved = tot_bytes * 1e3 / tot_ms
-        kname = (f"stream_roles_kernel<512,4,KPG,EpiStore> + stream_finish_kernel (role-specialised column-chunk streaming "
-                 f"SpMM with TMA-staged chunks, F={hidden})"
-                 if csr.streaming else f"spmm_kernel<4,32,{(hidden // 4 + 31) // 32},EpiStore> (gather SpMM, F={hidden})")
+        if getattr(csr, "roles2", False) and hidden % 128 == 0:
+            kname = (f"roles2_kernel + stream_finish_kernel (warp-per-slot role-specialised column-chunk streaming SpMM: "
+                     f"TMA-staged chunks, bulk-copy entry ring, FFMA2; F={hidden})")
+        elif csr.streaming:
+            kname = (f"stream_roles_kernel<512,4,KPG,EpiStore> + stream_finish_kernel (role-specialised column-chunk "
+                     f"streaming SpMM with TMA-staged chunks, F={hidden})")
+        else:
+            kname = f"spmm_kernel<4,32,{(hidden // 4 + 31) // 32},EpiStore> (gather SpMM, F={hidden})"
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if csr.streaming and world == 1 and os.path.exists(tpath):

@@ -293,7 +293,7 @@ static int launch_dense_nn(const float* A, int64_t lda, const float* W, int64_t 
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kHbTile = 32;        // rows per staged tile (one bit per row in the per-thread activity mask)
 constexpr int kHbStages = 3;       // cp.async pipeline depth (tiles in flight: kHbStages - 1)
-constexpr int kHbMaxGrid = 2 * kNumSM;  // 96 KB of staged tiles per CTA: two CTAs per SM
+constexpr int kHbMaxGrid = 4 * kNumSM;  // partial rows of the workspace (sparse kernel: 2 CTAs per SM, dense kernel: up to 4)
 
 __device__ __forceinline__ void hb_cp16(void* smem, const void* gmem, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -443,6 +443,127 @@ __global__ void __launch_bounds__(TB, (TB == 256 ? 2 : 1)) hidden_bwd_kernel(con
 }
 
 // out[e] = sum_{b < n_blocks} partials[b][e]  in block order
+// Dense variant with packed FMAs (FFMA2).  The sparse-walk kernel above is bound by shared memory, not by arithmetic: its
+// lanes walk DIFFERENT rows, so every step reads 32 lane-private rows of the dS2 tile (20 wavefronts), and the warp runs for
+// the maximum population count of its lanes (13.5 of 32 rows at 25 % density).  Here every lane of a warp works on the SAME
+// row: the dS2 row is five broadcast LDS.128 (5 wavefronts), H1 is read straight from global memory (one coalesced 128-byte
+// line per warp and row, no staging, no write-back pass), dZ1 is written the same way, and all 40 multiply-adds of a
+// (row, unit) pair are issued as 20 FFMA2 — zeros of H1 cost arithmetic again, but the FMA pipe has room for it now that
+// one instruction carries two of them.  Same summation order per element as the sparse kernel (zeros add exactly 0).
+constexpr int kHdTile = 64;   // rows of dS2 per staged tile
+constexpr int kHdBatch = 8;   // rows whose H1 values a thread holds in flight
+template <int NC4>
+__global__ void __launch_bounds__(256, 3) hidden_bwd_dense_kernel(const float* __restrict__ H1, int64_t ldh,
+                                                                  const float* __restrict__ dS2, int64_t ldd,
+                                                                  const float* __restrict__ W2, int64_t ldw, float scale,
+                                                                  float* __restrict__ dZ1, int64_t ldz,
+                                                                  float* __restrict__ partials, int64_t n, int h, int c,
+                                                                  int64_t rows_per_block) {
+    constexpr int CP = NC4 * 4;
+    __shared__ __align__(16) float Ds[2][kHdTile][CP];
+    const int j = threadIdx.x;
+    const bool live = j < h;
+    const int jc = live ? j : 0;
+    float2 w2[CP / 2], gw2[CP / 2];
+#pragma unroll
+    for (int q = 0; q < CP / 2; ++q) {
+        w2[q].x = (live && 2 * q < c) ? __ldg(W2 + (int64_t)j * ldw + 2 * q) : 0.f;
+        w2[q].y = (live && 2 * q + 1 < c) ? __ldg(W2 + (int64_t)j * ldw + 2 * q + 1) : 0.f;
+        gw2[q] = make_float2(0.f, 0.f);
+    }
+    float gb = 0.f;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r_end = min(n, r_begin + rows_per_block);
+    const int n_tiles = (int)((r_end - r_begin + kHdTile - 1) / kHdTile);
+    auto issue = [&](int t) {
+        if (t < n_tiles) {
+            const int64_t r0 = r_begin + (int64_t)t * kHdTile;
+            float* dsm = &Ds[t & 1][0][0];
+            for (int idx = j; idx < kHdTile * CP; idx += blockDim.x) {
+                const int rr = idx / CP, q = idx % CP;
+                const bool ok = r0 + rr < r_end && q < c;
+                hb_cp4(dsm + idx, ok ? dS2 + (r0 + rr) * ldd + q : dS2, ok);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    // row pointers advance by the leading dimensions (no 64-bit multiply per row); tiles that lie wholly inside the block's
+    // range (all but the last) take a path without per-row bounds checks
+    const float* hp = H1 + r_begin * ldh + jc;   // next row whose H1 value is still to be loaded
+    float* zp = dZ1 + r_begin * ldz + jc;        // next row to be written
+    int64_t hr = r_begin;                        // row index hp points at
+    float hv[kHdBatch];
+#pragma unroll
+    for (int u = 0; u < kHdBatch; ++u) {
+        hv[u] = (hr < r_end) ? __ldg(hp) : 0.f;
+        hp += ldh;
+        ++hr;
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+        issue(t + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const int64_t r0 = r_begin + (int64_t)t * kHdTile;
+        const bool full = r0 + kHdTile + kHdBatch <= r_end;   // this tile and the look-ahead batch are in range
+#pragma unroll 1
+        for (int b = 0; b < kHdTile; b += kHdBatch) {
+            float hn[kHdBatch];
+            if (full) {
+#pragma unroll
+                for (int u = 0; u < kHdBatch; ++u) {  // the next batch of H1 values: in flight while this batch is computed
+                    hn[u] = __ldg(hp);
+                    hp += ldh;
+                }
+                hr += kHdBatch;
+            } else {
+#pragma unroll
+                for (int u = 0; u < kHdBatch; ++u) {
+                    hn[u] = (hr < r_end) ? __ldg(hp) : 0.f;
+                    hp += ldh;
+                    ++hr;
+                }
+            }
+            const float4* dr = reinterpret_cast<const float4*>(&Ds[t & 1][b][0]);  // warp-uniform: broadcast reads
+#pragma unroll
+            for (int u = 0; u < kHdBatch; ++u) {
+                const float a = hv[u];
+                float2 dh01 = make_float2(0.f, 0.f), dh23 = make_float2(0.f, 0.f);
+                const float2 aa = make_float2(a, a);
+#pragma unroll
+                for (int q4 = 0; q4 < NC4; ++q4) {
+                    const float4 d = dr[u * NC4 + q4];
+                    dh01 = __ffma2_rn(make_float2(d.x, d.y), w2[2 * q4], dh01);
+                    dh23 = __ffma2_rn(make_float2(d.z, d.w), w2[2 * q4 + 1], dh23);
+                    gw2[2 * q4] = __ffma2_rn(aa, make_float2(d.x, d.y), gw2[2 * q4]);
+                    gw2[2 * q4 + 1] = __ffma2_rn(aa, make_float2(d.z, d.w), gw2[2 * q4 + 1]);
+                }
+                const float dz = (a > 0.f) ? ((dh01.x + dh01.y) + (dh23.x + dh23.y)) * scale : 0.f;
+                gb += dz;
+                if (full) {
+                    if (live) *zp = dz;
+                } else if (live && r0 + b + u < r_end) {
+                    *zp = dz;
+                }
+                zp += ldz;
+            }
+#pragma unroll
+            for (int u = 0; u < kHdBatch; ++u) hv[u] = hn[u];
+        }
+        __syncthreads();  // the tile buffer is refilled by the next iteration's issue
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (live) {
+        float* out = partials + (int64_t)blockIdx.x * h * (c + 1);
+#pragma unroll
+        for (int q = 0; q < CP / 2; ++q) {
+            if (2 * q < c) out[(int64_t)j * c + 2 * q] = gw2[q].x;
+            if (2 * q + 1 < c) out[(int64_t)j * c + 2 * q + 1] = gw2[q].y;
+        }
+        out[(int64_t)h * c + j] = gb;
+    }
+}
+
 __global__ void sum_partials_kernel(const float* __restrict__ partials, int64_t n_blocks, int64_t n_elem,
                                     float* __restrict__ out_a, int64_t split, float* __restrict__ out_b) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -453,12 +574,31 @@ __global__ void sum_partials_kernel(const float* __restrict__ partials, int64_t 
     else out_b[e - split] = s;
 }
 
+static bool dense_hidden_enabled() {
+    const char* v = getenv("TG_HIDDEN_DENSE");
+    return !(v && *v) || atoi(v) != 0;
+}
+
 template <int NC4>
 static int launch_hidden_bwd(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw,
                              float scale, float* dZ1, int64_t ldz, float* dW2, float* db1, float* partials, int64_t n,
                              int h, int c, cudaStream_t st) {
+    if (h <= 256 && dense_hidden_enabled()) {
+        // dense FFMA2 kernel: three CTAs of 256 threads per SM
+        int64_t grid = 3 * kNumSM;
+        int64_t rpb = ceil_div64(n > 0 ? n : 1, grid);
+        rpb = ceil_div64(rpb, kHdTile) * kHdTile;
+        grid = ceil_div64(n > 0 ? n : 1, rpb);
+        const int threads = ((h + 31) / 32) * 32;
+        hidden_bwd_dense_kernel<NC4><<<(unsigned)grid, threads, 0, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb);
+        TG_LAUNCH_CHECK();
+        const int64_t n_elem = (int64_t)h * (c + 1);
+        sum_partials_kernel<<<(unsigned)ceil_div64(n_elem, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1);
+        TG_LAUNCH_CHECK();
+        return TG_OK;
+    }
     int64_t grid = ceil_div64(n, 2 * kHbTile);
-    if (grid > kHbMaxGrid) grid = kHbMaxGrid;
+    if (grid > 2 * kNumSM) grid = 2 * kNumSM;  // the sparse-walk kernel stages 96 KB of tiles per CTA: two CTAs per SM
     if (grid < 1) grid = 1;
     int64_t rpb = ceil_div64(n, grid);
     rpb = ceil_div64(rpb, kHbTile) * kHbTile;

@@ -53,6 +53,15 @@ class _call:
         return False
 
 
+def _spmm_launches(csr, n_feat: int, philox: bool = False) -> int:
+    """Kernels one SpMM-type call launches: the product itself, the finishing kernel of the streaming paths (hub rows =
+    fixed-order sum of the per-CTA partials + epilogue) and, for Philox dropout on the warp-per-slot path, the kernel
+    that draws the bit-packed keep mask."""
+    streamed = bool(getattr(csr, "streaming", False)) and (n_feat > 32 or bool(getattr(csr, "roles2", False)))
+    mask_kernel = philox and bool(getattr(csr, "roles2", False)) and n_feat % 128 == 0
+    return 1 + int(streamed) + int(mask_kernel)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # tensor plumbing
 # ---------------------------------------------------------------------------------------------------------------
@@ -98,7 +107,7 @@ def spmm(csr: DeviceCSR, B: torch.Tensor, bias: Optional[torch.Tensor] = None,
     if out is None:
         out = torch.empty((csr.n_rows, F), dtype=torch.float32, device=B.device)
     ws, ws_bytes = csr.workspace(F)
-    with torch.cuda.device(B.device), _call("spmm", 1, n_feat=F, csr=csr):
+    with torch.cuda.device(B.device), _call("spmm", _spmm_launches(csr, F), n_feat=F, csr=csr):
         N.check(N.lib().tg_spmm_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(B), _ld(B),
                                     N.ptr(out), _ld(out), F, N.ptr(bias), N.ptr(out_scale), ws, ws_bytes, _stream()),
                 "tg_spmm_f32")
@@ -123,7 +132,7 @@ def gc1_forward(csr: DeviceCSR, S: torch.Tensor, bias: Optional[torch.Tensor], p
     if out is None:
         out = torch.empty((csr.n_rows, F), dtype=torch.float32, device=S.device)
     ws, ws_bytes = csr.workspace(F)
-    with torch.cuda.device(S.device), _call("gc1_fwd", 1, n_feat=F, csr=csr):
+    with torch.cuda.device(S.device), _call("gc1_fwd", _spmm_launches(csr, F, philox=bool(training) and keep_mask is None and p > 0.0), n_feat=F, csr=csr):
         N.check(N.lib().tg_gc1_fwd_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(S), _ld(S),
                                        N.ptr(bias), N.ptr(out), _ld(out), F, float(p), int(bool(training)),
                                        N.ptr(keep_mask), int(seed) & (2**64 - 1), int(offset) & (2**64 - 1),
@@ -172,7 +181,7 @@ def gc2_loss_forward(csr: DeviceCSR, S2: torch.Tensor, bias: Optional[torch.Tens
     dZ2 = torch.empty((csr.n_rows, Cc), dtype=torch.float32, device=dev) if want_grad else None
     row_loss = torch.empty(csr.n_rows, dtype=torch.float32, device=dev)
     ws, ws_bytes = csr.workspace(Cc)
-    with torch.cuda.device(dev), _call("gc2_loss_fwd", 1, n_feat=Cc, csr=csr):
+    with torch.cuda.device(dev), _call("gc2_loss_fwd", _spmm_launches(csr, Cc), n_feat=Cc, csr=csr):
         N.check(N.lib().tg_gc2_loss_fwd_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(S2),
                                             _ld(S2), N.ptr(bias), N.ptr(row_label), float(inv_count), N.ptr(logits),
                                             Cc, N.ptr(dZ2), Cc, N.ptr(row_loss), Cc, ws, ws_bytes, _stream()),
