@@ -207,6 +207,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the single JSON line of the contract: NCCL's version/debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     tg._native.lib()
 
@@ -242,9 +244,7 @@ def run_ours(args):
             # step, the loss goes back to the host (trainer.py:357-367: forward, loss, backward, loss.item())
             for p in model.parameters():
                 p.grad = None
-            labels = labels_host.to(dev, non_blocking=True)
-            index = index_host.to(dev, non_blocking=True)
-            loss = model.loss(x, adj, labels, index)
+            loss = model.loss(x, adj, labels_host, index_host)  # host tensors: copied on a side stream inside the call
             loss.backward()
             return float(loss.item())
 
@@ -274,9 +274,7 @@ def run_ours(args):
         def step_e2e():
             for p in model.parameters():
                 p.grad = None
-            labels = labels_host.to(dev, non_blocking=True)
-            index = index_host.to(dev, non_blocking=True)
-            loss = model.loss(labels=labels, index=index)
+            loss = model.loss(labels=labels_host, index=index_host)  # host tensors: copied on a side stream inside the call
             loss.backward()
             return float(loss.item())
 

@@ -144,16 +144,9 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
             for (int kk = 0; kk < kKPW; ++kk) {
                 int q = htw[kk];  // warp-uniform broadcast reads
                 const int h1 = htw[kk + 1];
-                if ((q & 1) && q < h1) {  // align the run to an entry pair: the pairs below are single 16-byte broadcast reads
-                    const int2 e0 = he[q];
-                    fma4p(acc[kk], __int_as_float(e0.y), lds128(Bl + e0.x));
-                    ++q;
-                }
 #pragma unroll 1
                 for (; q + 4 <= h1; q += 4) {
-                    const int4 p01 = *reinterpret_cast<const int4*>(he + q), p23 = *reinterpret_cast<const int4*>(he + q + 2);
-                    const int2 e0 = make_int2(p01.x, p01.y), e1 = make_int2(p01.z, p01.w);
-                    const int2 e2 = make_int2(p23.x, p23.y), e3 = make_int2(p23.z, p23.w);
+                    const int2 e0 = he[q], e1 = he[q + 1], e2 = he[q + 2], e3 = he[q + 3];
                     const float4 b0 = lds128(Bl + e0.x), b1 = lds128(Bl + e1.x), b2 = lds128(Bl + e2.x), b3 = lds128(Bl + e3.x);
                     fma4p(acc[kk], __int_as_float(e0.y), b0);
                     fma4p(acc[kk], __int_as_float(e1.y), b1);
@@ -161,10 +154,10 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
                     fma4p(acc[kk], __int_as_float(e3.y), b3);
                 }
                 if (q + 2 <= h1) {
-                    const int4 p01 = *reinterpret_cast<const int4*>(he + q);
-                    const float4 b0 = lds128(Bl + p01.x), b1 = lds128(Bl + p01.z);
-                    fma4p(acc[kk], __int_as_float(p01.y), b0);
-                    fma4p(acc[kk], __int_as_float(p01.w), b1);
+                    const int2 e0 = he[q], e1 = he[q + 1];
+                    const float4 b0 = lds128(Bl + e0.x), b1 = lds128(Bl + e1.x);
+                    fma4p(acc[kk], __int_as_float(e0.y), b0);
+                    fma4p(acc[kk], __int_as_float(e1.y), b1);
                     q += 2;
                 }
                 if (q < h1) {

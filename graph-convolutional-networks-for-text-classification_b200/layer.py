@@ -171,7 +171,10 @@ class GCN(Module):
         S1 = _support(x, self.gc1.weight)
         mask, seed, off = self._dropout_state()
         if row_label is None:
-            row_label = ops.make_row_label(csr.n_rows, target, index)
+            if target.is_cuda and index.is_cuda:
+                row_label = ops.make_row_label(csr.n_rows, target, index)
+            else:  # host labels / indices (trainer.py keeps them on the host until convert_tensor): copy on a side stream
+                row_label = ops.make_row_label_async(csr.n_rows, target, index, self.gc1.weight.device)
         inv = 1.0 / max(int(index.numel()), 1)
         loss, logits = ops.GCNLossFunction.apply(S1, self.gc1.bias, self.gc2.weight, self.gc2.bias, csr,
                                                  float(self.dropout), bool(self.training), mask, seed, off, row_label,

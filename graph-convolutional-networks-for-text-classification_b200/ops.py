@@ -168,6 +168,36 @@ def make_row_label(n_rows: int, target: torch.Tensor, index: torch.Tensor) -> to
     return row_label
 
 
+_side_streams: dict = {}
+_ready_events: dict = {}
+
+
+def make_row_label_async(n_rows: int, target: torch.Tensor, index: torch.Tensor, device) -> torch.Tensor:
+    """make_row_label for labels / indices that live in (pinned) HOST memory: the host->device copies and the scatter run
+    on a side stream, so they overlap the layer-1 kernels; the consumer (gc2_loss_forward / masked_ce) makes the compute
+    stream wait on the recorded event just before it launches.  The host tensors must stay unchanged until then."""
+    device = torch.device(device)
+    side = _side_streams.get(device)
+    if side is None:
+        side = _side_streams[device] = torch.cuda.Stream(device)
+    main = torch.cuda.current_stream(device)
+    with torch.cuda.stream(side):
+        t = target.to(device, non_blocking=True)
+        i = index.to(device, non_blocking=True)
+        row_label = make_row_label(n_rows, t, i)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    row_label.record_stream(main)
+    _ready_events[row_label.data_ptr()] = ev
+    return row_label
+
+
+def _wait_ready(row_label: torch.Tensor) -> None:
+    ev = _ready_events.pop(row_label.data_ptr(), None)
+    if ev is not None:
+        torch.cuda.current_stream(row_label.device).wait_event(ev)
+
+
 def gc2_loss_forward(csr: DeviceCSR, S2: torch.Tensor, bias: Optional[torch.Tensor], row_label: torch.Tensor,
                      inv_count: float, want_logits: bool = True, want_grad: bool = True):
     """(loss, logits, dZ2) with Z2 = A @ S2 + b2 and loss = mean CE over labelled rows: tg_gc2_loss_fwd_f32."""
@@ -177,6 +207,7 @@ def gc2_loss_forward(csr: DeviceCSR, S2: torch.Tensor, bias: Optional[torch.Tens
     if row_label.dtype != torch.int32 or row_label.numel() != csr.n_rows or not row_label.is_cuda:
         raise N.TopicGCNError("row_label must be a CUDA int32 vector with one entry per row")
     dev = S2.device
+    _wait_ready(row_label)
     logits = torch.empty((csr.n_rows, Cc), dtype=torch.float32, device=dev) if want_logits else None
     dZ2 = torch.empty((csr.n_rows, Cc), dtype=torch.float32, device=dev) if want_grad else None
     row_loss = torch.empty(csr.n_rows, dtype=torch.float32, device=dev)
@@ -193,6 +224,7 @@ def masked_ce(logits: torch.Tensor, row_label: torch.Tensor, inv_count: float, w
     """(loss, dZ) on existing logits: tg_masked_ce_f32."""
     logits = _dense2d(logits, "logits")
     n, Cc = int(logits.shape[0]), int(logits.shape[1])
+    _wait_ready(row_label)
     dZ = torch.empty((n, Cc), dtype=torch.float32, device=logits.device) if want_grad else None
     row_loss = torch.empty(n, dtype=torch.float32, device=logits.device)
     with torch.cuda.device(logits.device), _call("masked_ce", 1):

@@ -262,7 +262,10 @@ class ShardedGCN(torch.nn.Module):
         if row_label is None:
             labels = lg.labels if labels is None else labels
             index = lg.train_idx if index is None else index
-            row_label = ops.make_row_label(lg.n_local, labels, index)
+            if labels.is_cuda and index.is_cuda:
+                row_label = ops.make_row_label(lg.n_local, labels, index)
+            else:
+                row_label = ops.make_row_label_async(lg.n_local, labels, index, self.gc1.weight.device)
         self._calls += int(self.training)
         return _ShardedLoss.apply(self.gc1.weight, self.gc1.bias, self.gc2.weight, self.gc2.bias, self, row_label,
                                   keep_mask)

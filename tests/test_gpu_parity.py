@@ -573,3 +573,26 @@ def test_roles2_narrow_kernel_parity(tg, monkeypatch, n_docs, n_topics, thr, C):
     assert rel_err(logits.cpu().numpy(), logits_ref) <= SPMM_RTOL
     assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
     assert rel_err(dz.cpu().numpy(), dz_ref) <= 2e-5
+
+
+def test_loss_with_host_labels_matches_device_labels(tg):
+    """GCN.loss accepts the labels / train index in pinned host memory (copied on a side stream that overlaps layer 1) and
+    returns exactly what it returns for device tensors, gradients included."""
+    from topicgcn_b200 import graphgen
+    g, hidden, n_class = graphgen.make_config("c2_20ng_shape", device="cuda:0")
+    torch.manual_seed(0)
+    model = tg.GCN(g.n, hidden, n_class, 0.5).to(dev())
+    model.eval()
+    adj = g.adj()
+    out = []
+    for host in (False, True):
+        for p in model.parameters():
+            p.grad = None
+        labels = g.labels.cpu().pin_memory() if host else g.labels
+        index = g.train_idx.cpu().pin_memory() if host else g.train_idx
+        loss = model.loss(None, adj, labels, index)
+        loss.backward()
+        out.append((loss.detach().clone(), [p.grad.clone() for p in model.parameters()]))
+    assert torch.equal(out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert torch.equal(a, b)
