@@ -564,12 +564,27 @@ __global__ void __launch_bounds__(256, 3) hidden_bwd_dense_kernel(const float* _
     }
 }
 
+// Fixed-order sum of per-block partial rows.  Eight lanes per element take the blocks b = l, l + 8, ... (each in
+// ascending order, four loads in flight) and their eight sums meet in a fixed shuffle tree: deterministic, and the
+// latency of a serial walk over hundreds of L2-resident rows no longer sits on the step's critical path.
 __global__ void sum_partials_kernel(const float* __restrict__ partials, int64_t n_blocks, int64_t n_elem,
                                     float* __restrict__ out_a, int64_t split, float* __restrict__ out_b) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_elem) return;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = t >> 3;
+    const int l = (int)(t & 7);
     float s = 0.f;
-    for (int64_t b = 0; b < n_blocks; ++b) s += partials[b * n_elem + e];
+    if (e < n_elem) {
+        int64_t b = l;
+        for (; b + 24 < n_blocks; b += 32) {
+            const float v0 = partials[b * n_elem + e], v1 = partials[(b + 8) * n_elem + e];
+            const float v2 = partials[(b + 16) * n_elem + e], v3 = partials[(b + 24) * n_elem + e];
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; b < n_blocks; b += 8) s += partials[b * n_elem + e];
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (e >= n_elem || l != 0) return;
     if (e < split) out_a[e] = s;
     else out_b[e - split] = s;
 }
@@ -593,7 +608,7 @@ static int launch_hidden_bwd(const float* H1, int64_t ldh, const float* dS2, int
         hidden_bwd_dense_kernel<NC4><<<(unsigned)grid, threads, 0, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb);
         TG_LAUNCH_CHECK();
         const int64_t n_elem = (int64_t)h * (c + 1);
-        sum_partials_kernel<<<(unsigned)ceil_div64(n_elem, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1);
+        sum_partials_kernel<<<(unsigned)ceil_div64(n_elem * 8, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1);
         TG_LAUNCH_CHECK();
         return TG_OK;
     }
@@ -624,7 +639,7 @@ static int launch_hidden_bwd(const float* H1, int64_t ldh, const float* dS2, int
     }
     TG_LAUNCH_CHECK();
     const int64_t n_elem = (int64_t)h * (c + 1);
-    sum_partials_kernel<<<(unsigned)ceil_div64(n_elem, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1);
+    sum_partials_kernel<<<(unsigned)ceil_div64(n_elem * 8, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1);
     TG_LAUNCH_CHECK();
     return TG_OK;
 }
@@ -771,7 +786,7 @@ int tg_colsum_f32(const float* X, int64_t ldx, int64_t n, int32_t c, float* scra
     const int grid = colsum_grid(n, &rpb);
     colsum_partial_kernel<<<grid, 256, 0, st>>>(X, ldx, n, c, cw, rpb, scratch);
     TG_LAUNCH_CHECK();
-    sum_partials_kernel<<<(unsigned)ceil_div64(c, 256), 256, 0, st>>>(scratch, grid, c, out, c, nullptr);
+    sum_partials_kernel<<<(unsigned)ceil_div64((int64_t)c * 8, 256), 256, 0, st>>>(scratch, grid, c, out, c, nullptr);
     TG_LAUNCH_CHECK();
     return TG_OK;
 }

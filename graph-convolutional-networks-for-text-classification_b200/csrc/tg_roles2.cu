@@ -1060,7 +1060,7 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         cstart.push_back(0);
         for (int64_t j = 0; j < n; ++j) {
             const int d = h_deg[(size_t)j];
-            if (rows == T || ents + d > cap - 2) {  // -2: the staged run starts at an even entry and has even length
+            if (rows > 0 && (rows == T || ents + d > cap - 2)) {  // -2: the staged run starts at an even entry and has even length
                 cstart.push_back((int32_t)j);
                 rows = 0;
                 ents = 0;
@@ -1209,7 +1209,16 @@ int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cuda
     }
     // share of the SMs given to the hub role (both fronts must advance together so that the second reader of a row of B
     // hits L2); the document role also runs the Philox dropout when the epilogue draws the mask itself
-    const int hub_pct = env_int2("TG_ROLES2_HUB_PCT", (epi.drop_mode == 1 && !a.keep_bits) ? 38 : 44);
+    // Both roles are bound by the shared-memory pipe, so the split follows their wavefront counts (128-byte shared-memory
+    // transactions per column slice): hub role 5 per entry (row of B + broadcast entry) + 4 per node (TMA fill), document
+    // role 4 per hub-column entry + ~14 per row (entries, self loop, store), weighted by the pipe utilisation each role
+    // reaches (82 % / 67 %, profiles/r01_roles2_*_only_full.md).  C3: 44 %, the measured optimum.
+    const double hub_w = (5.0 * (double)pl->hub_nnz + 4.0 * (double)pl->n_rows) / 0.82;
+    const double doc_w = (4.0 * (double)(pl->nnz - pl->hub_nnz - pl->n_rows) + 14.0 * (double)pl->n_rows) / 0.67;
+    int auto_pct = (int)(100.0 * hub_w / (hub_w + doc_w) + 0.5);
+    auto_pct = auto_pct < 10 ? 10 : (auto_pct > 90 ? 90 : auto_pct);
+    if (epi.drop_mode == 1 && !a.keep_bits) auto_pct = auto_pct > 16 ? auto_pct - 6 : auto_pct;  // in-kernel Philox loads the document role
+    const int hub_pct = env_int2("TG_ROLES2_HUB_PCT", auto_pct);
     int hub_lanes = (kNumSM * hub_pct / 100) / slices;
     if (hub_lanes < 1) hub_lanes = 1;
     if (hub_lanes > a.n_chunks) hub_lanes = a.n_chunks;

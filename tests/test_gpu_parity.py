@@ -596,3 +596,31 @@ def test_loss_with_host_labels_matches_device_labels(tg):
     assert torch.equal(out[0][0], out[1][0])
     for a, b in zip(out[0][1], out[1][1]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("F", [128, 20])
+def test_roles2_rows_with_other_columns(tg, F):
+    """Short rows whose non-hub columns are more than the self loop (document-document edges next to the document-topic
+    ones): the document role takes its gather path for those entries; parity with the oracle."""
+    from topicgcn_b200 import graphgen
+    n_docs, n_topics = 4000, 48
+    gen = torch.Generator(device="cuda:0").manual_seed(11)
+    d, t, w = graphgen.doc_topic_edges(n_docs, n_topics, 3, 9, gen, dev())
+    ti, tj, ts = graphgen.topic_topic_edges(n_topics, gen, dev(), True)
+    a = torch.randint(0, n_docs, (6000,), generator=gen, device=dev())
+    b = torch.randint(0, n_docs, (6000,), generator=gen, device=dev())
+    lo, hi = torch.minimum(a, b), torch.maximum(a, b)
+    key = torch.unique((lo * n_docs + hi)[lo != hi])
+    u = torch.cat([d, ti + n_docs, key // n_docs])
+    v = torch.cat([t + n_docs, tj + n_docs, key % n_docs])
+    ww = torch.cat([w, ts, torch.rand(key.numel(), generator=gen, device=dev()) * 0.5 + 0.05])
+    n = n_docs + n_topics
+    rows, cols, vals = graphgen.normalize_undirected(u, v, ww, n)
+    csr = tg.DeviceCSR.from_coo(rows, cols, vals, n, n, hub_threshold=64, segment_nnz=32)
+    assert csr.streaming and csr.roles2 and csr.n_hub_rows == n_topics
+    B = torch.randn(n, F, device=dev(), generator=gen)
+    coo = O.Coo(rows.cpu().numpy(), cols.cpu().numpy(), vals.cpu().numpy(), (n, n))
+    ref = O.spmm(coo, B.cpu().numpy())
+    y = tg.spmm(csr, B)
+    assert rel_err(y.cpu().numpy(), ref) <= SPMM_RTOL
+    assert torch.equal(y, tg.spmm(csr, B))
