@@ -169,8 +169,10 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
         }
     }
     float* dst = a.partials + ((int64_t)hl * kKv + warp * kKPW) * a.ldp + (int64_t)(slice * 32 + lane) * 4;
+    if (slice * 32 + lane < a.n_chunks4) {  // (the last slice of a width that is no multiple of 128 is narrower; TMA zero-fills it)
 #pragma unroll
-    for (int kk = 0; kk < kKPW; ++kk) *reinterpret_cast<float4*>(dst + (int64_t)kk * a.ldp) = acc[kk];
+        for (int kk = 0; kk < kKPW; ++kk) *reinterpret_cast<float4*>(dst + (int64_t)kk * a.ldp) = acc[kk];
+    }
 }
 
 // =============================================== document role ===========================================================
@@ -180,6 +182,11 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
     const unsigned gmask = group_mask<8>(lane);
     const int slice = bid % a.doc_slices, dl = bid / a.doc_slices;
     const int q0 = slice * 32 + gl;  // this lane owns the float4 chunks q0 + 8u, u < 4
+    // the last slice of a width that is no multiple of 128 columns is narrower: chunks at or past n_chunks4 do not exist
+    const int slice_bytes = min(kRowBytes, (a.n_chunks4 - slice * 32) * 16);
+    bool valid[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) valid[u] = q0 + 8 * u < a.n_chunks4;
     const size_t bh_bytes = align128((size_t)a.Kh * kRowBytes);
     const size_t en_bytes = align128((size_t)a.cap_doc * 8);
     const size_t st_bytes = en_bytes + (size_t)kJobRows * 8;
@@ -195,12 +202,12 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
         }
         mbar_init(bhbar, 1);
         mbar_fence_init();
-        mbar_expect_tx(bhbar, (unsigned)a.Kh * kRowBytes);
+        mbar_expect_tx(bhbar, (unsigned)a.Kh * (unsigned)slice_bytes);
     }
     __syncthreads();
     // the hub rows of B (this slice) stay resident for the whole kernel
     for (int k = tid; k < a.Kh; k += kThreads)
-        bulk_load_1d(smem + (size_t)k * kRowBytes, a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb + (int64_t)slice * kFT, kRowBytes, bhbar);
+        bulk_load_1d(smem + (size_t)k * kRowBytes, a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb + (int64_t)slice * kFT, (unsigned)slice_bytes, bhbar);
     auto issue = [&](int itn, int jobn) {
         const int s = itn % kStages;
         const int2 jd = __ldg(a.jdesc + jobn);
@@ -223,7 +230,7 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
         if (jobx < a.n_jobs && row < a.n) {
             const float* p = a.B + row * a.ldb + (int64_t)q0 * 4;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) dst[u] = ldg_f4_stream(p + u * 32);
+            for (int u = 0; u < 4; ++u) dst[u] = valid[u] ? ldg_f4_stream(p + u * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
 #pragma unroll
             for (int u = 0; u < 4; ++u) dst[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -233,10 +240,10 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
     float4 bias4[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-        bias4[u] = epi.bias ? __ldg(reinterpret_cast<const float4*>(epi.bias + (int64_t)(q0 + 8 * u) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bias4[u] = (epi.bias && valid[u]) ? __ldg(reinterpret_cast<const float4*>(epi.bias + (int64_t)(q0 + 8 * u) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float gscale = epi.out_scale ? __ldg(epi.out_scale) : 1.f;
     const uint64_t rng_offset = (epi.drop_mode == 1 && epi.offset_dev) ? epi.offset + __ldg(epi.offset_dev) : epi.offset;
-    const int mask_words = a.n_chunks4 / 8;
+    const int mask_words = a.doc_slices * 4;  // row stride of the bit-packed mask: four words per 128-column slice
     auto load_bits = [&](int jobx) {
         const int64_t row = (int64_t)jobx * kJobRows + grp;
         if (a.keep_bits && jobx < a.n_jobs && row < a.n)
@@ -281,7 +288,8 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
             } else {
                 const float* src = a.B + (int64_t)en.x * a.ldb + (int64_t)q0 * 4;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) fma4p(acc[u], v, ldg_f4(src + u * 32));
+                for (int u = 0; u < 4; ++u)
+                    if (valid[u]) fma4p(acc[u], v, ldg_f4(src + u * 32));
             }
         }
         load_self(cur, job + a.doc_lanes);  // next job's self-loop operand: in flight during the hub-column loop
@@ -313,11 +321,13 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
             float* yrow = epi.Y + row * epi.ldy + (int64_t)q0 * 4;
             if (row >= epi.raw_row_begin) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(yrow + u * 32) = acc[u];
+                for (int u = 0; u < 4; ++u)
+                    if (valid[u]) *reinterpret_cast<float4*>(yrow + u * 32) = acc[u];
             } else {
                 Philox4 rnd = Philox4{0, 0, 0, 0};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
+                    if (!valid[u]) continue;
                     float y[4] = {acc[u].x, acc[u].y, acc[u].z, acc[u].w};
                     const float bb[4] = {bias4[u].x, bias4[u].y, bias4[u].z, bias4[u].w};
                     if (epi.bias) {
@@ -338,7 +348,7 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
 #pragma unroll
                         for (int k = 0; k < 4; ++k) y[k] = ((w >> k) & 1u) ? y[k] * epi.scale : 0.f;
                     } else if (epi.drop_mode == 1 && epi.keep_thr == kDropoutHalfThr) {
-                        if (u == 0) rnd = dropout_philox_half(row, (uint32_t)(q >> 5), epi.seed, rng_offset);  // one call per slice
+                        if (u == 0) rnd = dropout_philox_half(row, (uint32_t)(q >> 5), epi.seed, rng_offset);  // one call per slice (u = 0 is valid whenever any chunk is)
                         const uint32_t w = dropout_half_word(rnd, q) >> (4 * (q & 7));
 #pragma unroll
                         for (int k = 0; k < 4; ++k) y[k] = ((w >> k) & 1u) ? y[k] * epi.scale : 0.f;
@@ -1155,7 +1165,7 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
 bool roles2_applicable(const tg_plan* pl, const StreamCall& c) {
     if (!pl || !pl->r2_ok) return false;
     if (env_int2("TG_ROLES2", 1) == 0) return false;
-    if (c.n_feat < kFT || c.n_feat % kFT != 0 || c.n_feat > 1024) return false;
+    if (c.n_feat < 64 || c.n_feat % 4 != 0 || c.n_feat > 1024) return false;
     if (c.ldb % 4 != 0 || !aligned16(c.B) || !encode_tiled_fn()) return false;
     return true;
 }
@@ -1164,7 +1174,7 @@ size_t roles2_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
     if (!pl || !pl->r2_ok) return 0;
     const size_t ld = (size_t)((n_feat + 3) / 4) * 4;
     // per-CTA hub partials + the bit-packed dropout keep mask (n x n_feat / 8 bytes)
-    return (size_t)kNumSM * kKv * ld * sizeof(float) + 16 + (size_t)pl->n_rows * (ld / 8) + 256;
+    return (size_t)kNumSM * kKv * ld * sizeof(float) + 16 + (size_t)pl->n_rows * (((ld + kFT - 1) / kFT) * 16) + 256;
 }
 
 int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st) {
@@ -1177,7 +1187,7 @@ int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cuda
     a.B = c.B; a.ldb = c.ldb; a.n = pl->n_rows; a.n_chunks4 = c.n_feat / 4;
     a.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(c.workspace) + 15u) & ~(uintptr_t)15u);
     a.ldp = (int64_t)((c.n_feat + 3) / 4) * 4;
-    const int slices = c.n_feat / kFT;
+    const int slices = (c.n_feat + kFT - 1) / kFT;
     a.hub_slices = a.doc_slices = slices;
     // Philox dropout: the keep mask is drawn by a separate ALU-bound kernel into a bit-packed side buffer (1 bit per
     // element) instead of inside the document role, whose CTAs have no issue slots to spare (ncu: the in-kernel RNG
@@ -1185,14 +1195,14 @@ int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cuda
     a.keep_bits = nullptr;
     if (epi.drop_mode == 1 && env_int2("TG_ROLES2_BITMASK", 1) != 0) {
         const size_t part_bytes = ((size_t)kNumSM * kKv * a.ldp * sizeof(float) + 16 + 255) & ~(size_t)255;
-        const size_t mask_bytes = (size_t)pl->n_rows * (size_t)(c.n_feat / 8);
+        const size_t mask_bytes = (size_t)pl->n_rows * (size_t)slices * 16;  // four words per row and 128-column slice
         if (c.workspace_bytes >= part_bytes + mask_bytes + 16) {
             uint32_t* bits = reinterpret_cast<uint32_t*>(
                 (reinterpret_cast<uintptr_t>(c.workspace) + part_bytes + 15u) & ~(uintptr_t)15u);
-            const int n_blk = c.n_feat / 64;
+            const int n_blk = slices * 2;  // 64-column blocks, padded to whole slices
             const int64_t threads = pl->n_rows * (int64_t)n_blk * 8;
             if (epi.keep_thr == kDropoutHalfThr) {
-                const int n_words = c.n_feat / 32;
+                const int n_words = slices * 4;
                 const int64_t th = pl->n_rows * (int64_t)((n_words + 3) / 4);
                 r2_keep_bits_half_kernel<<<(unsigned)ceil_div64(th, 256), 256, 0, st>>>(bits, pl->n_rows, n_words, epi.seed, epi.offset,
                                                                                         epi.offset_dev);

@@ -58,7 +58,7 @@ def _spmm_launches(csr, n_feat: int, philox: bool = False) -> int:
     fixed-order sum of the per-CTA partials + epilogue) and, for Philox dropout on the warp-per-slot path, the kernel
     that draws the bit-packed keep mask."""
     streamed = bool(getattr(csr, "streaming", False)) and (n_feat > 32 or bool(getattr(csr, "roles2", False)))
-    mask_kernel = philox and bool(getattr(csr, "roles2", False)) and n_feat % 128 == 0
+    mask_kernel = philox and bool(getattr(csr, "roles2", False)) and n_feat >= 64 and n_feat % 4 == 0
     return 1 + int(streamed) + int(mask_kernel)
 
 

@@ -488,7 +488,7 @@ def test_captured_train_step_matches_eager(tg, small_golden):
 # warp-per-slot role kernels (tg_roles2.cu): F % 128 == 0, <= 256 hub rows
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n_docs,n_topics,F,thr", [(3000, 64, 128, 64), (9000, 256, 256, 48), (777, 37, 384, 24),
-                                                    (20000, 100, 256, 256)])
+                                                    (20000, 100, 256, 256), (5000, 50, 200, 64), (2000, 20, 72, 32)])
 def test_roles2_kernel_parity(tg, monkeypatch, n_docs, n_topics, F, thr):
     """Plain product, fused layer-1 epilogue (eval / explicit mask / Philox via the bit-packed side mask / in-kernel
     Philox) and the raw-row (document-sharded) mode of the warp-per-slot kernels against the oracle; bitwise
