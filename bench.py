@@ -365,7 +365,7 @@ def run_ours(args):
         tot_bytes = sum(v["algorithmic_GB"] * v["launches"] for _, v in dom)
         n_l = sum(v["launches"] for _, v in dom)
         achieved = tot_bytes * 1e3 / tot_ms
-        if getattr(csr, "roles2", False) and hidden >= 64 and hidden % 4 == 0:
+        if ops.roles2_path(csr, hidden) == "wide":
             kname = (f"roles2_kernel + stream_finish_kernel (warp-per-slot role-specialised column-chunk streaming SpMM: "
                      f"TMA-staged chunks, bulk-copy entry ring, FFMA2; F={hidden})")
         elif csr.streaming:

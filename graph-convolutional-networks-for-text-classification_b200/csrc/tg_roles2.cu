@@ -1166,6 +1166,9 @@ bool roles2_applicable(const tg_plan* pl, const StreamCall& c) {
     if (!pl || !pl->r2_ok) return false;
     if (env_int2("TG_ROLES2", 1) == 0) return false;
     if (c.n_feat < 64 || c.n_feat % 4 != 0 || c.n_feat > 1024) return false;
+    // below ~16 K rows a launch is a few microseconds of work and the 148-CTA prologue (resident hub rows, barriers, TMA
+    // descriptors) costs more than it saves: R8 shape 0.150 vs 0.113 ms per captured step with the first-generation kernels
+    if (pl->n_rows < (int64_t)env_int2("TG_ROLES2_MIN_ROWS", 16384)) return false;
     if (c.ldb % 4 != 0 || !aligned16(c.B) || !encode_tiled_fn()) return false;
     return true;
 }
@@ -1270,6 +1273,8 @@ bool roles2_narrow_applicable(const tg_plan* pl, const StreamCall& c) {
     if (!pl || !pl->r2_ok) return false;
     if (env_int2("TG_ROLES2", 1) == 0 || env_int2("TG_ROLES2_NARROW", 1) == 0) return false;
     if (c.n_feat < 4 || c.n_feat > 32 || c.n_feat % 4 != 0) return false;
+    // a narrow operand of a small graph is L2 resident and the gather kernel is faster (20NG shape: 0.033 vs 0.052 ms)
+    if (pl->n_rows < (int64_t)env_int2("TG_ROLES2_NARROW_MIN_ROWS", 131072)) return false;
     if (c.ldb % 4 != 0 || !aligned16(c.B) || !encode_tiled_fn()) return false;
     size_t hub_s, doc_s, lane_s;
     narrow_smem(pl, c.n_feat, &hub_s, &doc_s, &lane_s);

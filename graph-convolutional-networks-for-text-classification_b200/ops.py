@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import os
+
 import torch
 
 from . import _native as N
@@ -53,13 +55,26 @@ class _call:
         return False
 
 
+def roles2_path(csr, n_feat: int):
+    """Which warp-per-slot kernel (csrc/tg_roles2.cu) a product with `n_feat` columns runs on this matrix: "wide", "narrow"
+    or None (first-generation streaming / gather kernels).  Mirrors roles2_applicable / roles2_narrow_applicable."""
+    if not getattr(csr, "roles2", False) or os.environ.get("TG_ROLES2", "1") == "0" or n_feat % 4 != 0:
+        return None
+    if 64 <= n_feat <= 1024 and csr.n_rows >= int(os.environ.get("TG_ROLES2_MIN_ROWS", "16384")):
+        return "wide"
+    if (n_feat <= 32 and os.environ.get("TG_ROLES2_NARROW", "1") != "0"
+            and csr.n_rows >= int(os.environ.get("TG_ROLES2_NARROW_MIN_ROWS", "131072"))):
+        return "narrow"
+    return None
+
+
 def _spmm_launches(csr, n_feat: int, philox: bool = False) -> int:
     """Kernels one SpMM-type call launches: the product itself, the finishing kernel of the streaming paths (hub rows =
     fixed-order sum of the per-CTA partials + epilogue) and, for Philox dropout on the warp-per-slot path, the kernel
     that draws the bit-packed keep mask."""
-    streamed = bool(getattr(csr, "streaming", False)) and (n_feat > 32 or bool(getattr(csr, "roles2", False)))
-    mask_kernel = philox and bool(getattr(csr, "roles2", False)) and n_feat >= 64 and n_feat % 4 == 0
-    return 1 + int(streamed) + int(mask_kernel)
+    path = roles2_path(csr, n_feat)
+    streamed = bool(getattr(csr, "streaming", False)) and (n_feat > 32 or path == "narrow")
+    return 1 + int(streamed) + int(philox and path == "wide")
 
 
 # ---------------------------------------------------------------------------------------------------------------

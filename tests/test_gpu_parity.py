@@ -493,6 +493,8 @@ def test_roles2_kernel_parity(tg, monkeypatch, n_docs, n_topics, F, thr):
     """Plain product, fused layer-1 epilogue (eval / explicit mask / Philox via the bit-packed side mask / in-kernel
     Philox) and the raw-row (document-sharded) mode of the warp-per-slot kernels against the oracle; bitwise
     reproducible; agrees with the first-generation role kernel."""
+    monkeypatch.setenv("TG_ROLES2_MIN_ROWS", "0")          # (the kernels are reserved for large graphs by default)
+    monkeypatch.setenv("TG_ROLES2_NARROW_MIN_ROWS", "0")
     from topicgcn_b200 import graphgen, ops
     g = graphgen.doc_topic_topic_graph(n_docs, n_topics, deg_lo=2, deg_hi=13, dense_topics=True, seed=3, device="cuda:0")
     csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n, hub_threshold=thr, segment_nnz=max(8, thr // 2))
@@ -546,6 +548,8 @@ def test_roles2_narrow_kernel_parity(tg, monkeypatch, n_docs, n_topics, thr, C):
     """Class-sized operands (F <= 32) through the narrow variant of the warp-per-slot kernels: plain product and the fused
     layer-2 epilogue (bias + log-softmax + masked cross-entropy + gradient) against the oracle; deterministic; agrees
     with the gather kernel."""
+    monkeypatch.setenv("TG_ROLES2_MIN_ROWS", "0")          # (the kernels are reserved for large graphs by default)
+    monkeypatch.setenv("TG_ROLES2_NARROW_MIN_ROWS", "0")
     from topicgcn_b200 import graphgen, ops
     g = graphgen.doc_topic_topic_graph(n_docs, n_topics, deg_lo=2, deg_hi=13, dense_topics=True, seed=4, device="cuda:0")
     csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n, hub_threshold=thr, segment_nnz=max(8, thr // 2))
@@ -599,9 +603,11 @@ def test_loss_with_host_labels_matches_device_labels(tg):
 
 
 @pytest.mark.parametrize("F", [128, 20])
-def test_roles2_rows_with_other_columns(tg, F):
+def test_roles2_rows_with_other_columns(tg, monkeypatch, F):
     """Short rows whose non-hub columns are more than the self loop (document-document edges next to the document-topic
     ones): the document role takes its gather path for those entries; parity with the oracle."""
+    monkeypatch.setenv("TG_ROLES2_MIN_ROWS", "0")
+    monkeypatch.setenv("TG_ROLES2_NARROW_MIN_ROWS", "0")
     from topicgcn_b200 import graphgen
     n_docs, n_topics = 4000, 48
     gen = torch.Generator(device="cuda:0").manual_seed(11)
