@@ -315,7 +315,7 @@ def run_ours(args):
     ms_total, launches, clocks = timed(step_device, args.steps, args.warmup, use_hook=True)
     ms_step = ms_total / args.steps
     # ---- with Adam (reported, not the headline) -----------------------------------------------------------------------
-    opt = torch.optim.Adam(params, lr=0.02, fused=True)
+    opt = tg.optim.Adam(params, lr=0.02)  # one tg_adam_f32 pass per parameter (torch.optim.Adam semantics, trainer.py:307)
 
     def step_adam():
         step_device()

@@ -10,7 +10,8 @@ from .csr import DeviceCSR, cached_csr
 from .layer import GCN, GraphConvolution, Featureless
 from .graph import CapturedTrainStep
 from .ops import masked_cross_entropy, spmm
+from . import optim
 
 __all__ = ["GCN", "GraphConvolution", "Featureless", "DeviceCSR", "cached_csr", "masked_cross_entropy", "spmm", "CapturedTrainStep",
-           "TopicGCNError", "LIB_PATH"]
+           "optim", "TopicGCNError", "LIB_PATH"]
 __version__ = "0.1.0"

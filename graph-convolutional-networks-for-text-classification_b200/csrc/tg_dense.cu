@@ -10,6 +10,7 @@
 // All of them read an [N x H] operand once from HBM; the arithmetic (2*N*H*C flop per product) is done on the
 // fp32 FMA pipes because the reference's parity budget (1e-5 relative) rules out TF32 tensor-core inputs.
 // Every cross-block reduction is two-stage with a fixed order: no float atomics.
+#include <math.h>
 #include <stdlib.h>
 
 #include "tg_common.cuh"
@@ -824,3 +825,66 @@ int tg_relu_dropout_bwd_f32(const float* H, int64_t ldh, const float* dH, int64_
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// Adam step (torch.optim.Adam semantics, no amsgrad): one streaming pass, 128-bit accesses, grid = 8 CTAs per SM
+// ------------------------------------------------------------------------------------------------------------
+namespace tg {
+// om1 = 1 - beta1, om2 = 1 - beta2 are formed in double on the host (1.f - 0.999f is 1.3e-5 away from 0.001f)
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float lr_t, float om1, float b2, float om2,
+                                          float inv_bc2_sqrt, float eps, float wd) {
+    g = fmaf(wd, p, g);
+    m = fmaf(om1, g - m, m);
+    v = fmaf(om2, g * g, b2 * v);
+    const float denom = fmaf(sqrtf(v), inv_bc2_sqrt, eps);
+    p -= lr_t * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, float lr_t, float om1, float b2, float om2,
+                                                   float inv_bc2_sqrt, float eps, float wd, int vec) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const int64_t n4 = n >> 2;
+        for (; i < n4; i += stride) {
+            float4 p4 = reinterpret_cast<float4*>(param)[i];
+            const float4 g4 = ldg_f4_stream(grad + i * 4);
+            float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+            adam_elem(p4.x, g4.x, m4.x, v4.x, lr_t, om1, b2, om2, inv_bc2_sqrt, eps, wd);
+            adam_elem(p4.y, g4.y, m4.y, v4.y, lr_t, om1, b2, om2, inv_bc2_sqrt, eps, wd);
+            adam_elem(p4.z, g4.z, m4.z, v4.z, lr_t, om1, b2, om2, inv_bc2_sqrt, eps, wd);
+            adam_elem(p4.w, g4.w, m4.w, v4.w, lr_t, om1, b2, om2, inv_bc2_sqrt, eps, wd);
+            reinterpret_cast<float4*>(param)[i] = p4;
+            reinterpret_cast<float4*>(m)[i] = m4;
+            reinterpret_cast<float4*>(v)[i] = v4;
+        }
+        i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // tail
+    }
+    for (; i < n; i += stride) {
+        float p1 = param[i], m1 = m[i], v1 = v[i];
+        adam_elem(p1, grad[i], m1, v1, lr_t, om1, b2, om2, inv_bc2_sqrt, eps, wd);
+        param[i] = p1; m[i] = m1; v[i] = v1;
+    }
+}
+}  // namespace tg
+
+extern "C" int tg_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                           double beta2, double eps, double weight_decay, int64_t step, void* stream) {
+    using namespace tg;
+    TG_REQUIRE(param && grad && exp_avg && exp_avg_sq, TG_ERR_INVALID_ARG, "null pointer");
+    TG_REQUIRE(n >= 0 && step >= 1, TG_ERR_INVALID_ARG, "n must be >= 0 and step >= 1");
+    if (n == 0) return TG_OK;
+    // bias corrections in double on the host, like torch.optim.Adam
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    const float lr_t = (float)(lr / bc1);
+    const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const int vec = al16(param) && al16(grad) && al16(exp_avg) && al16(exp_avg_sq);
+    int64_t grid = ceil_div64(vec ? (n + 3) / 4 : n, 256);
+    if (grid > 8 * kNumSM) grid = 8 * kNumSM;
+    adam_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr_t, (float)(1.0 - beta1), (float)beta2,
+                                                              (float)(1.0 - beta2), inv_bc2_sqrt, (float)eps, (float)weight_decay, vec);
+    TG_LAUNCH_CHECK();
+    return TG_OK;
+}

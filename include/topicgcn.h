@@ -177,6 +177,20 @@ int tg_colsum_f32(const float* X, int64_t ldx, int64_t n, int32_t c, float* scra
 int tg_relu_dropout_bwd_f32(const float* H, int64_t ldh, const float* dH, int64_t lddh, float scale,
                             float* dZ, int64_t ldz, int64_t n, int32_t f, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer for the featureless first layer.
+ *   tg_adam_f32 : one Adam step on n elements, in place — torch.optim.Adam semantics without amsgrad
+ *                 (reference trainer.py:307 `th.optim.Adam(model.parameters(), lr=0.02)`, step at :362):
+ *                     g   = grad + weight_decay * param
+ *                     m   = m + (1 - beta1) * (g - m) ;  v = beta2 * v + (1 - beta2) * g * g
+ *                     param -= (lr / (1 - beta1^step)) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ *                 `step` is the 1-based step count; the hyper-parameters are doubles like torch's (1 - beta and the
+ *                 bias corrections are formed in double, then rounded to fp32).  With X = I the weight of layer 1 is [N x hidden]
+ *                 (1 GB at 1 M nodes): the update is one pass, 16 B read + 12 B written per element.
+ * ---------------------------------------------------------------------------------------------- */
+int tg_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                double beta1, double beta2, double eps, double weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -630,3 +630,37 @@ def test_roles2_rows_with_other_columns(tg, monkeypatch, F):
     y = tg.spmm(csr, B)
     assert rel_err(y.cpu().numpy(), ref) <= SPMM_RTOL
     assert torch.equal(y, tg.spmm(csr, B))
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_adam_matches_torch_adam(tg, wd):
+    """tg.optim.Adam (one tg_adam_f32 pass per parameter) against torch.optim.Adam and the oracle's adam_step over several
+    steps; the state dicts interchange (same keys, same shapes)."""
+    gen = torch.Generator(device="cuda:0").manual_seed(3)
+    shapes = [(1031, 200), (200,), (200, 8), (7,)]
+    p0 = [torch.randn(s, device=dev(), generator=gen) for s in shapes]
+    ours = [p.clone().requires_grad_(True) for p in p0]
+    ref = [p.clone().requires_grad_(True) for p in p0]
+    o1 = tg.optim.Adam(ours, lr=0.02, weight_decay=wd)
+    o2 = torch.optim.Adam(ref, lr=0.02, weight_decay=wd)
+    params_np = {str(i): p.cpu().numpy().copy() for i, p in enumerate(p0)}
+    st_np = {}
+    for step in range(6):
+        grads = [torch.randn(s, device=dev(), generator=gen) * (0.1 + step) for s in shapes]
+        for a, b, g in zip(ours, ref, grads):
+            a.grad, b.grad = g.clone(), g.clone()
+        o1.step()
+        o2.step()
+        if wd == 0.0:
+            O.adam_step(params_np, {str(i): g.cpu().numpy() for i, g in enumerate(grads)}, st_np, lr=0.02)
+    for i, (a, b) in enumerate(zip(ours, ref)):
+        assert rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy()) <= 2e-6
+        if wd == 0.0:
+            assert rel_err(a.detach().cpu().numpy(), params_np[str(i)]) <= 2e-6
+    sd1, sd2 = o1.state_dict(), o2.state_dict()
+    assert set(sd1["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    for k in sd1["state"]:
+        assert rel_err(sd1["state"][k]["exp_avg"].cpu().numpy(), sd2["state"][k]["exp_avg"].cpu().numpy()) <= 2e-6
+        assert rel_err(sd1["state"][k]["exp_avg_sq"].cpu().numpy(), sd2["state"][k]["exp_avg_sq"].cpu().numpy()) <= 2e-6
+    o3 = torch.optim.Adam([p.clone().requires_grad_(True) for p in p0], lr=0.02, weight_decay=wd)
+    o3.load_state_dict(sd1)   # a checkpoint written with ours loads into torch's optimizer
