@@ -888,3 +888,53 @@ extern "C" int tg_adam_f32(float* param, const float* grad, float* exp_avg, floa
     TG_LAUNCH_CHECK();
     return TG_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// per-class tp / fp / fn counts of argmax(logits) against the row labels (integer atomics: order independent)
+// ------------------------------------------------------------------------------------------------------------
+namespace tg {
+constexpr int kCcMaxClass = 1024;
+__global__ void __launch_bounds__(256) class_counts_kernel(const float* __restrict__ logits, int64_t ldl,
+                                                           const int32_t* __restrict__ row_label, int64_t n, int c,
+                                                           int32_t* __restrict__ counts) {
+    extern __shared__ int32_t cc_sh[];  // [3 * c]
+    for (int i = threadIdx.x; i < 3 * c; i += blockDim.x) cc_sh[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        const int y = __ldg(row_label + r);
+        if (y < 0) continue;
+        const float* z = logits + r * ldl;
+        float best = __ldg(z);
+        int pred = 0;
+        for (int k = 1; k < c; ++k) {
+            const float v = __ldg(z + k);
+            if (v > best) { best = v; pred = k; }  // strict: the first maximum wins, like th.max
+        }
+        if (pred == y) {
+            atomicAdd(&cc_sh[y], 1);
+        } else {
+            atomicAdd(&cc_sh[c + pred], 1);
+            if (y < c) atomicAdd(&cc_sh[2 * c + y], 1);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * c; i += blockDim.x)
+        if (cc_sh[i]) atomicAdd(counts + i, cc_sh[i]);
+}
+}  // namespace tg
+
+extern "C" int tg_class_counts_i32(const float* logits, int64_t ldl, const int32_t* row_label, int64_t n, int32_t c,
+                                   int32_t* counts, void* stream) {
+    using namespace tg;
+    TG_REQUIRE(logits && row_label && counts, TG_ERR_INVALID_ARG, "null pointer");
+    TG_REQUIRE(c >= 1 && c <= kCcMaxClass && ldl >= c && n >= 0, TG_ERR_INVALID_ARG, "need 1 <= c <= %d, ldl >= c", kCcMaxClass);
+    cudaStream_t st = as_stream(stream);
+    TG_CUDA(cudaMemsetAsync(counts, 0, (size_t)3 * c * sizeof(int32_t), st));
+    if (n == 0) return TG_OK;
+    int64_t grid = ceil_div64(n, 256);
+    if (grid > 4 * kNumSM) grid = 4 * kNumSM;
+    class_counts_kernel<<<(unsigned)grid, 256, (size_t)3 * c * sizeof(int32_t), st>>>(logits, ldl, row_label, n, c, counts);
+    TG_LAUNCH_CHECK();
+    return TG_OK;
+}

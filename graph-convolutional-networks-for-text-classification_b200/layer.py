@@ -14,6 +14,8 @@ entry (forward + masked cross-entropy of trainer.py:357-359 in one autograd node
 """
 from __future__ import annotations
 
+import functools
+
 import math
 from typing import Optional
 
@@ -72,6 +74,22 @@ def _as_csr(adj) -> DeviceCSR:
             raise N.TopicGCNError("adj must be on a CUDA device; topicgcn_b200 has no CPU fallback")
         return cached_csr(adj)
     raise N.TopicGCNError("adj must be a torch sparse tensor (COO/CSR) or a DeviceCSR")
+
+
+def _metrics_from_counts(tp, fp, fn, n_rows: int) -> dict:
+    """utils.accuracy / utils.macro_f1 (reference utils.py:71-85, 107): per-class ratios with 0/0 -> 0, macro-averaged,
+    F1 of the two averages."""
+    import numpy as np
+    tp, fp, fn = (np.asarray(a, dtype=np.float64) for a in (tp, fp, fn))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        prec = tp / (tp + fp)
+        rec = tp / (tp + fn)
+    prec[np.isnan(prec)] = 0
+    rec[np.isnan(rec)] = 0
+    P, R = float(prec.mean()), float(rec.mean())
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f1 = float(np.float64(2 * P * R) / np.float64(P + R))
+    return {"acc": float(tp.sum()) / max(int(n_rows), 1), "macro_f1": f1, "precision": P, "recall": R}
 
 
 def _support(x, weight: torch.Tensor) -> torch.Tensor:
@@ -174,9 +192,40 @@ class GCN(Module):
             if target.is_cuda and index.is_cuda:
                 row_label = ops.make_row_label(csr.n_rows, target, index)
             else:  # host labels / indices (trainer.py keeps them on the host until convert_tensor): copy on a side stream
-                row_label = ops.make_row_label_async(csr.n_rows, target, index, self.gc1.weight.device)
+                # (a callable: the fused step launches layer 1 first and only then queues the copies on the side stream)
+                row_label = functools.partial(ops.make_row_label_async, csr.n_rows, target, index, self.gc1.weight.device)
         inv = 1.0 / max(int(index.numel()), 1)
         loss, logits = ops.GCNLossFunction.apply(S1, self.gc1.bias, self.gc2.weight, self.gc2.bias, csr,
                                                  float(self.dropout), bool(self.training), mask, seed, off, row_label,
                                                  inv, bool(return_logits), self._offset_dev)
         return (loss, logits) if return_logits else loss
+
+    @torch.no_grad()
+    def evaluate(self, x, adj, target: torch.Tensor, index: torch.Tensor, prefix: str = "val") -> dict:
+        """The reference's validation / test pass (`TopicGCNTrainer.val`, trainer.py:378-398): eval-mode forward, mean
+        cross-entropy, accuracy and macro F1 / precision / recall on `index` — with the per-class counts taken by one
+        kernel and ONE device->host copy instead of the reference's 3 * nclass + 2 `.item()` syncs (utils.py:25-109).
+        The module's train / eval flag is left as it was.  Returns the reference's dict."""
+        was_training = self.training
+        self.eval()
+        try:
+            csr = _as_csr(adj)
+            S1 = _support(x, self.gc1.weight)
+            if target.is_cuda and index.is_cuda:
+                row_label = ops.make_row_label(csr.n_rows, target, index)
+            else:
+                row_label = ops.make_row_label_async(csr.n_rows, target, index, self.gc1.weight.device)
+            n_index = max(int(index.numel()), 1)
+            H1 = ops.gc1_forward(csr, S1.detach(), self.gc1.bias.detach() if self.gc1.bias is not None else None,
+                                 float(self.dropout), False)
+            S2 = ops.dense_nn(H1, self.gc2.weight.detach())
+            loss, logits, _ = ops.gc2_loss_forward(csr, S2, self.gc2.bias.detach() if self.gc2.bias is not None else None,
+                                                   row_label, 1.0 / n_index, want_logits=True, want_grad=False)
+            counts = ops.class_counts(logits, row_label)
+            packed = torch.cat([loss.reshape(1).to(torch.float64), counts.reshape(-1).to(torch.float64)]).cpu()  # the one sync
+        finally:
+            self.train(was_training)
+        loss_v = float(packed[0])
+        c = counts.shape[1]
+        tp, fp, fn = (packed[1 + i * c:1 + (i + 1) * c].numpy() for i in range(3))
+        return {f"{prefix}_loss": loss_v, **_metrics_from_counts(tp, fp, fn, n_index)}

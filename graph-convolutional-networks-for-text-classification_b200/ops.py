@@ -248,6 +248,21 @@ def masked_ce(logits: torch.Tensor, row_label: torch.Tensor, inv_count: float, w
     return reduce_sum(row_loss), dZ
 
 
+def class_counts(logits: torch.Tensor, row_label: torch.Tensor) -> torch.Tensor:
+    """int32 [3 x C] true positives / false positives / false negatives of argmax(logits) on the rows with
+    row_label >= 0: tg_class_counts_i32 (the sums behind utils.accuracy / utils.macro_f1, reference utils.py:25-109)."""
+    logits = _dense2d(logits, "logits")
+    n, Cc = int(logits.shape[0]), int(logits.shape[1])
+    if row_label.dtype != torch.int32 or row_label.numel() != n or not row_label.is_cuda:
+        raise N.TopicGCNError("row_label must be a CUDA int32 vector with one entry per row")
+    _wait_ready(row_label)
+    counts = torch.empty((3, Cc), dtype=torch.int32, device=logits.device)
+    with torch.cuda.device(logits.device), _call("class_counts", 1):
+        N.check(N.lib().tg_class_counts_i32(N.ptr(logits), _ld(logits), N.ptr(row_label), n, Cc, N.ptr(counts), _stream()),
+                "tg_class_counts_i32")
+    return counts
+
+
 def dense_nn(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
     """A[n x h] @ W[h x c] for skinny c: tg_dense_nn_f32."""
     A = _dense2d(A, "A")
@@ -399,6 +414,8 @@ class GCNLossFunction(torch.autograd.Function):
                 row_label, inv_count: float, want_logits: bool, offset_dev=None):
         H1 = gc1_forward(csr, S1, b1, p, training, keep_mask, seed, offset, offset_dev=offset_dev)
         S2 = dense_nn(H1, W2)
+        if callable(row_label):  # host labels: start their copy only now, with layer 1 already queued on the device
+            row_label = row_label()
         loss, logits, dZ2 = gc2_loss_forward(csr, S2, b2, row_label, inv_count, want_logits=want_logits, want_grad=True)
         ctx.save_for_backward(H1, W2, dZ2)
         ctx.csr, ctx.scale = csr, _dropout_scale(p, training)

@@ -178,6 +178,17 @@ int tg_relu_dropout_bwd_f32(const float* H, int64_t ldh, const float* dH, int64_
                             float* dZ, int64_t ldz, int64_t n, int32_t f, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Validation metrics on the device: the per-class counts behind utils.accuracy and
+ * utils.macro_f1 (reference utils.py:25-109, called from trainer.py:385-389) in ONE kernel instead of
+ * 3 * nclass + 1 `.item()` round trips.
+ *   tg_class_counts_i32 : for every row with row_label >= 0: pred = argmax(logits[row, 0..c)) (ties: lowest
+ *                         class);  counts[0*c + k] true positives, [1*c + k] false positives, [2*c + k]
+ *                         false negatives of class k.  counts [3*c] int32 is zeroed by the call.
+ * ---------------------------------------------------------------------------------------------- */
+int tg_class_counts_i32(const float* logits, int64_t ldl, const int32_t* row_label, int64_t n, int32_t c,
+                        int32_t* counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimizer for the featureless first layer.
  *   tg_adam_f32 : one Adam step on n elements, in place — torch.optim.Adam semantics without amsgrad
  *                 (reference trainer.py:307 `th.optim.Adam(model.parameters(), lr=0.02)`, step at :362):

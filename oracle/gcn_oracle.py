@@ -351,6 +351,34 @@ def adam_step(params: dict, grads: dict, state: dict, lr: float = 0.02, b1: floa
         params[k] -= (np.float32(step) * m / denom).astype(np.float32)
 
 
+def class_counts(logits: np.ndarray, target: np.ndarray, index: np.ndarray, n_class: int) -> np.ndarray:
+    """[3 x n_class] true positives / false positives / false negatives of argmax(logits[index]) against target[index]
+    (the per-class sums of utils.macro_f1, reference utils.py:57-69; ties resolve to the lowest class like th.max)."""
+    pred = logits[index].argmax(axis=1)
+    targ = np.asarray(target)[index]
+    out = np.zeros((3, n_class), dtype=np.int64)
+    for c in range(n_class):
+        out[0, c] = np.sum((pred == c) & (targ == c))
+        out[1, c] = np.sum((pred == c) & (targ != c))
+        out[2, c] = np.sum((pred != c) & (targ == c))
+    return out
+
+
+def metrics_from_counts(counts: np.ndarray, n_rows: int) -> dict:
+    """accuracy (utils.py:89-109) and macro F1 / precision / recall (utils.py:71-85: per-class ratios with 0/0 -> 0,
+    macro-averaged, F1 of the two averages) from the per-class counts."""
+    tp, fp, fn = (np.asarray(counts[i], dtype=np.float64) for i in range(3))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        prec = tp / (tp + fp)
+        rec = tp / (tp + fn)
+    prec[np.isnan(prec)] = 0
+    rec[np.isnan(rec)] = 0
+    P, R = float(prec.mean()), float(rec.mean())
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f1 = float(np.float64(2 * P * R) / np.float64(P + R))
+    return {"acc": float(tp.sum()) / max(int(n_rows), 1), "macro_f1": f1, "precision": P, "recall": R}
+
+
 def accuracy(logits: np.ndarray, target: np.ndarray, index: np.ndarray) -> float:
     """utils.accuracy (reference utils.py:89-109) on logits[index]."""
     return float((logits[index].argmax(axis=1) == np.asarray(target)[index]).mean())

@@ -664,3 +664,32 @@ def test_adam_matches_torch_adam(tg, wd):
         assert rel_err(sd1["state"][k]["exp_avg_sq"].cpu().numpy(), sd2["state"][k]["exp_avg_sq"].cpu().numpy()) <= 2e-6
     o3 = torch.optim.Adam([p.clone().requires_grad_(True) for p in p0], lr=0.02, weight_decay=wd)
     o3.load_state_dict(sd1)   # a checkpoint written with ours loads into torch's optimizer
+
+
+def test_class_counts_and_evaluate(tg):
+    """tg_class_counts_i32 against the oracle on the reference-generated metric fixtures (bit-exact integers), and
+    GCN.evaluate (the reference's val(): eval forward + loss + accuracy + macro F1, one host sync) against the oracle."""
+    import os
+    from topicgcn_b200 import graphgen, ops
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics.npz"))
+    for i in range(int(g["n_cases"])):
+        logits, target, ref = g[f"logits_{i}"], g[f"target_{i}"], g[f"ref_{i}"]
+        n, c = logits.shape
+        index = np.arange(0, n, 2)   # a subset: the other rows carry label -1 and must not count
+        row_label = ops.make_row_label(n, torch.tensor(target, device=dev()), torch.tensor(index, device=dev()))
+        counts = ops.class_counts(torch.tensor(logits, device=dev()), row_label).cpu().numpy()
+        assert np.array_equal(counts, O.class_counts(logits, target, index, c))
+    gg, hidden, n_class = graphgen.make_config("c2_20ng_shape", device="cuda:0")
+    torch.manual_seed(1)
+    model = tg.GCN(gg.n, hidden, n_class, 0.5).to(dev())
+    model.train()
+    res = model.evaluate(None, gg.adj(), gg.labels.cpu().pin_memory(), gg.val_idx.cpu().pin_memory(), prefix="val")
+    assert model.training                                     # flag restored
+    model.eval()
+    logits = model(None, gg.adj()).detach().cpu().numpy()
+    idx, lab = gg.val_idx.cpu().numpy(), gg.labels.cpu().numpy()
+    want = O.metrics_from_counts(O.class_counts(logits, lab, idx, n_class), idx.size)
+    for k in ("acc", "macro_f1", "precision", "recall"):
+        assert abs(res[k] - want[k]) <= 1e-12, (k, res[k], want[k])
+    loss_ref, _ = O.masked_cross_entropy(logits, lab, idx)
+    assert abs(res["val_loss"] - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))

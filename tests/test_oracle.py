@@ -118,3 +118,17 @@ def test_philox_mask_statistics():
     m2 = O.philox_keep_mask(257, 200, 0.5, seed=1234, offset=4)
     assert (m != m2).mean() > 0.4
     assert abs(O.philox_keep_mask(64, 256, 0.2, 7, 1).mean() - 0.8) < 0.02
+
+
+def test_metrics_match_reference_golden():
+    """oracle class_counts / metrics_from_counts against utils.accuracy / utils.macro_f1 of the real reference
+    (tests/golden/make_golden_metrics.py), including classes that never occur (0/0 -> 0)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics.npz"))
+    for i in range(int(g["n_cases"])):
+        logits, target, ref = g[f"logits_{i}"], g[f"target_{i}"], g[f"ref_{i}"]
+        index = np.arange(logits.shape[0])
+        counts = O.class_counts(logits, target, index, logits.shape[1])
+        m = O.metrics_from_counts(counts, index.size)
+        got = np.array([m["acc"], m["macro_f1"], m["precision"], m["recall"]])
+        assert np.allclose(got, ref, rtol=0, atol=1e-12), (i, got, ref)
