@@ -119,3 +119,23 @@ def test_bench_reference_arm_contract():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "gcn_fwd_bwd_epochs_per_sec" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_gpu():
+    """tg_adam_f32 / tg_class_counts_i32 validate their arguments before touching CUDA: callable (and failing loudly)
+    on a GPU-less host; `optim.Adam` and `GCN.evaluate` refuse CPU tensors instead of falling back."""
+    from topicgcn_b200 import _native as N
+    lib = N.lib()
+    assert lib.tg_adam_f32(0, 0, 0, 0, 16, 0.02, 0.9, 0.999, 1e-8, 0.0, 1, 0) != 0
+    assert b"null pointer" in lib.tg_last_error()
+    buf = np.zeros(16, dtype=np.float32)
+    ptr = buf.ctypes.data
+    assert lib.tg_adam_f32(ptr, ptr, ptr, ptr, 16, 0.02, 0.9, 0.999, 1e-8, 0.0, 0, 0) != 0      # step must be >= 1
+    assert lib.tg_class_counts_i32(0, 4, 0, 4, 4, 0, 0) != 0
+    assert lib.tg_class_counts_i32(ptr, 4, ptr, 4, 4096, ptr, 0) != 0                          # too many classes
+    p = torch.nn.Parameter(torch.zeros(8))
+    p.grad = torch.ones(8)
+    with pytest.raises(tg.TopicGCNError):
+        tg.optim.Adam([p], lr=0.02).step()
+    with pytest.raises(ValueError):
+        tg.optim.Adam([p], lr=-1.0)
