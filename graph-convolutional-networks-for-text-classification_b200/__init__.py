@@ -11,7 +11,8 @@ from .layer import GCN, GraphConvolution, Featureless
 from .graph import CapturedTrainStep
 from .ops import masked_cross_entropy, spmm
 from . import optim
+from . import ingest
 
 __all__ = ["GCN", "GraphConvolution", "Featureless", "DeviceCSR", "cached_csr", "masked_cross_entropy", "spmm", "CapturedTrainStep",
-           "optim", "TopicGCNError", "LIB_PATH"]
+           "optim", "ingest", "TopicGCNError", "LIB_PATH"]
 __version__ = "0.1.0"

@@ -50,14 +50,17 @@ class SyntheticGraph:
                                        check_invariants=False)
 
 
-def normalize_undirected(u: torch.Tensor, v: torch.Tensor, w: torch.Tensor, n: int):
+def normalize_undirected(u: torch.Tensor, v: torch.Tensor, w: torch.Tensor, n: int, diag_extra=None):
     """Unique undirected edges (u != v) with fp32 weights -> row-major COO of Â = D^-1/2 (A+I) D^-1/2 with the
-    reference's arithmetic (utils.py:206-213).  Returns (rows int64, cols int64, vals fp32)."""
+    reference's arithmetic (utils.py:206-213).  Returns (rows int64, cols int64, vals fp32).
+    diag_extra: optional float64 [n] added to the diagonal of A + I (self loops of an ingested edge list)."""
     dev = u.device
     ar = torch.arange(n, dtype=torch.int64, device=dev)
     r = torch.cat([u, v, ar])
     c = torch.cat([v, u, ar])
     a = torch.cat([w, w, torch.ones(n, dtype=torch.float32, device=dev)]).to(torch.float64)
+    if diag_extra is not None:
+        a[2 * u.numel():] += diag_extra.to(torch.float64)
     del ar
     order = torch.argsort(r * n + c)  # keys are unique: any sort is a row-major ordering
     r, c, a = r[order], c[order], a[order]

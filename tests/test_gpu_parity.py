@@ -693,3 +693,24 @@ def test_class_counts_and_evaluate(tg):
         assert abs(res[k] - want[k]) <= 1e-12, (k, res[k], want[k])
     loss_ref, _ = O.masked_cross_entropy(logits, lab, idx)
     assert abs(res["val_loss"] - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+
+
+def test_edge_list_ingest_on_device(tg):
+    """The device-side ingest gives the reference's adjacency bit for bit (fixture made by the real reference ingest) and
+    the result goes straight into the drop-in module."""
+    import os
+    from topicgcn_b200 import ingest
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    ref = np.load(os.path.join(gdir, "edges_small_adj.npz"))
+    adj = ingest.load_adjacency(os.path.join(gdir, "edges_small.txt"), device="cuda:0")
+    idx = adj._indices().cpu().numpy()
+    assert np.array_equal(idx[0], ref["rows"]) and np.array_equal(idx[1], ref["cols"])
+    assert np.array_equal(adj._values().cpu().numpy().view(np.uint32), ref["vals"].view(np.uint32))
+    n = int(ref["n"])
+    torch.manual_seed(0)
+    model = tg.GCN(n, 16, 4, 0.5).to(dev()).eval()
+    logits = model(None, adj).detach().cpu().numpy()
+    coo = O.Coo(ref["rows"], ref["cols"], ref["vals"], (n, n))
+    params = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    want, _ = O.gcn_forward(None, coo, params, training=False)
+    assert rel_err(logits, want) <= 2e-5

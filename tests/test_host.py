@@ -139,3 +139,29 @@ def test_new_entry_points_reject_bad_arguments_without_a_gpu():
         tg.optim.Adam([p], lr=0.02).step()
     with pytest.raises(ValueError):
         tg.optim.Adam([p], lr=-1.0)
+
+
+def test_edge_list_ingest_matches_reference_bit_for_bit(tmp_path):
+    """ingest.load_adjacency on the committed edge-list fixture == the adjacency the REAL reference ingest
+    (networkx + scipy + utils.preprocess_adj, tests/golden/make_golden_ingest.py) made of the same file: indices and fp32
+    bits; duplicate edges keep their last weight; ids must be dense; self loops land on the diagonal."""
+    from topicgcn_b200 import ingest
+    gdir = os.path.join(ROOT, "tests", "golden")
+    ref = np.load(os.path.join(gdir, "edges_small_adj.npz"))
+    adj = ingest.load_adjacency(os.path.join(gdir, "edges_small.txt"), device="cpu")
+    assert tuple(adj.shape) == (int(ref["n"]), int(ref["n"]))
+    idx = adj._indices().numpy()
+    assert np.array_equal(idx[0], ref["rows"]) and np.array_equal(idx[1], ref["cols"])
+    assert np.array_equal(adj._values().numpy().view(np.uint32), ref["vals"].view(np.uint32))
+    # a hole in the id range is an error, like the reference's nodelist=range(n)
+    bad = tmp_path / "bad.txt"
+    bad.write_text("0 1 0.5\n1 3 0.25\n")
+    with pytest.raises(tg.TopicGCNError):
+        ingest.load_adjacency(str(bad), device="cpu")
+    # self loop: (A + I)[1,1] = 1 + 0.5 ; rows: 0:{0,1} 1:{0,1} ; oracle arithmetic
+    loop = tmp_path / "loop.txt"
+    loop.write_text("0 1 0.25\n1 1 0.5\n")
+    a = ingest.load_adjacency(str(loop), device="cpu").to_dense().numpy()
+    d0, d1 = (1 + 0.25) ** -0.5, (1.5 + 0.25) ** -0.5
+    want = np.array([[d0 * d0, 0.25 * d0 * d1], [0.25 * d0 * d1, 1.5 * d1 * d1]])
+    assert np.allclose(a, want, rtol=1e-6)
