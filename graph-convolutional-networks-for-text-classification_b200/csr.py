@@ -55,6 +55,7 @@ class DeviceCSR:
         self.n_hub_rows, self.n_segments, self.hub_nnz, self.max_row_nnz = (int(info[i]) for i in range(4))
         self.hub_threshold, self.segment_nnz = int(info[4]), int(info[5])
         self.streaming, self.chunk_rows = bool(info[6] & 1), int(info[7])
+        self.roles2_rect = int(info[6] >> 2) & 3  # 1: resident-table product (X @ W), 2: all-hub product (X^T @ dS)
         self.roles2 = bool(info[6] & 2)  # warp-per-slot role kernels (tg_roles2.cu) used for 64 <= F <= 1024 (F % 4 == 0) and for F <= 32
 
     def __del__(self):

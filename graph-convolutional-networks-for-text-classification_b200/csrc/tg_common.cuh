@@ -68,6 +68,12 @@ struct tg_plan {
 
     // ---- warp-per-slot role kernels (tg_roles2.cu): hub rows <= 256, 128-column slices -------------------------------
     bool r2_ok = false;
+    // rectangular operands (sparse feature matrices X [n x nfeat <= 256] and their transposes):
+    //   1 = "table": every column's row of B is resident (document role only: X * W)
+    //   2 = "all hub": every row is a hub row (hub role only: X^T * dS)
+    int32_t r2_rect = 0;
+    int32_t r2_stages = 4;           // document-role ring depth that fits next to the resident table
+    int32_t* r2_ident = nullptr;     // [n_cols] 0,1,2,... (the table rows of mode 1)
     int32_t r2_T = 0, r2_n_chunks = 0, r2_cap_hub = 0;   // hub role: nodes per chunk, chunks, staged entries per chunk (max)
     int32_t r2_n_jobs = 0, r2_cap_doc = 0;               // document role: jobs of 64 rows, staged entries per job (max)
     int2* r2_hent = nullptr;         // [hub_nnz+2] hub entries, (chunk, slot)-major: {byte offset of the column's row in the staged tile, value bits}

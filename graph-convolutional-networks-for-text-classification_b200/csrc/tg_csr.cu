@@ -361,6 +361,14 @@ int tg_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* va
         tg_plan_destroy(pl);
         return rc;
     }
+    // optional sub-plans for rectangular operands (sparse feature matrix / its transpose, <= 256 features)
+    if (!pl->r2_ok) {
+        const int rc2 = tg::roles2_rect_plan_build(pl, rowptr, colidx, vals, h_ptr.data(), st);
+        if (rc2 != TG_OK) {
+            tg_plan_destroy(pl);
+            return rc2;
+        }
+    }
     *plan_out = pl;
     return TG_OK;
 }
@@ -377,7 +385,7 @@ int tg_plan_info(const tg_plan* pl, int64_t info[8]) {
     TG_REQUIRE(pl && info, TG_ERR_INVALID_ARG, "null pointer");
     info[0] = pl->n_hub; info[1] = pl->n_seg; info[2] = pl->hub_nnz;
     info[3] = pl->max_row_nnz; info[4] = pl->hub_threshold; info[5] = pl->segment_nnz;
-    info[6] = (pl->stream_ok ? 1 : 0) | (pl->r2_ok ? 2 : 0); info[7] = pl->stream_ok ? pl->chunk_rows : 0;
+    info[6] = (pl->stream_ok ? 1 : 0) | ((pl->r2_ok && pl->r2_rect == 0) ? 2 : 0) | ((pl->r2_ok && pl->r2_rect != 0) ? 4 * pl->r2_rect : 0); info[7] = pl->stream_ok ? pl->chunk_rows : 0;
     return TG_OK;
 }
 
@@ -385,7 +393,8 @@ size_t tg_plan_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
     if (!pl || n_feat <= 0) return 0;
     const size_t ld = (size_t)((n_feat + 3) / 4) * 4;
     const size_t v1 = (size_t)pl->n_seg * ld * sizeof(float) + 16;
-    const size_t v2 = tg::stream_workspace_bytes(pl, n_feat);
+    size_t v2 = tg::stream_workspace_bytes(pl, n_feat);
+    if (pl->r2_ok && pl->r2_rect != 0) v2 = tg::roles2_workspace_bytes(pl, n_feat);
     return v1 > v2 ? v1 : v2;
 }
 

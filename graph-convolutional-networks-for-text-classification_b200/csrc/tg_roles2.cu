@@ -70,6 +70,8 @@ struct R2Args {
     float* partials;
     int64_t ldp;
     int32_t hub_slices, hub_lanes, doc_slices, doc_lanes, only_role;
+    int32_t table_mode;  // 1: B is only the resident table (no self loops to prefetch): X * W with X [n x <= 256]
+    int32_t n_stages;    // document-role ring depth actually used (<= kStages)
     const uint32_t* __restrict__ keep_bits;  // bit-packed dropout keep mask [n][n_feat/32] (bit b of word w = column 32w+b) or null
 };
 
@@ -208,8 +210,10 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
     // the hub rows of B (this slice) stay resident for the whole kernel
     for (int k = tid; k < a.Kh; k += kThreads)
         bulk_load_1d(smem + (size_t)k * kRowBytes, a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb + (int64_t)slice * kFT, (unsigned)slice_bytes, bhbar);
+    const int ns = a.n_stages;               // ring depth (<= kStages): smaller when the resident table is large
+    const int pf = ns > kPF ? kPF : ns - 1;  // jobs issued ahead
     auto issue = [&](int itn, int jobn) {
-        const int s = itn % kStages;
+        const int s = itn % ns;
         const int2 jd = __ldg(a.jdesc + jobn);
         unsigned char* base = ring + (size_t)s * st_bytes;
         fence_proxy_async();
@@ -218,16 +222,17 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
         bulk_load_1d(base + en_bytes, a.rdesc + (int64_t)jobn * kJobRows, (unsigned)(kJobRows * 8), &full[s]);
     };
     if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < kPF; ++i)
+        for (int i = 0; i < pf; ++i)
             if (dl + i * a.doc_lanes < a.n_jobs) issue(i, dl + i * a.doc_lanes);
+        if (!a.table_mode) {
 #pragma unroll
-        for (int i = 1; i < kL2PF; ++i)
-            if (dl + i * a.doc_lanes < a.n_jobs) tma_prefetch_l2_2d(tmap_job, slice * kFT, (dl + i * a.doc_lanes) * kJobRows);
+            for (int i = 1; i < kL2PF; ++i)
+                if (dl + i * a.doc_lanes < a.n_jobs) tma_prefetch_l2_2d(tmap_job, slice * kFT, (dl + i * a.doc_lanes) * kJobRows);
+        }
     }
     auto load_self = [&](float4(&dst)[4], int jobx) {
         const int64_t row = (int64_t)jobx * kJobRows + grp;
-        if (jobx < a.n_jobs && row < a.n) {
+        if (!a.table_mode && jobx < a.n_jobs && row < a.n) {
             const float* p = a.B + row * a.ldb + (int64_t)q0 * 4;
 #pragma unroll
             for (int u = 0; u < 4; ++u) dst[u] = valid[u] ? ldg_f4_stream(p + u * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -258,19 +263,19 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
     int it = 0;
     for (int job = dl; job < a.n_jobs; job += a.doc_lanes, ++it) {
         if (tid == 0) {
-            const int itn = it + kPF, jobn = job + kPF * a.doc_lanes;
+            const int itn = it + pf, jobn = job + pf * a.doc_lanes;
             if (jobn < a.n_jobs) {
-                // the stage was last read by iteration itn - kStages
-                if (itn >= kStages) mbar_wait(&empty[itn % kStages], (unsigned)(itn / kStages - 1) & 1u);
+                // the stage was last read by iteration itn - ns
+                if (itn >= ns) mbar_wait(&empty[itn % ns], (unsigned)(itn / ns - 1) & 1u);
                 issue(itn, jobn);
             }
             // the rows of B the self loops of a later job need: into L2 now, so that the register prefetch one job ahead
             // sees L2 latency instead of HBM latency (bytes in flight per SM, not bandwidth, were the limit)
             const int jobp = job + kL2PF * a.doc_lanes;
-            if (jobp < a.n_jobs) tma_prefetch_l2_2d(tmap_job, slice * kFT, jobp * kJobRows);
+            if (!a.table_mode && jobp < a.n_jobs) tma_prefetch_l2_2d(tmap_job, slice * kFT, jobp * kJobRows);
         }
-        const int s = it % kStages;
-        mbar_wait(&full[s], (unsigned)(it / kStages) & 1u);
+        const int s = it % ns;
+        mbar_wait(&full[s], (unsigned)(it / ns) & 1u);
         const unsigned char* base = ring + (size_t)s * st_bytes;
         const int2 rd = reinterpret_cast<const int2*>(base + en_bytes)[grp];
         const int n_tot = rd.y >> 16, n_nh = rd.y & 0xffff;
@@ -935,8 +940,8 @@ int env_int2(const char* name, int dflt) {
 size_t hub_smem(int T, int cap_hub) {
     return 2 * ((size_t)T * kRowBytes + align128((size_t)cap_hub * 8) + align128((size_t)kHtW * 4));
 }
-size_t doc_smem(int Kh, int cap_doc) {
-    return align128((size_t)Kh * kRowBytes) + (size_t)kStages * (align128((size_t)cap_doc * 8) + (size_t)kJobRows * 8);
+size_t doc_smem(int Kh, int cap_doc, int stages = kStages) {
+    return align128((size_t)Kh * kRowBytes) + (size_t)stages * (align128((size_t)cap_doc * 8) + (size_t)kJobRows * 8);
 }
 
 }  // namespace
@@ -944,10 +949,12 @@ size_t doc_smem(int Kh, int cap_doc) {
 void roles2_plan_free(tg_plan* pl) {
     if (!pl) return;
     cudaFree(pl->r2_hent); cudaFree(pl->r2_htab); cudaFree(pl->r2_cdesc); cudaFree(pl->r2_vmap); cudaFree(pl->r2_vcnt);
-    cudaFree(pl->r2_dent); cudaFree(pl->r2_rdesc); cudaFree(pl->r2_jdesc);
+    cudaFree(pl->r2_dent); cudaFree(pl->r2_rdesc); cudaFree(pl->r2_jdesc); cudaFree(pl->r2_ident);
+    pl->r2_ident = nullptr;
     pl->r2_hent = nullptr; pl->r2_htab = nullptr; pl->r2_cdesc = nullptr; pl->r2_vmap = nullptr; pl->r2_vcnt = nullptr;
     pl->r2_dent = nullptr; pl->r2_rdesc = nullptr; pl->r2_jdesc = nullptr;
     pl->r2_ok = false;
+    pl->r2_rect = 0;
 }
 
 // Builds the sub-plan of the warp-per-slot kernels on top of the streaming sub-plan (which provides colidx2 / rsplit, the
@@ -957,8 +964,11 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     (void)d_slot_of;
     pl->r2_ok = false;
     if (env_int2("TG_ROLES2", 1) == 0) return TG_OK;
-    if (!pl->stream_ok || pl->n_hub < 1 || pl->n_hub > kKv || !pl->colidx2 || !pl->rsplit) return TG_OK;
+    const bool all_hub = pl->r2_rect == 2;  // rectangular [K x N] operand whose rows are all hub rows: hub side only
+    if (pl->n_hub < 1 || pl->n_hub > kKv) return TG_OK;
+    if (!all_hub && (!pl->stream_ok || !pl->colidx2 || !pl->rsplit)) return TG_OK;
     const int64_t n = pl->n_rows;
+    const int64_t n_nodes = pl->n_cols;     // nodes the hub role streams over (= n for the square graphs)
     const int Kh = pl->n_hub;
     const int64_t hub_nnz = pl->hub_nnz;
     if (hub_nnz >= (int64_t)0x7fffffff) return TG_OK;
@@ -1033,7 +1043,7 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     // A chunk is a run of consecutive nodes with at most T rows AND at most `cap` hub entries, so that its tile of B and
     // its entries always fit one shared-memory stage: document ranges are cut by the row limit, the dense topic-topic
     // block (every hub node carries Kh entries) by the entry limit.
-    const double avg_deg = (double)hub_nnz / (double)n;
+    const double avg_deg = (double)hub_nnz / (double)n_nodes;
     static const int kTs[] = {192, 176, 160, 144, 128, 96, 64, 32};
     const int t_first = env_int2("TG_ROLES2_T", 192);
     int T = 0, cap = 0;
@@ -1051,16 +1061,16 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         roles2_plan_free(pl);
         return TG_OK;
     }
-    std::vector<int32_t> h_deg((size_t)n), node_chunk((size_t)n), cstart;
+    std::vector<int32_t> h_deg((size_t)n_nodes), node_chunk((size_t)n_nodes), cstart;
     {
         int32_t* d_deg = nullptr;
-        TG_TRY(cudaMalloc((void**)&d_deg, (size_t)n * sizeof(int32_t)));
-        e = cudaMemsetAsync(d_deg, 0, (size_t)n * sizeof(int32_t), st);
+        TG_TRY(cudaMalloc((void**)&d_deg, (size_t)n_nodes * sizeof(int32_t)));
+        e = cudaMemsetAsync(d_deg, 0, (size_t)n_nodes * sizeof(int32_t), st);
         if (e == cudaSuccess) {
             r2_hub_deg_kernel<<<Kh, 256, 0, st>>>(rowptr, colidx, pl->hub_rows, d_deg);
             e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(h_deg.data(), d_deg, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_deg.data(), d_deg, (size_t)n_nodes * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         cudaFree(d_deg);
         if (e != cudaSuccess) return fail(e, "hub degree histogram");
@@ -1068,7 +1078,7 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     {
         int rows = 0, ents = 0;
         cstart.push_back(0);
-        for (int64_t j = 0; j < n; ++j) {
+        for (int64_t j = 0; j < n_nodes; ++j) {
             const int d = h_deg[(size_t)j];
             if (rows > 0 && (rows == T || ents + d > cap - 2)) {  // -2: the staged run starts at an even entry and has even length
                 cstart.push_back((int32_t)j);
@@ -1081,7 +1091,7 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         }
     }
     const int n_chunks = (int)cstart.size();
-    cstart.push_back((int32_t)n);
+    cstart.push_back((int32_t)n_nodes);
     if ((uint64_t)n_chunks * (uint64_t)kKv >= 0xFFFFFFFFull) {
         release_tmp();
         roles2_plan_free(pl);
@@ -1091,9 +1101,9 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         int32_t *d_node_chunk = nullptr, *d_cstart = nullptr;
         auto drop = [&]() { cudaFree(d_node_chunk); cudaFree(d_cstart); };
 #define TG_TRY2(call) do { e = (call); if (e != cudaSuccess) { drop(); return fail(e, #call); } } while (0)
-        TG_TRY2(cudaMalloc((void**)&d_node_chunk, (size_t)n * sizeof(int32_t)));
+        TG_TRY2(cudaMalloc((void**)&d_node_chunk, (size_t)n_nodes * sizeof(int32_t)));
         TG_TRY2(cudaMalloc((void**)&d_cstart, (size_t)(n_chunks + 1) * sizeof(int32_t)));
-        TG_TRY2(cudaMemcpyAsync(d_node_chunk, node_chunk.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        TG_TRY2(cudaMemcpyAsync(d_node_chunk, node_chunk.data(), (size_t)n_nodes * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         TG_TRY2(cudaMemcpyAsync(d_cstart, cstart.data(), (size_t)(n_chunks + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         r2_hub_keys_kernel<<<Kh, 256, 0, st>>>(rowptr, colidx, pl->hub_rows, d_ofs, d_node_chunk, pl->r2_vmap, pl->r2_vcnt, keys_a, src_a);
         TG_TRY2(cudaGetLastError());
@@ -1121,6 +1131,12 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         pl->r2_T = T;
         pl->r2_n_chunks = n_chunks;
         pl->r2_cap_hub = cap;
+    }
+
+    if (all_hub) {  // no short rows: the hub side is the whole plan
+        release_tmp();
+        pl->r2_ok = true;
+        return TG_OK;
     }
 
     // ---- document side: compact entry copy, row descriptors, job descriptors --------------------------------------------------
@@ -1163,7 +1179,7 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
 }
 
 bool roles2_applicable(const tg_plan* pl, const StreamCall& c) {
-    if (!pl || !pl->r2_ok) return false;
+    if (!pl || !pl->r2_ok || pl->r2_rect != 0) return false;
     if (env_int2("TG_ROLES2", 1) == 0) return false;
     if (c.n_feat < 64 || c.n_feat % 4 != 0 || c.n_feat > 1024) return false;
     // below ~16 K rows a launch is a few microseconds of work and the 148-CTA prologue (resident hub rows, barriers, TMA
@@ -1175,6 +1191,8 @@ bool roles2_applicable(const tg_plan* pl, const StreamCall& c) {
 
 size_t roles2_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
     if (!pl || !pl->r2_ok) return 0;
+    if (pl->r2_rect == 1) return 16;
+    if (pl->r2_rect == 2) return (size_t)kNumSM * kKv * ((size_t)((n_feat + 3) / 4) * 4) * sizeof(float) + 16;
     const size_t ld = (size_t)((n_feat + 3) / 4) * 4;
     // per-CTA hub partials + the bit-packed dropout keep mask (n x n_feat / 8 bytes)
     return (size_t)kNumSM * kKv * ld * sizeof(float) + 16 + (size_t)pl->n_rows * (((ld + kFT - 1) / kFT) * 16) + 256;
@@ -1196,6 +1214,8 @@ int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cuda
     // element) instead of inside the document role, whose CTAs have no issue slots to spare (ncu: the in-kernel RNG
     // cost 0.4 ms at 1M x 256).  Same mask, bit for bit, as the in-kernel definition (tg_common.cuh).
     a.keep_bits = nullptr;
+    a.table_mode = 0;
+    a.n_stages = kStages;
     if (epi.drop_mode == 1 && env_int2("TG_ROLES2_BITMASK", 1) != 0) {
         const size_t part_bytes = ((size_t)kNumSM * kKv * a.ldp * sizeof(float) + 16 + 255) & ~(size_t)255;
         const size_t mask_bytes = (size_t)pl->n_rows * (size_t)slices * 16;  // four words per row and 128-column slice
@@ -1270,7 +1290,7 @@ static void narrow_smem(const tg_plan* pl, int n_feat, size_t* hub_s, size_t* do
 }
 
 bool roles2_narrow_applicable(const tg_plan* pl, const StreamCall& c) {
-    if (!pl || !pl->r2_ok) return false;
+    if (!pl || !pl->r2_ok || pl->r2_rect != 0) return false;
     if (env_int2("TG_ROLES2", 1) == 0 || env_int2("TG_ROLES2_NARROW", 1) == 0) return false;
     if (c.n_feat < 4 || c.n_feat > 32 || c.n_feat % 4 != 0) return false;
     // a narrow operand of a small graph is L2 resident and the gather kernel is faster (20NG shape: 0.033 vs 0.052 ms)
@@ -1294,6 +1314,8 @@ static int roles2_narrow_run_t(const tg_plan* pl, const StreamCall& c, const Epi
     a.ldp = (int64_t)((c.n_feat + 3) / 4) * 4;
     a.hub_slices = a.doc_slices = 1;
     a.keep_bits = nullptr;
+    a.table_mode = 0;
+    a.n_stages = kStages;
     const int hub_pct = env_int2("TG_ROLES2_NARROW_HUB_PCT", 52);
     int hub_lanes = kNumSM * hub_pct / 100;
     if (hub_lanes < 1) hub_lanes = 1;
@@ -1341,6 +1363,172 @@ int roles2_narrow_run(const tg_plan* pl, const StreamCall& c, const EpiStore& ep
 }
 int roles2_narrow_run(const tg_plan* pl, const StreamCall& c, const EpiLoss& epi, cudaStream_t st) {
     return roles2_narrow_run_t(pl, c, epi, st);
+}
+
+// ---- rectangular operands ---------------------------------------------------------------------------------------------------
+// table mode: every entry of a row addresses the resident table (rows of B = the dense weight): {column * 512, value}
+__global__ void r2_table_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                     const int32_t* __restrict__ start, int64_t n, int64_t n_pad, int2* __restrict__ dent2,
+                                     int2* __restrict__ rdesc, int2* __restrict__ jdesc) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    const int64_t j0 = r / kJobRows * kJobRows;
+    const int jbase = start[j0] & ~1;
+    int2 rd = make_int2(0, 0);
+    if (r < n) {
+        const int s = rowptr[r], len = rowptr[r + 1] - s;
+        if (len > 0) {
+            const int o = start[r];
+            for (int p = 0; p < len; ++p) dent2[o + p] = make_int2(colidx[s + p] * kRowBytes, __float_as_int(vals[s + p]));
+            rd = make_int2(o - jbase, len << 16);
+        }
+    }
+    rdesc[r] = rd;
+    if (r == j0) {
+        const int64_t j1 = (j0 + kJobRows < n_pad) ? j0 + kJobRows : n_pad;
+        jdesc[r / kJobRows] = make_int2(jbase, ((start[j1] - jbase) + 1) & ~1);
+    }
+}
+
+__global__ void r2_iota_kernel(int32_t* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+
+// Sub-plans for the two products of a sparse feature matrix X [n x nfeat], nfeat <= 256 (reference layer.py:102 with the
+// topic features of trainer.py:197-238, and its autograd transpose product):
+//   X * W      (plan of X):   every column's row of W is resident in shared memory -> the document role alone;
+//   X^T * dS   (plan of X^T): every row is a hub row                               -> the hub role alone + finish.
+int roles2_rect_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx, const float* vals, const int32_t* h_rowptr,
+                           cudaStream_t st) {
+    if (pl->r2_ok || env_int2("TG_ROLES2", 1) == 0 || env_int2("TG_ROLES2_RECT", 1) == 0) return TG_OK;
+    if (!colidx || !vals || pl->nnz == 0 || pl->nnz >= (int64_t)0x7fffffff) return TG_OK;
+    const int64_t min_rows = env_int2("TG_ROLES2_MIN_ROWS", 16384);
+    if (pl->n_rows <= kKv && pl->n_hub == pl->n_rows && pl->n_cols >= min_rows && pl->n_cols > pl->n_rows) {
+        // ---- all-hub mode: the hub side of the square plan, over the columns of this matrix ----
+        std::vector<int32_t> hub_rows((size_t)pl->n_rows);
+        for (int64_t i = 0; i < pl->n_rows; ++i) hub_rows[(size_t)i] = (int32_t)i;
+        pl->r2_rect = 2;
+        const int rc = roles2_plan_build(pl, rowptr, colidx, vals, h_rowptr, nullptr, hub_rows.data(), st);
+        if (rc != TG_OK || !pl->r2_ok) pl->r2_rect = 0;
+        return rc;
+    }
+    if (pl->n_cols <= kKv && pl->n_hub == 0 && pl->n_rows >= min_rows && pl->n_rows > pl->n_cols) {
+        // ---- table mode: compact entries + row / job descriptors, the ring depth that fits next to the table ----
+        const int64_t n = pl->n_rows;
+        const int64_t n_jobs = ceil_div64(n, kJobRows), n_pad = n_jobs * kJobRows;
+        int32_t *d_len = nullptr, *d_start = nullptr;
+        void* tmp = nullptr;
+        cudaError_t e = cudaSuccess;
+        auto fail = [&](cudaError_t err, const char* what) {
+            cudaFree(d_len); cudaFree(d_start); cudaFree(tmp);
+            roles2_plan_free(pl);
+            return cuda_fail(err, what, __FILE__, __LINE__);
+        };
+#define TG_TRY(call) do { e = (call); if (e != cudaSuccess) return fail(e, #call); } while (0)
+        TG_TRY(cudaMalloc((void**)&d_len, (size_t)(n_pad + 1) * sizeof(int32_t)));
+        TG_TRY(cudaMalloc((void**)&d_start, (size_t)(n_pad + 1) * sizeof(int32_t)));
+        r2_row_len_kernel<<<(unsigned)ceil_div64(n_pad + 1, 256), 256, 0, st>>>(rowptr, n, n_pad, 0x7fffffff, d_len);
+        TG_TRY(cudaGetLastError());
+        size_t scan_bytes = 0;
+        TG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_len, d_start, (int)(n_pad + 1), st));
+        TG_TRY(cudaMalloc(&tmp, scan_bytes ? scan_bytes : 1));
+        TG_TRY(cub::DeviceScan::ExclusiveSum(tmp, scan_bytes, d_len, d_start, (int)(n_pad + 1), st));
+        TG_TRY(cudaMalloc((void**)&pl->r2_dent, ((size_t)pl->nnz + 2) * sizeof(int2)));
+        TG_TRY(cudaMemsetAsync(pl->r2_dent, 0, ((size_t)pl->nnz + 2) * sizeof(int2), st));
+        TG_TRY(cudaMalloc((void**)&pl->r2_rdesc, (size_t)n_pad * sizeof(int2)));
+        TG_TRY(cudaMalloc((void**)&pl->r2_jdesc, (size_t)(n_jobs + 8) * sizeof(int2)));
+        TG_TRY(cudaMemsetAsync(pl->r2_jdesc, 0, (size_t)(n_jobs + 8) * sizeof(int2), st));
+        r2_table_fill_kernel<<<(unsigned)ceil_div64(n_pad, 256), 256, 0, st>>>(rowptr, colidx, vals, d_start, n, n_pad, pl->r2_dent,
+                                                                               pl->r2_rdesc, pl->r2_jdesc);
+        TG_TRY(cudaGetLastError());
+        TG_TRY(cudaMalloc((void**)&pl->r2_ident, (size_t)pl->n_cols * sizeof(int32_t)));
+        r2_iota_kernel<<<(unsigned)ceil_div64(pl->n_cols, 256), 256, 0, st>>>(pl->r2_ident, (int)pl->n_cols);
+        TG_TRY(cudaGetLastError());
+        std::vector<int2> h_jdesc((size_t)n_jobs);
+        TG_TRY(cudaMemcpyAsync(h_jdesc.data(), pl->r2_jdesc, (size_t)n_jobs * sizeof(int2), cudaMemcpyDeviceToHost, st));
+        TG_TRY(cudaStreamSynchronize(st));
+#undef TG_TRY
+        cudaFree(d_len); cudaFree(d_start); cudaFree(tmp);
+        int cap_doc = 2;
+        for (const int2& d : h_jdesc) cap_doc = std::max(cap_doc, d.y);
+        pl->r2_n_jobs = (int32_t)n_jobs;
+        pl->r2_cap_doc = cap_doc;
+        int stages = 0;
+        for (int sgs = kStages; sgs >= 2; --sgs)
+            if (doc_smem((int)pl->n_cols, cap_doc, sgs) + 256 <= kSmemMax) { stages = sgs; break; }
+        if (stages == 0) {
+            roles2_plan_free(pl);
+            return TG_OK;
+        }
+        pl->r2_stages = stages;
+        pl->r2_rect = 1;
+        pl->r2_ok = true;
+    }
+    return TG_OK;
+}
+
+bool roles2_rect_applicable(const tg_plan* pl, const StreamCall& c) {
+    if (!pl || !pl->r2_ok || pl->r2_rect == 0) return false;
+    if (env_int2("TG_ROLES2", 1) == 0 || env_int2("TG_ROLES2_RECT", 1) == 0) return false;
+    if (c.n_feat < 64 || c.n_feat % 4 != 0 || c.n_feat > 1024) return false;
+    if (c.ldb % 4 != 0 || !aligned16(c.B) || !encode_tiled_fn()) return false;
+    return true;
+}
+
+int roles2_rect_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st) {
+    R2Args a;
+    memset(&a, 0, sizeof(a));
+    a.B = c.B; a.ldb = c.ldb; a.n = pl->n_rows; a.n_chunks4 = c.n_feat / 4;
+    a.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(c.workspace) + 15u) & ~(uintptr_t)15u);
+    a.ldp = (int64_t)((c.n_feat + 3) / 4) * 4;
+    const int slices = (c.n_feat + kFT - 1) / kFT;
+    a.hub_slices = a.doc_slices = slices;
+    a.keep_bits = nullptr;
+    a.only_role = 0;
+    CUtensorMap tmap, tmap_job;
+    memset(&tmap, 0, sizeof(tmap));
+    memset(&tmap_job, 0, sizeof(tmap_job));
+    if (pl->r2_rect == 1) {
+        // X * W: the rows of W (c.B, n_cols of them) are the resident table; all CTAs run the document role
+        a.dent = pl->r2_dent; a.rdesc = pl->r2_rdesc; a.jdesc = pl->r2_jdesc;
+        a.n_jobs = pl->r2_n_jobs; a.cap_doc = pl->r2_cap_doc;
+        a.hub_rows = pl->r2_ident; a.Kh = (int32_t)pl->n_cols;
+        a.table_mode = 1;
+        a.n_stages = pl->r2_stages;
+        a.hub_lanes = 0;
+        int doc_lanes = kNumSM / slices;
+        if (doc_lanes < 1) doc_lanes = 1;
+        if (doc_lanes > a.n_jobs) doc_lanes = a.n_jobs;
+        a.doc_lanes = doc_lanes;
+        const size_t smem = doc_smem(a.Kh, a.cap_doc, a.n_stages) + 128;
+        TG_CUDA(cudaFuncSetAttribute(roles2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roles2_kernel<<<(unsigned)(doc_lanes * slices), kThreads, smem, st>>>(a, epi, tmap, tmap_job);
+        TG_LAUNCH_CHECK();
+        return TG_OK;
+    }
+    // X^T * dS: every row of this matrix is a hub row; all CTAs run the hub role over the rows of c.B, then the finish
+    a.hent = pl->r2_hent; a.htab = pl->r2_htab; a.cdesc = pl->r2_cdesc;
+    a.T = pl->r2_T; a.n_chunks = pl->r2_n_chunks; a.cap_hub = pl->r2_cap_hub;
+    a.hub_rows = pl->hub_rows; a.Kh = pl->n_hub;
+    a.table_mode = 0;
+    a.n_stages = kStages;
+    a.doc_lanes = 0;
+    int hub_lanes = kNumSM / slices;
+    if (hub_lanes < 1) hub_lanes = 1;
+    if (hub_lanes > a.n_chunks) hub_lanes = a.n_chunks;
+    a.hub_lanes = hub_lanes;
+    const size_t need = (size_t)hub_lanes * kKv * a.ldp * sizeof(float);
+    TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
+               c.workspace_bytes, need + 16);
+    TG_REQUIRE(make_tensor_map(&tmap, a.B, pl->n_cols, c.n_feat, a.ldb, a.T, kFT), TG_ERR_UNSUPPORTED,
+               "cuTensorMapEncodeTiled failed (TMA tile of the dense operand)");
+    const size_t smem = hub_smem(a.T, a.cap_hub) + 128;
+    TG_CUDA(cudaFuncSetAttribute(roles2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roles2_kernel<<<(unsigned)(hub_lanes * slices), kThreads, smem, st>>>(a, epi, tmap, tmap_job);
+    TG_LAUNCH_CHECK();
+    FinishArgs f{a.partials, a.ldp, hub_lanes, a.Kh, kKv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
+    return finish_run(f, epi, st);
 }
 
 }  // namespace tg

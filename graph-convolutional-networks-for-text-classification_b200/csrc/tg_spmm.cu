@@ -16,6 +16,8 @@
 //     fixed by the plan, so results are bitwise reproducible run to run.
 // Hub segments occupy the first blocks of the grid so the long work starts first.
 #include "tg_epilogue.cuh"
+#include <type_traits>
+
 #include "tg_stream.cuh"
 
 namespace tg {
@@ -301,6 +303,10 @@ static int run_spmm(const tg_plan* pl, const int32_t* rowptr, const int32_t* col
     {
         // column-chunk streaming kernel (tg_stream.cu) when the plan carries the sub-plan and the operands qualify
         StreamCall sc{rowptr, vals, B, ldb, n_feat, workspace, workspace_bytes};
+        if constexpr (std::is_same<Epi, EpiStore>::value) {
+            // rectangular operands (sparse feature matrix x weight, and the transpose product): one role of tg_roles2.cu
+            if (out_vec4_ok && roles2_rect_applicable(pl, sc)) return roles2_rect_run(pl, sc, epi, st);
+        }
         if (stream_applicable(pl, sc, out_vec4_ok, EpiTraits<Epi>::whole_row)) return stream_dispatch(pl, sc, epi, st);
     }
     SpmmArgs a;

@@ -32,6 +32,11 @@ void roles2_plan_free(tg_plan* pl);
 bool roles2_applicable(const tg_plan* pl, const StreamCall& c);
 size_t roles2_workspace_bytes(const tg_plan* pl, int32_t n_feat);
 int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st);
+// rectangular operands: sparse feature matrix times dense weight (document role only) and its transpose product (hub role only)
+int roles2_rect_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx, const float* vals, const int32_t* h_rowptr,
+                           cudaStream_t st);
+bool roles2_rect_applicable(const tg_plan* pl, const StreamCall& c);
+int roles2_rect_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st);
 bool roles2_narrow_applicable(const tg_plan* pl, const StreamCall& c);   // n_feat <= 32 (class-sized operands)
 int roles2_narrow_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st);
 int roles2_narrow_run(const tg_plan* pl, const StreamCall& c, const EpiLoss& epi, cudaStream_t st);

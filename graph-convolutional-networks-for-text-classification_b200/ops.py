@@ -72,6 +72,9 @@ def _spmm_launches(csr, n_feat: int, philox: bool = False) -> int:
     """Kernels one SpMM-type call launches: the product itself, the finishing kernel of the streaming paths (hub rows =
     fixed-order sum of the per-CTA partials + epilogue) and, for Philox dropout on the warp-per-slot path, the kernel
     that draws the bit-packed keep mask."""
+    rect = int(getattr(csr, "roles2_rect", 0))
+    if rect and 64 <= n_feat <= 1024 and n_feat % 4 == 0 and os.environ.get("TG_ROLES2_RECT", "1") != "0":
+        return rect  # resident-table product: one kernel; all-hub product: hub role + finish
     path = roles2_path(csr, n_feat)
     streamed = bool(getattr(csr, "streaming", False)) and (n_feat > 32 or path == "narrow")
     return 1 + int(streamed) + int(philox and path == "wide")

@@ -88,7 +88,8 @@ int tg_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* va
                    int32_t segment_nnz /*<=0: default*/, tg_plan** plan_out, void* stream);
 void tg_plan_destroy(tg_plan* plan);
 /* info: [0]=n_hub_rows [1]=n_segments [2]=hub_nnz [3]=max_row_nnz [4]=hub_threshold [5]=segment_nnz
- *       [6]=bit 0: streaming layout present, bit 1: warp-per-slot role kernels available (hub rows <= 256)
+ *       [6]=bit 0: streaming layout present, bit 1: warp-per-slot role kernels available (hub rows <= 256),
+ *           bits 2-3: rectangular sub-plan (1 = resident-table product X*W, 2 = all-hub product X^T*dS)
  *       [7]=nodes per chunk */
 int tg_plan_info(const tg_plan* plan, int64_t info_host[8]);
 /* bytes of scratch a tg_spmm* / tg_gc* call with `n_feat` columns needs (partials of split hub rows) */

@@ -714,3 +714,33 @@ def test_edge_list_ingest_on_device(tg):
     params = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
     want, _ = O.gcn_forward(None, coo, params, training=False)
     assert rel_err(logits, want) <= 2e-5
+
+
+@pytest.mark.parametrize("n_rows,n_feat_in,H,row_nnz", [(20000, 100, 256, 40), (17000, 256, 200, 12), (30000, 37, 128, 37)])
+def test_rectangular_products_of_a_sparse_feature_matrix(tg, monkeypatch, n_rows, n_feat_in, H, row_nnz):
+    """The two products of the reference's real feature mode (X sparse [n x nfeat <= 256], trainer.py:197-238):
+    X @ W through the resident-table plan (document role only) and X^T @ dS through the all-hub plan (hub role only),
+    against the oracle; deterministic; the gather kernel (TG_ROLES2_RECT=0) agrees."""
+    gen = torch.Generator(device="cuda:0").manual_seed(n_rows)
+    cols = torch.rand(n_rows, n_feat_in, device=dev(), generator=gen).topk(row_nnz, dim=1).indices.sort(dim=1).values
+    vals = torch.randn(n_rows, row_nnz, device=dev(), generator=gen)
+    rows = torch.arange(n_rows, device=dev()).unsqueeze(1).expand(-1, row_nnz)
+    r, c, v = rows.reshape(-1), cols.reshape(-1), vals.reshape(-1)
+    X = tg.DeviceCSR.from_coo(r, c, v, n_rows, n_feat_in)
+    assert X.roles2_rect == 1
+    XT = X.transpose()
+    assert XT.roles2_rect == 2
+    W = torch.randn(n_feat_in, H, device=dev(), generator=gen)
+    dS = torch.randn(n_rows, H, device=dev(), generator=gen)
+    coo = O.Coo(r.cpu().numpy(), c.cpu().numpy(), v.cpu().numpy(), (n_rows, n_feat_in))
+    y, g = tg.spmm(X, W), tg.spmm(XT, dS)
+    assert rel_err(y.cpu().numpy(), O.spmm(coo, W.cpu().numpy())) <= SPMM_RTOL
+    ref_g, ref_g64 = O.spmm(coo.transpose(), dS.cpu().numpy()), O.spmm_f64(coo.transpose(), dS.cpu().numpy())
+    assert rel_err(g.cpu().numpy(), ref_g64) <= rel_err(ref_g, ref_g64) + 2e-7   # long rows: not worse than the reference's sum
+    assert rel_err(g.cpu().numpy(), ref_g) <= 2e-5
+    assert torch.equal(y, tg.spmm(X, W)) and torch.equal(g, tg.spmm(XT, dS))
+    monkeypatch.setenv("TG_ROLES2_RECT", "0")
+    y0, g0 = tg.spmm(X, W), tg.spmm(XT, dS)
+    monkeypatch.delenv("TG_ROLES2_RECT")
+    assert float((y0 - y).abs().max() / y.abs().max()) <= SPMM_RTOL
+    assert float((g0 - g).abs().max() / g.abs().max()) <= 2e-5
