@@ -178,6 +178,7 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
 }
 
 // =============================================== document role ===========================================================
+template <bool TABLE>
 __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, const CUtensorMap* tmap_job, unsigned char* smem,
                                          uint64_t* bars, int bid) {
     const int tid = threadIdx.x, lane = tid & 31, gl = lane & 7, grp = tid >> 3;
@@ -210,8 +211,10 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
     // the hub rows of B (this slice) stay resident for the whole kernel
     for (int k = tid; k < a.Kh; k += kThreads)
         bulk_load_1d(smem + (size_t)k * kRowBytes, a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb + (int64_t)slice * kFT, (unsigned)slice_bytes, bhbar);
-    const int ns = a.n_stages;               // ring depth (<= kStages): smaller when the resident table is large
-    const int pf = ns > kPF ? kPF : ns - 1;  // jobs issued ahead
+    // ring depth and look-ahead: compile-time constants on the graph path, run-time (smaller when the resident table is
+    // large) for the resident-table product of a rectangular operand
+    const int ns = TABLE ? a.n_stages : kStages;
+    const int pf = TABLE ? (ns > kPF ? kPF : ns - 1) : kPF;
     auto issue = [&](int itn, int jobn) {
         const int s = itn % ns;
         const int2 jd = __ldg(a.jdesc + jobn);
@@ -224,7 +227,7 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
     if (tid == 0) {
         for (int i = 0; i < pf; ++i)
             if (dl + i * a.doc_lanes < a.n_jobs) issue(i, dl + i * a.doc_lanes);
-        if (!a.table_mode) {
+        if (!TABLE) {
 #pragma unroll
             for (int i = 1; i < kL2PF; ++i)
                 if (dl + i * a.doc_lanes < a.n_jobs) tma_prefetch_l2_2d(tmap_job, slice * kFT, (dl + i * a.doc_lanes) * kJobRows);
@@ -232,7 +235,7 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
     }
     auto load_self = [&](float4(&dst)[4], int jobx) {
         const int64_t row = (int64_t)jobx * kJobRows + grp;
-        if (!a.table_mode && jobx < a.n_jobs && row < a.n) {
+        if (!TABLE && jobx < a.n_jobs && row < a.n) {
             const float* p = a.B + row * a.ldb + (int64_t)q0 * 4;
 #pragma unroll
             for (int u = 0; u < 4; ++u) dst[u] = valid[u] ? ldg_f4_stream(p + u * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -272,7 +275,7 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
             // the rows of B the self loops of a later job need: into L2 now, so that the register prefetch one job ahead
             // sees L2 latency instead of HBM latency (bytes in flight per SM, not bandwidth, were the limit)
             const int jobp = job + kL2PF * a.doc_lanes;
-            if (!a.table_mode && jobp < a.n_jobs) tma_prefetch_l2_2d(tmap_job, slice * kFT, jobp * kJobRows);
+            if (!TABLE && jobp < a.n_jobs) tma_prefetch_l2_2d(tmap_job, slice * kFT, jobp * kJobRows);
         }
         const int s = it % ns;
         mbar_wait(&full[s], (unsigned)(it / ns) & 1u);
@@ -431,6 +434,7 @@ __global__ void __launch_bounds__(256) r2_keep_bits_half_kernel(uint32_t* __rest
     }
 }
 
+template <bool TABLE>
 __global__ void __launch_bounds__(kThreads, 1) roles2_kernel(const R2Args a, const EpiStore epi, const __grid_constant__ CUtensorMap tmapB,
                                                             const __grid_constant__ CUtensorMap tmapJob) {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) roles2_kernel(const R2Args a, con
         hub_role(a, &tmapB, smem, bars, bid);
     } else {
         if (a.only_role == 1) return;
-        doc_role(a, epi, &tmapJob, smem, bars, bid - n_hub_ctas);
+        doc_role<TABLE>(a, epi, &tmapJob, smem, bars, bid - n_hub_ctas);
     }
 }
 
@@ -1273,9 +1277,9 @@ int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cuda
     TG_REQUIRE(make_tensor_map(&tmap_job, a.B, a.n, c.n_feat, a.ldb, kJobRows, kFT), TG_ERR_UNSUPPORTED,
                "cuTensorMapEncodeTiled failed (L2 prefetch tile of the dense operand)");
     size_t smem = std::max(hub_smem(a.T, a.cap_hub), doc_smem(a.Kh, a.cap_doc)) + 128;
-    TG_CUDA(cudaFuncSetAttribute(roles2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TG_CUDA(cudaFuncSetAttribute(roles2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((hub_lanes + doc_lanes) * slices);
-    roles2_kernel<<<grid, kThreads, smem, st>>>(a, epi, tmap, tmap_job);
+    roles2_kernel<false><<<grid, kThreads, smem, st>>>(a, epi, tmap, tmap_job);
     TG_LAUNCH_CHECK();
     FinishArgs f{a.partials, a.ldp, hub_lanes, a.Kh, kKv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
     return finish_run(f, epi, st);
@@ -1502,8 +1506,8 @@ int roles2_rect_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi,
         if (doc_lanes > a.n_jobs) doc_lanes = a.n_jobs;
         a.doc_lanes = doc_lanes;
         const size_t smem = doc_smem(a.Kh, a.cap_doc, a.n_stages) + 128;
-        TG_CUDA(cudaFuncSetAttribute(roles2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        roles2_kernel<<<(unsigned)(doc_lanes * slices), kThreads, smem, st>>>(a, epi, tmap, tmap_job);
+        TG_CUDA(cudaFuncSetAttribute(roles2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roles2_kernel<true><<<(unsigned)(doc_lanes * slices), kThreads, smem, st>>>(a, epi, tmap, tmap_job);
         TG_LAUNCH_CHECK();
         return TG_OK;
     }
@@ -1524,8 +1528,8 @@ int roles2_rect_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi,
     TG_REQUIRE(make_tensor_map(&tmap, a.B, pl->n_cols, c.n_feat, a.ldb, a.T, kFT), TG_ERR_UNSUPPORTED,
                "cuTensorMapEncodeTiled failed (TMA tile of the dense operand)");
     const size_t smem = hub_smem(a.T, a.cap_hub) + 128;
-    TG_CUDA(cudaFuncSetAttribute(roles2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    roles2_kernel<<<(unsigned)(hub_lanes * slices), kThreads, smem, st>>>(a, epi, tmap, tmap_job);
+    TG_CUDA(cudaFuncSetAttribute(roles2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roles2_kernel<false><<<(unsigned)(hub_lanes * slices), kThreads, smem, st>>>(a, epi, tmap, tmap_job);
     TG_LAUNCH_CHECK();
     FinishArgs f{a.partials, a.ldp, hub_lanes, a.Kh, kKv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
     return finish_run(f, epi, st);
