@@ -694,9 +694,9 @@ __global__ void __launch_bounds__(kThreads, 1) roles2n_kernel(const R2Args a, co
 
 // Lane-per-row document role for narrow operands whose rows lie back to back (ldb == n_feat): a row is NV float4 chunks
 // held by ONE lane, so a warp covers 32 rows per instruction instead of 4 and the per-entry bookkeeping is amortised over
-// the whole row (ncu on the group-per-row variant: 106 M warp instructions for 16 M entries at F = 20).  A stage carries a
-// "super job" of 8 consecutive jobs (512 rows, one per thread): their entries (one contiguous run), row descriptors,
-// job descriptors and the 512 rows of B for the self loops, as four bulk copies; two stages.
+// the whole row (ncu on the group-per-row variant: 106 M warp instructions for 16 M entries at F = 20).  The CTA is cut
+// into eight teams of two warps; a team owns a job sequence of its own (64 rows per job, one per lane) and a two-stage
+// ring that brings a job's entries, row descriptors and the 64 rows of B for the self loops as three bulk copies.
 constexpr int kTeams = 8;       // lane-per-row document role: teams of two warps, one job (64 rows) per team and stage
 constexpr int kTeamStages = 2;
 template <int NV, class Epi>
