@@ -1320,7 +1320,7 @@ static int roles2_narrow_run_t(const tg_plan* pl, const StreamCall& c, const Epi
     a.keep_bits = nullptr;
     a.table_mode = 0;
     a.n_stages = kStages;
-    const int hub_pct = env_int2("TG_ROLES2_NARROW_HUB_PCT", 52);
+    const int hub_pct = env_int2("TG_ROLES2_NARROW_HUB_PCT", 57);
     int hub_lanes = kNumSM * hub_pct / 100;
     if (hub_lanes < 1) hub_lanes = 1;
     if (hub_lanes > a.n_chunks) hub_lanes = a.n_chunks;
