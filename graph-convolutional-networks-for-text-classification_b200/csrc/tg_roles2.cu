@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "tg_async.cuh"
@@ -1320,7 +1321,9 @@ static int roles2_narrow_run_t(const tg_plan* pl, const StreamCall& c, const Epi
     a.keep_bits = nullptr;
     a.table_mode = 0;
     a.n_stages = kStages;
-    const int hub_pct = env_int2("TG_ROLES2_NARROW_HUB_PCT", 57);
+    // measured balance points at C3, F = 20: 57 % hub CTAs for the plain product, 52 % when the document role also runs the
+    // log-softmax / cross-entropy epilogue
+    const int hub_pct = env_int2("TG_ROLES2_NARROW_HUB_PCT", std::is_same<Epi, EpiLoss>::value ? 52 : 57);
     int hub_lanes = kNumSM * hub_pct / 100;
     if (hub_lanes < 1) hub_lanes = 1;
     if (hub_lanes > a.n_chunks) hub_lanes = a.n_chunks;
