@@ -168,8 +168,10 @@ __global__ void __launch_bounds__(kMmaWarps * 32) dense_nn_mma_kernel(const floa
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int64_t row0 = ((int64_t)blockIdx.x * kMmaWarps + warp) * kMmaRowsPerWarp;
-    if (row0 >= n) return;
+    // persistent CTAs: W hi/lo are split and staged once per CTA, then the CTA walks its row blocks
+    for (int64_t blk = blockIdx.x; blk * (kMmaWarps * kMmaRowsPerWarp) < n; blk += gridDim.x) {
+    const int64_t row0 = (blk * kMmaWarps + warp) * kMmaRowsPerWarp;
+    if (row0 >= n) continue;
     // rows of the two m16 tiles this lane touches: row0 + {g, g+8, g+16, g+24}
     const float* ap[4];
     bool ok[4];
@@ -255,6 +257,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) dense_nn_mma_kernel(const floa
                 if (col + 1 < c) C[row * ldc + col + 1] = acc[m][j][2 * hh + 1];
             }
         }
+    }  // row blocks of this CTA
 }
 
 static size_t dense_mma_smem(int h) { return (size_t)2 * ((h + 15) & ~15) * kMmaWS * sizeof(float); }
@@ -263,8 +266,9 @@ static int launch_dense_nn_mma(const float* A, int64_t lda, const float* W, int6
                                int h, int c, cudaStream_t st) {
     const size_t smem = dense_mma_smem(h);
     TG_CUDA(cudaFuncSetAttribute(dense_nn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)ceil_div64(n, kMmaWarps * kMmaRowsPerWarp);
-    dense_nn_mma_kernel<<<grid, kMmaWarps * 32, smem, st>>>(A, lda, W, ldw, C, ldc, n, h, c);
+    int64_t grid = ceil_div64(n, kMmaWarps * kMmaRowsPerWarp);
+    if (grid > 2 * kNumSM) grid = 2 * kNumSM;  // two CTAs per SM (registers), each staging W once
+    dense_nn_mma_kernel<<<(unsigned)grid, kMmaWarps * 32, smem, st>>>(A, lda, W, ldw, C, ldc, n, h, c);
     TG_LAUNCH_CHECK();
     return TG_OK;
 }
