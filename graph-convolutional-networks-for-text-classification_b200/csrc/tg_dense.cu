@@ -456,9 +456,9 @@ __global__ void __launch_bounds__(TB, (TB == 256 ? 2 : 1)) hidden_bwd_kernel(con
 // (row, unit) pair are issued as 20 FFMA2 — zeros of H1 cost arithmetic again, but the FMA pipe has room for it now that
 // one instruction carries two of them.  Same summation order per element as the sparse kernel (zeros add exactly 0).
 constexpr int kHdTile = 64;   // rows of dS2 per staged tile
-constexpr int kHdBatch = 8;   // rows whose H1 values a thread holds in flight
+constexpr int kHdBatch = 16;  // rows whose H1 values a thread holds in flight
 template <int NC4>
-__global__ void __launch_bounds__(256, 3) hidden_bwd_dense_kernel(const float* __restrict__ H1, int64_t ldh,
+__global__ void __launch_bounds__(256, 2) hidden_bwd_dense_kernel(const float* __restrict__ H1, int64_t ldh,
                                                                   const float* __restrict__ dS2, int64_t ldd,
                                                                   const float* __restrict__ W2, int64_t ldw, float scale,
                                                                   float* __restrict__ dZ1, int64_t ldz,
@@ -605,7 +605,7 @@ static int launch_hidden_bwd(const float* H1, int64_t ldh, const float* dS2, int
                              int h, int c, cudaStream_t st) {
     if (h <= 256 && dense_hidden_enabled()) {
         // dense FFMA2 kernel: three CTAs of 256 threads per SM
-        int64_t grid = 3 * kNumSM;
+        int64_t grid = 2 * kNumSM;
         int64_t rpb = ceil_div64(n > 0 ? n : 1, grid);
         rpb = ceil_div64(rpb, kHdTile) * kHdTile;
         grid = ceil_div64(n > 0 ? n : 1, rpb);
