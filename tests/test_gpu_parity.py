@@ -485,7 +485,7 @@ def test_captured_train_step_matches_eager(tg, small_golden):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# warp-per-slot role kernels (tg_roles2.cu): F % 128 == 0, <= 256 hub rows
+# warp-per-slot role kernels (tg_roles2.cu): 64 <= F <= 1024 (wide) or F <= 32 (narrow), <= 256 hub rows
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n_docs,n_topics,F,thr", [(3000, 64, 128, 64), (9000, 256, 256, 48), (777, 37, 384, 24),
                                                     (20000, 100, 256, 256), (5000, 50, 200, 64), (2000, 20, 72, 32)])
