@@ -1,5 +1,12 @@
-import os, sys, torch
-sys.path.insert(0, '/root/repo')
+#!/usr/bin/env python
+"""Time the two products of a sparse feature matrix X [1M x 256, 50 entries per row] (X @ W and X^T @ dS) on the
+rectangular sub-plans of the role kernels against the gather kernel (TG_ROLES2_RECT=0).  GPU box: python tools/rect_bench.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import topicgcn_b200 as tg
 dev = torch.device('cuda:0')
 n, F, H, nnz_row = 1_000_256, 256, 256, 50
