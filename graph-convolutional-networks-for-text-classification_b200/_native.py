@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libtopicgcn.so")
 EXPORTED_SYMBOLS = [
     "tg_version", "tg_last_error", "tg_status_string",
     "tg_csr_from_coo", "tg_csr_transpose",
-    "tg_plan_create", "tg_plan_destroy", "tg_plan_info", "tg_plan_workspace_bytes",
+    "tg_plan_create", "tg_plan_destroy", "tg_plan_info", "tg_plan_workspace_bytes", "tg_plan_spmm_launches",
     "tg_spmm_f32", "tg_gc1_fwd_f32", "tg_dropout_keep_mask", "tg_gc2_loss_fwd_f32", "tg_masked_ce_f32",
     "tg_reduce_scratch_floats", "tg_reduce_sum_f32",
     "tg_dense_nn_f32", "tg_hidden_bwd_scratch_floats", "tg_hidden_bwd_f32",
@@ -53,6 +53,7 @@ def _declare(lib) -> None:
     sig("tg_plan_destroy", None, _p)
     sig("tg_plan_info", C.c_int, _p, C.POINTER(_i64))
     sig("tg_plan_workspace_bytes", _sz, _p, _i32)
+    sig("tg_plan_spmm_launches", C.c_int, _p, _p, _i64, _i32, _i32, _i32)
     sig("tg_spmm_f32", C.c_int, _p, _p, _p, _p, _p, _i64, _p, _i64, _i32, _p, _p, _p, _sz, _p)
     sig("tg_gc1_fwd_f32", C.c_int, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _i32, _f32, _i32, _p, _u64, _u64,
         _p, _i64, _p, _sz, _p)

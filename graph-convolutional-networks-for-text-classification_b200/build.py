@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libtopicgcn.so")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
-SOURCES = ["tg_api.cu", "tg_csr.cu", "tg_spmm.cu", "tg_dense.cu", "tg_stream.cu", "tg_roles2.cu"]
+SOURCES = ["tg_api.cu", "tg_csr.cu", "tg_spmm.cu", "tg_dense.cu", "tg_roles2.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -54,9 +54,18 @@ class DeviceCSR:
         N.check(N.lib().tg_plan_info(self._plan, info), "tg_plan_info")
         self.n_hub_rows, self.n_segments, self.hub_nnz, self.max_row_nnz = (int(info[i]) for i in range(4))
         self.hub_threshold, self.segment_nnz = int(info[4]), int(info[5])
-        self.streaming, self.chunk_rows = bool(info[6] & 1), int(info[7])
+        self.streaming = bool(info[6] & 1)  # role-specialised streaming kernels (csrc/tg_roles2.cu) on the square graph
+        self.roles2 = bool(info[6] & 2)
         self.roles2_rect = int(info[6] >> 2) & 3  # 1: resident-table product (X @ W), 2: all-hub product (X^T @ dS)
-        self.roles2 = bool(info[6] & 2)  # warp-per-slot role kernels (tg_roles2.cu) used for 64 <= F <= 1024 (F % 4 == 0) and for F <= 32
+        self.chunk_rows = int(info[7]) & 0xFFFF
+        self.hub_groups = (int(info[7]) >> 16) & 0xFF   # hub slot groups of 256 (K = 1024 topics: 4-5)
+        self.doc_nq = (int(info[7]) >> 24) & 0xFF       # float4 chunks per lane of the document role (slice = 32 * nq columns)
+
+    def spmm_launches(self, B: torch.Tensor, n_feat: int, philox: bool = False, out_vec4_ok: bool = True) -> int:
+        """Kernels one tg_spmm* / tg_gc* call on this matrix launches (tg_plan_spmm_launches: the library's own kernel
+        selection, no Python mirror of it)."""
+        ld = int(B.stride(0)) if B.shape[0] > 1 else int(B.shape[1])
+        return int(N.lib().tg_plan_spmm_launches(self._plan, N.ptr(B), ld, int(n_feat), int(bool(philox)), int(bool(out_vec4_ok))))
 
     def __del__(self):
         try:

@@ -51,39 +51,34 @@ struct tg_plan {
     uint32_t* tickets = nullptr;     // [n_hub]   arrival counters (integer; reset by the last arriver)
     int32_t* seg_order = nullptr;    // [n_seg]   execution order: segments sorted by their first column (L2 reuse of B)
 
-    // ---- column-chunk streaming sub-plan (tg_stream.cu); present when the hub set is compact -------------------
-    bool stream_ok = false;
-    int32_t chunk_rows = 0;          // T: nodes per column chunk
-    int32_t n_chunks = 0;
-    int32_t cap_doc = 0, cap_hub = 0;  // staged entry windows (entries per chunk held in shared memory)
-    int32_t* colidx2 = nullptr;      // [nnz] int2 {hub slot or column id, value bits}; per row: non-hub columns first
-    int32_t* hcol = nullptr;         // [hub_nnz] chunk-major copy of the hub rows' entries: column LOCAL to its chunk
-    float* hval = nullptr;           // [hub_nnz]
-    int32_t* htab = nullptr;         // [n_chunks][n_hub+1] offsets into hcol/hval: segment (chunk, hub slot)
-    int4* cdesc = nullptr;           // [n_chunks] {first CSR entry of the chunk's rows, one past the last, htab[c][0], htab[c][n_hub]}
-    int32_t n_vslot = 0;             // virtual hub slots (heavy hub rows are split; multiple of 64)
-    int32_t* vmap = nullptr;         // [n_hub][8] virtual slots of each hub row
-    int32_t* vcnt = nullptr;         // [n_hub]
-    int32_t* rsplit = nullptr;       // [n_rows] first hub-column entry of each row in colidx2 (rows are reordered: others | hubs)
-
-    // ---- warp-per-slot role kernels (tg_roles2.cu): hub rows <= 256, 128-column slices -------------------------------
+    // ---- role-specialised column-chunk streaming kernels (tg_roles2.cu) ----------------------------------------------
+    // Square graphs with a compact hub set (<= 1280 hub rows: the document-topic-topic graphs).  Hub slots are cut into
+    // GROUPS of 256 (one hub CTA owns one group of one 128-column slice); the document role keeps all hub rows of B
+    // resident in shared memory and therefore works on column slices of 32 * r2_nq columns (r2_nq = 4 / 2 / 1 for up to
+    // 256 / 512 / 1280 hub rows).
     bool r2_ok = false;
-    // rectangular operands (sparse feature matrices X [n x nfeat <= 256] and their transposes):
+    // rectangular operands (sparse feature matrices X [n x nfeat] and their transposes):
     //   1 = "table": every column's row of B is resident (document role only: X * W)
     //   2 = "all hub": every row is a hub row (hub role only: X^T * dS)
     int32_t r2_rect = 0;
-    int32_t r2_stages = 4;           // document-role ring depth that fits next to the resident table
+    int32_t r2_groups = 1;           // hub slot groups (256 slots each)
+    int32_t r2_nq = 4;               // float4 chunks per lane of the document role (slice = 32 * r2_nq columns)
+    int32_t r2_stages = 4;           // document-role ring depth that fits next to the resident rows
     int32_t* r2_ident = nullptr;     // [n_cols] 0,1,2,... (the table rows of mode 1)
-    int32_t r2_T = 0, r2_n_chunks = 0, r2_cap_hub = 0;   // hub role: nodes per chunk, chunks, staged entries per chunk (max)
+    int32_t r2_T = 0, r2_n_chunks = 0, r2_cap_hub = 0;   // hub role: nodes per chunk, chunks, staged entries per (chunk, group) (max)
     int32_t r2_n_jobs = 0, r2_cap_doc = 0;               // document role: jobs of 64 rows, staged entries per job (max)
-    int2* r2_hent = nullptr;         // [hub_nnz+2] hub entries, (chunk, slot)-major: {byte offset of the column's row in the staged tile, value bits}
-    int32_t* r2_htab = nullptr;      // [r2_n_chunks][260] offsets of the 256 slots relative to the chunk's (even-aligned) base
-    int4* r2_cdesc = nullptr;        // [r2_n_chunks] {aligned base into r2_hent, staged entry count (even), first node, -}
-    int32_t* r2_vmap = nullptr;      // [n_hub][8] slots of each hub row (slot = warp * 16 + position)
+    int2* r2_hent = nullptr;         // [hub_nnz+2] hub entries, (group, chunk, slot)-major: {byte offset of the column's row in the staged tile, value bits}
+    int32_t* r2_htab = nullptr;      // [r2_groups * r2_n_chunks][260] offsets of the 256 slots relative to the (even-aligned) base of the (group, chunk) run
+    int4* r2_cdesc = nullptr;        // [r2_groups * r2_n_chunks] {aligned base into r2_hent, staged entry count (even), first node, -}
+    int32_t* r2_vmap = nullptr;      // [n_hub][8] slots of each hub row (slot = group * 256 + warp * 16 + position)
     int32_t* r2_vcnt = nullptr;      // [n_hub]
-    int2* r2_dent = nullptr;         // compact entries of the short rows, per row: other columns {col, v}, then hub columns {hub * 512, v}
-    int2* r2_rdesc = nullptr;        // [r2_n_jobs*64] {first entry relative to the job's base, n_entries << 16 | n_other}
+    int2* r2_dent = nullptr;         // compact entries of the short rows, per row: other columns {col, v}, then hub columns {hub * 128 * r2_nq, v}
+    int2* r2_rdesc = nullptr;        // [r2_n_jobs*64] {first entry relative to the job's base, n_entries << 16 | n_other}; y < 0: not a short row
     int2* r2_jdesc = nullptr;        // [r2_n_jobs] {aligned base into r2_dent, staged entry count (even)}
+    // knobs, read from the environment ONCE at plan creation (profiling / tests), never on the hot path
+    int32_t r2_min_rows = 16384, r2_narrow_min_rows = 131072, r2_hub_pct = -1, r2_narrow_hub_pct = -1, r2_only_role = 0;
+    int32_t r2_narrow_lane = 1;
+    bool r2_narrow_ok = true;
 };
 
 namespace tg {

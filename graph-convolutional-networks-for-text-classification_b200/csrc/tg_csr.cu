@@ -9,7 +9,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "tg_stream.cuh"
+#include "tg_roles.cuh"
 
 namespace tg {
 
@@ -355,13 +355,15 @@ int tg_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* va
             return cuda_fail(e, "segment order", __FILE__, __LINE__);
         }
     }
-    // optional streaming sub-plan (square matrices with a compact hub set: the document-topic-topic graphs)
-    const int rc = stream_plan_build(pl, rowptr, colidx, vals, h_ptr.data(), st);
-    if (rc != TG_OK) {
-        tg_plan_destroy(pl);
-        return rc;
+    // optional sub-plan of the role kernels (square matrices with a compact hub set: the document-topic-topic graphs)
+    if (pl->n_rows == pl->n_cols && pl->n_hub >= 1) {
+        const int rc = tg::roles2_plan_build(pl, rowptr, colidx, vals, h_ptr.data(), hub_rows.data(), st);
+        if (rc != TG_OK) {
+            tg_plan_destroy(pl);
+            return rc;
+        }
     }
-    // optional sub-plans for rectangular operands (sparse feature matrix / its transpose, <= 256 features)
+    // optional sub-plans for rectangular operands (sparse feature matrix / its transpose, <= 1280 features)
     if (!pl->r2_ok) {
         const int rc2 = tg::roles2_rect_plan_build(pl, rowptr, colidx, vals, h_ptr.data(), st);
         if (rc2 != TG_OK) {
@@ -375,7 +377,7 @@ int tg_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* va
 
 void tg_plan_destroy(tg_plan* pl) {
     if (!pl) return;
-    tg::stream_plan_free(pl);
+    tg::roles2_plan_free(pl);
     cudaFree(pl->hub_rows); cudaFree(pl->hub_seg_ptr); cudaFree(pl->seg_hub);
     cudaFree(pl->seg_begin); cudaFree(pl->seg_end); cudaFree(pl->tickets); cudaFree(pl->seg_order);
     delete pl;
@@ -385,7 +387,9 @@ int tg_plan_info(const tg_plan* pl, int64_t info[8]) {
     TG_REQUIRE(pl && info, TG_ERR_INVALID_ARG, "null pointer");
     info[0] = pl->n_hub; info[1] = pl->n_seg; info[2] = pl->hub_nnz;
     info[3] = pl->max_row_nnz; info[4] = pl->hub_threshold; info[5] = pl->segment_nnz;
-    info[6] = (pl->stream_ok ? 1 : 0) | ((pl->r2_ok && pl->r2_rect == 0) ? 2 : 0) | ((pl->r2_ok && pl->r2_rect != 0) ? 4 * pl->r2_rect : 0); info[7] = pl->stream_ok ? pl->chunk_rows : 0;
+    // bit 0 / 1: role kernels on the square graph, bits 2-3: rectangular mode; info[7]: nodes per hub chunk | groups << 16 | nq << 24
+    info[6] = ((pl->r2_ok && pl->r2_rect == 0) ? 3 : 0) | ((pl->r2_ok && pl->r2_rect != 0) ? 4 * pl->r2_rect : 0);
+    info[7] = pl->r2_ok ? ((int64_t)pl->r2_T | ((int64_t)pl->r2_groups << 16) | ((int64_t)pl->r2_nq << 24)) : 0;
     return TG_OK;
 }
 
@@ -393,9 +397,18 @@ size_t tg_plan_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
     if (!pl || n_feat <= 0) return 0;
     const size_t ld = (size_t)((n_feat + 3) / 4) * 4;
     const size_t v1 = (size_t)pl->n_seg * ld * sizeof(float) + 16;
-    size_t v2 = tg::stream_workspace_bytes(pl, n_feat);
-    if (pl->r2_ok && pl->r2_rect != 0) v2 = tg::roles2_workspace_bytes(pl, n_feat);
+    const size_t v2 = tg::roles2_workspace_bytes(pl, n_feat);
     return v1 > v2 ? v1 : v2;
+}
+
+int tg_plan_spmm_launches(const tg_plan* pl, const float* B, int64_t ldb, int32_t n_feat, int32_t philox, int32_t out_vec4_ok) {
+    if (!pl || n_feat <= 0) return 0;
+    if (out_vec4_ok) {
+        tg::StreamCall sc{nullptr, nullptr, B, ldb, n_feat, nullptr, 0};
+        const int k = tg::roles2_launches(pl, sc, philox != 0);
+        if (k > 0) return k;
+    }
+    return 1;  // gather kernel: split rows are finished by the last arriver inside the same launch
 }
 
 }  // extern "C"

@@ -1,22 +1,23 @@
-// tg_roles2.cu — role-specialised streaming SpMM, second generation ("warp per hub slot").
+// tg_roles2.cu — role-specialised column-chunk streaming SpMM ("warp per hub slot").
 //
-// Same product and same data flow as the role kernel of tg_stream.cu (reference layer.py:106 and its autograd transpose
-// product; B is read from HBM once, its second use is served by L2), reorganised around what the profiles of the first
-// generation showed (profiles/r01_final_full.md: 42 % issue utilisation, shared-memory pipe at 50 %, short-scoreboard
-// and long-scoreboard stalls, and — simulated from the plan — a 2.3x lock-step loss in the hub role because the four
-// 8-lane groups of a warp ran slot loops of different lengths and the 64 groups met at a barrier after every chunk):
+// Product: Y = A * B for the normalised adjacency of a document-topic-topic graph (reference layer.py:106 and its autograd
+// transpose product).  B is read from HBM once; its second use is served by L2.  One launch, two kinds of CTAs:
 //
 //   hub CTAs  (128-column slices, 16 warps): a WARP owns 16 hub slots; its 32 lanes cover the slice with one float4 each,
 //             so every lane of the warp works on the same entry (no divergence inside a warp) and the sixteen
-//             accumulators are sixteen float4 registers.  Heavy hub rows are split over the spare slots and the pieces
-//             are dealt to the warps longest-first, so the warps of a CTA carry the same load.  Chunks of T nodes are
-//             staged with one 2-D TMA tile + two bulk copies per stage (double buffered on mbarriers).  Entries carry
-//             the byte offset of their row inside the staged tile: address = base + offset, one LDS.128, two FFMA2.
-//   doc CTAs  (128-column slices, 64 groups of 8 lanes): the K hub rows of B stay resident in shared memory (bulk
-//             copies); a job is 64 consecutive rows — one row per group.  The job's entries and row descriptors arrive
-//             through a four-stage bulk-copy ring (mbarrier full/empty pairs, issued two jobs ahead by one thread), and
-//             each group prefetches the slice of B its NEXT row needs for the self loop into registers one job ahead,
-//             so no consumer instruction waits on global memory.
+//             accumulators are sixteen float4 registers.  A CTA therefore owns a GROUP of 256 slots; graphs with more hub
+//             rows (K = 1024 topics) use several groups — CTA (group g, slice s, lane l) streams the node range like every
+//             other hub CTA but only walks the entries of its group.  Heavy hub rows are split over spare slots and the
+//             pieces are dealt to the warps of all groups longest-first, so every warp carries the same load.  Chunks of
+//             T nodes are staged with one 2-D TMA tile + two bulk copies per stage (double buffered on mbarriers).
+//             Entries carry the byte offset of their row inside the staged tile: address = base + offset, one LDS.128,
+//             two FFMA2.
+//   doc CTAs  (slices of 32*NQ columns, 64 groups of 8 lanes): the K hub rows of B stay resident in shared memory (bulk
+//             copies) — NQ = 4 / 2 / 1 float4 per lane for up to ~368 / ~736 / 1280 hub rows, so that the resident rows
+//             always fit; a job is 64 consecutive rows — one row per group.  The job's entries and row descriptors arrive
+//             through a bulk-copy ring (mbarrier full/empty pairs, issued two jobs ahead by one thread), and each group
+//             prefetches the slice of B its NEXT row needs for the self loop into registers one job ahead, so no
+//             consumer instruction waits on global memory.
 //
 // All floating-point additions happen in an order fixed by the plan: bitwise reproducible, no float atomics.
 // Packed fp32 FMAs (FFMA2, fma.rn.f32x2) halve the issue slots of the arithmetic; the results are the IEEE fma results.
@@ -30,7 +31,7 @@
 
 #include "tg_async.cuh"
 #include "tg_finish.cuh"
-#include "tg_stream.cuh"
+#include "tg_roles.cuh"
 
 namespace tg {
 namespace {
@@ -38,18 +39,22 @@ namespace {
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kKPW = 16;              // hub slots per warp
-constexpr int kKv = kWarps * kKPW;    // 256 slots per CTA
+constexpr int kKv = kWarps * kKPW;    // 256 slots per hub CTA = one slot group
+constexpr int kMaxGroups = 5;         // up to 1280 slots (1024 hub rows + 256 spare slots for splitting the heavy ones)
 constexpr int kHtW = kKv + 4;         // offset-table row: 257 offsets padded to a multiple of 16 bytes
-constexpr int kFT = 128;              // columns per CTA slice
-constexpr int kRowBytes = kFT * 4;
+constexpr int kFT = 128;              // columns per hub-CTA slice
+constexpr int kRowBytes = kFT * 4;    // bytes of a row of the staged hub tile
+constexpr int kHubEnc = 128;          // document-role entries address hub row h as h * kHubEnc (scaled by NQ in the kernel)
 constexpr int kJobRows = 64;          // document role: rows per job = row groups per CTA
-constexpr int kStages = 4;            // document role: entry ring depth
+constexpr int kStages = 4;            // document role: entry ring depth (maximum)
 constexpr int kPF = 2;                // ... jobs issued ahead
 constexpr int kL2PF = 4;              // document role: jobs whose self-loop rows of B are prefetched into L2 ahead
+constexpr int kHubL2PF = 4;           // hub role: chunks (per chunk lane) whose tiles of B are prefetched into L2 ahead
 constexpr int kNStages = 4;            // narrow kernels: hub stages
 constexpr int kNRing = 8;              // narrow kernels: document ring depth
 constexpr int kNPF = 6;                // ... jobs issued ahead
 constexpr size_t kSmemMax = 227 * 1024;
+constexpr int32_t kNotShort = -1;      // rdesc.y of rows the document role does not produce (hub rows, padding)
 
 struct R2Args {
     // hub role
@@ -57,6 +62,7 @@ struct R2Args {
     const int32_t* __restrict__ htab;
     const int4* __restrict__ cdesc;     // {aligned base into hent, staged entries (even), first node of the chunk, -}
     int32_t T, n_chunks, cap_hub;
+    int32_t groups, Kv;                 // slot groups (hub CTAs per chunk lane and slice), total slots = groups * 256
     // document role
     const int2* __restrict__ dent;
     const int2* __restrict__ rdesc;
@@ -71,7 +77,6 @@ struct R2Args {
     float* partials;
     int64_t ldp;
     int32_t hub_slices, hub_lanes, doc_slices, doc_lanes, only_role;
-    int32_t table_mode;  // 1: B is only the resident table (no self loops to prefetch): X * W with X [n x <= 256]
     int32_t n_stages;    // document-role ring depth actually used (<= kStages)
     const uint32_t* __restrict__ keep_bits;  // bit-packed dropout keep mask [n][n_feat/32] (bit b of word w = column 32w+b) or null
 };
@@ -99,7 +104,11 @@ __device__ __forceinline__ float4 lds128(const unsigned char* p) { return *reint
 __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tmap, unsigned char* smem, uint64_t* bars,
                                          int bid) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int slice = bid % a.hub_slices, hl = bid / a.hub_slices;
+    // CTA = (chunk lane hl, slot group grp, column slice): the CTAs that share a chunk sequence are neighbours in the
+    // grid, so the groups x slices readers of a node range run at the same time and share its rows of B in L2
+    const int slice = bid % a.hub_slices, grp = (bid / a.hub_slices) % a.groups, hl = bid / (a.hub_slices * a.groups);
+    const int4* __restrict__ cdesc = a.cdesc + (int64_t)grp * a.n_chunks;
+    const int32_t* __restrict__ htab = a.htab + (int64_t)grp * a.n_chunks * kHtW;
     const size_t bs_bytes = (size_t)a.T * kRowBytes;
     const size_t he_bytes = align128((size_t)a.cap_hub * 8);
     const size_t st_bytes = bs_bytes + he_bytes + align128((size_t)kHtW * 4);
@@ -118,7 +127,7 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
         mbar_expect_tx(&full[buf], (unsigned)bs_bytes + (unsigned)d.y * 8u + (unsigned)(kHtW * 4));
         tma_load_2d(base, tmap, slice * kFT, d.z, &full[buf]);
         if (d.y) bulk_load_1d(base + bs_bytes, a.hent + d.x, (unsigned)d.y * 8u, &full[buf]);
-        bulk_load_1d(base + bs_bytes + he_bytes, a.htab + (int64_t)c * kHtW, (unsigned)(kHtW * 4), &full[buf]);
+        bulk_load_1d(base + bs_bytes + he_bytes, htab + (int64_t)c * kHtW, (unsigned)(kHtW * 4), &full[buf]);
     };
     float4 acc[kKPW];
 #pragma unroll
@@ -126,27 +135,52 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
     int c = hl;
     if (c < a.n_chunks) {
         int4 d_next = make_int4(0, 0, 0, 0);
+        int d_pf = 0;  // first node of the chunk kHubL2PF steps ahead (loaded one step early: no dependent stall)
         if (tid == 0) {
-            issue(0, c, __ldg(a.cdesc + c));
-            if (c + a.hub_lanes < a.n_chunks) d_next = __ldg(a.cdesc + c + a.hub_lanes);
+            issue(0, c, __ldg(cdesc + c));
+            if (c + a.hub_lanes < a.n_chunks) d_next = __ldg(cdesc + c + a.hub_lanes);
+            if (grp == 0) {
+                // the tiles of the next steps: into L2 now, so that the TMA loads one step ahead see L2 latency, not HBM latency
+                // (with one to two entries per slot and chunk a stage is ~1 us of work and the double buffer alone does not
+                // cover an HBM round trip); one slot group per chunk lane prefetches for all of them
+#pragma unroll
+                for (int i = 2; i < kHubL2PF; ++i)
+                    if (c + i * a.hub_lanes < a.n_chunks) tma_prefetch_l2_2d(tmap, slice * kFT, __ldg(cdesc + c + i * a.hub_lanes).z);
+                if (c + kHubL2PF * a.hub_lanes < a.n_chunks) d_pf = __ldg(cdesc + c + kHubL2PF * a.hub_lanes).z;
+            }
         }
         for (int it = 0; c < a.n_chunks; c += a.hub_lanes, ++it) {
             const int buf = it & 1;
             const int cn = c + a.hub_lanes;
             if (tid == 0 && cn < a.n_chunks) {
                 issue(buf ^ 1, cn, d_next);
-                if (cn + a.hub_lanes < a.n_chunks) d_next = __ldg(a.cdesc + cn + a.hub_lanes);
+                if (cn + a.hub_lanes < a.n_chunks) d_next = __ldg(cdesc + cn + a.hub_lanes);
+            }
+            if (tid == 0 && grp == 0) {
+                const int cp = c + kHubL2PF * a.hub_lanes;
+                if (cp < a.n_chunks) tma_prefetch_l2_2d(tmap, slice * kFT, d_pf);
+                if (cp + a.hub_lanes < a.n_chunks) d_pf = __ldg(cdesc + cp + a.hub_lanes).z;
             }
             mbar_wait(&full[buf], (unsigned)(it >> 1) & 1u);
             const unsigned char* base = smem + (size_t)buf * st_bytes;
             const unsigned char* Bl = base + lane * 16;
             const int2* he = reinterpret_cast<const int2*>(base + bs_bytes);
             const int32_t* ht = reinterpret_cast<const int32_t*>(base + bs_bytes + he_bytes);
-            const int32_t* htw = ht + warp * kKPW;
+            // the warp's 17 slot offsets: four broadcast LDS.128 + one LDS.32 (the table row and warp * 16 ints are 16-byte aligned)
+            int hofs[kKPW + 1];
+            {
+                const int4* ht4 = reinterpret_cast<const int4*>(ht + warp * kKPW);
+#pragma unroll
+                for (int i = 0; i < kKPW / 4; ++i) {
+                    const int4 t = ht4[i];
+                    hofs[4 * i] = t.x; hofs[4 * i + 1] = t.y; hofs[4 * i + 2] = t.z; hofs[4 * i + 3] = t.w;
+                }
+                hofs[kKPW] = ht[warp * kKPW + kKPW];
+            }
 #pragma unroll
             for (int kk = 0; kk < kKPW; ++kk) {
-                int q = htw[kk];  // warp-uniform broadcast reads
-                const int h1 = htw[kk + 1];
+                int q = hofs[kk];
+                const int h1 = hofs[kk + 1];
 #pragma unroll 1
                 for (; q + 4 <= h1; q += 4) {
                     const int2 e0 = he[q], e1 = he[q + 1], e2 = he[q + 2], e3 = he[q + 3];
@@ -171,7 +205,7 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
             __syncthreads();
         }
     }
-    float* dst = a.partials + ((int64_t)hl * kKv + warp * kKPW) * a.ldp + (int64_t)(slice * 32 + lane) * 4;
+    float* dst = a.partials + ((int64_t)hl * a.Kv + grp * kKv + warp * kKPW) * a.ldp + (int64_t)(slice * 32 + lane) * 4;
     if (slice * 32 + lane < a.n_chunks4) {  // (the last slice of a width that is no multiple of 128 is narrower; TMA zero-fills it)
 #pragma unroll
         for (int kk = 0; kk < kKPW; ++kk) *reinterpret_cast<float4*>(dst + (int64_t)kk * a.ldp) = acc[kk];
@@ -179,21 +213,33 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
 }
 
 // =============================================== document role ===========================================================
-template <bool TABLE>
+// NQ float4 chunks per lane: a group of 8 lanes covers a slice of 32 * NQ columns of a row; the resident hub rows take
+// Kh * 128 * NQ bytes of shared memory.  A group works on R = 4 / NQ rows AT ONCE (rows grp, grp + 64, ... of a super job of
+// 64 * R consecutive rows), walking their entry lists in lock step: every (super) job is the same amount of work —
+// 64 R rows x 32 NQ columns — and a warp always has four independent load -> FMA chains in flight per lane, whatever the
+// slice width (with one row per group the narrow slices were latency bound: 1.7 us per job for a quarter of the work).
+// TABLE: B is only the resident table (X * W with a sparse feature matrix X): no self loops to prefetch, every entry
+// addresses the table.
+template <int NQ, bool TABLE>
 __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, const CUtensorMap* tmap_job, unsigned char* smem,
                                          uint64_t* bars, int bid) {
+    constexpr int R = 4 / NQ;              // rows per group and job; plan jobs (64 rows) per super job
+    constexpr int kSliceCols = 32 * NQ;
+    constexpr int kRowB = kSliceCols * 4;  // bytes of a resident row
+    constexpr int kSJRows = kJobRows * R;
     const int tid = threadIdx.x, lane = tid & 31, gl = lane & 7, grp = tid >> 3;
-    const unsigned gmask = group_mask<8>(lane);
     const int slice = bid % a.doc_slices, dl = bid / a.doc_slices;
-    const int q0 = slice * 32 + gl;  // this lane owns the float4 chunks q0 + 8u, u < 4
-    // the last slice of a width that is no multiple of 128 columns is narrower: chunks at or past n_chunks4 do not exist
-    const int slice_bytes = min(kRowBytes, (a.n_chunks4 - slice * 32) * 16);
-    bool valid[4];
+    const int q0 = slice * (8 * NQ) + gl;  // this lane owns the float4 chunks q0 + 8u, u < NQ
+    // the last slice of a width that is no multiple of the slice width is narrower: chunks at or past n_chunks4 do not exist
+    const int slice_bytes = min(kRowB, (a.n_chunks4 - slice * 8 * NQ) * 16);
+    bool valid[NQ];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) valid[u] = q0 + 8 * u < a.n_chunks4;
-    const size_t bh_bytes = align128((size_t)a.Kh * kRowBytes);
-    const size_t en_bytes = align128((size_t)a.cap_doc * 8);
-    const size_t st_bytes = en_bytes + (size_t)kJobRows * 8;
+    for (int u = 0; u < NQ; ++u) valid[u] = q0 + 8 * u < a.n_chunks4;
+    const int n_sj = (a.n_jobs + R - 1) / R;  // super jobs
+    const size_t bh_bytes = align128((size_t)a.Kh * kRowB);
+    const size_t en_bytes = align128((size_t)a.cap_doc * 8 * R);
+    const size_t rd_bytes = (size_t)kSJRows * 8;
+    const size_t st_bytes = en_bytes + rd_bytes + 128;  // entries | row descriptors | the R job descriptors
     unsigned char* ring = smem + bh_bytes;
     uint64_t* full = bars;
     uint64_t* empty = bars + kStages;
@@ -211,133 +257,225 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
     __syncthreads();
     // the hub rows of B (this slice) stay resident for the whole kernel
     for (int k = tid; k < a.Kh; k += kThreads)
-        bulk_load_1d(smem + (size_t)k * kRowBytes, a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb + (int64_t)slice * kFT, (unsigned)slice_bytes, bhbar);
-    // ring depth and look-ahead: compile-time constants on the graph path, run-time (smaller when the resident table is
-    // large) for the resident-table product of a rectangular operand
-    const int ns = TABLE ? a.n_stages : kStages;
-    const int pf = TABLE ? (ns > kPF ? kPF : ns - 1) : kPF;
-    auto issue = [&](int itn, int jobn) {
-        const int s = itn % ns;
-        const int2 jd = __ldg(a.jdesc + jobn);
+        bulk_load_1d(smem + (size_t)k * kRowB, a.B + (int64_t)__ldg(a.hub_rows + k) * a.ldb + (int64_t)slice * kSliceCols, (unsigned)slice_bytes, bhbar);
+    // ring depth and look-ahead: what fits next to the resident rows (plan time)
+    const int ns = a.n_stages;
+    const int pf = ns > kPF ? kPF : ns - 1;
+    auto issue = [&](int s, int sjn) {  // s: ring stage
+        const int j0 = sjn * R, j1 = min(j0 + R, a.n_jobs) - 1;  // plan jobs of this super job: their entry runs are contiguous
+        const int2 jd0 = __ldg(a.jdesc + j0), jd1 = __ldg(a.jdesc + j1);
+        const unsigned n_ent = (unsigned)(jd1.x + jd1.y - jd0.x);
+        const unsigned n_rd = (unsigned)(j1 - j0 + 1) * (unsigned)(kJobRows * 8);
         unsigned char* base = ring + (size_t)s * st_bytes;
         fence_proxy_async();
-        mbar_expect_tx(&full[s], (unsigned)jd.y * 8u + (unsigned)(kJobRows * 8));
-        if (jd.y) bulk_load_1d(base, a.dent + jd.x, (unsigned)jd.y * 8u, &full[s]);
-        bulk_load_1d(base + en_bytes, a.rdesc + (int64_t)jobn * kJobRows, (unsigned)(kJobRows * 8), &full[s]);
+        mbar_expect_tx(&full[s], n_ent * 8u + n_rd + (R > 1 ? 16u * ((R + 1) / 2) : 0u));
+        if (n_ent) bulk_load_1d(base, a.dent + jd0.x, n_ent * 8u, &full[s]);
+        bulk_load_1d(base + en_bytes, a.rdesc + (int64_t)j0 * kJobRows, n_rd, &full[s]);
+        // (the job-descriptor array is padded with zeros past n_jobs: the copy of R of them never leaves it)
+        if (R > 1) bulk_load_1d(base + en_bytes + rd_bytes, a.jdesc + j0, 16u * ((R + 1) / 2), &full[s]);
     };
     if (tid == 0) {
         for (int i = 0; i < pf; ++i)
-            if (dl + i * a.doc_lanes < a.n_jobs) issue(i, dl + i * a.doc_lanes);
+            if (dl + i * a.doc_lanes < n_sj) issue(i, dl + i * a.doc_lanes);
         if (!TABLE) {
 #pragma unroll
             for (int i = 1; i < kL2PF; ++i)
-                if (dl + i * a.doc_lanes < a.n_jobs) tma_prefetch_l2_2d(tmap_job, slice * kFT, (dl + i * a.doc_lanes) * kJobRows);
+                if (dl + i * a.doc_lanes < n_sj) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) tma_prefetch_l2_2d(tmap_job, slice * kSliceCols, ((dl + i * a.doc_lanes) * R + r) * kJobRows);
+                }
         }
     }
-    auto load_self = [&](float4(&dst)[4], int jobx) {
-        const int64_t row = (int64_t)jobx * kJobRows + grp;
-        if (!TABLE && jobx < a.n_jobs && row < a.n) {
-            const float* p = a.B + row * a.ldb + (int64_t)q0 * 4;
+    auto load_self = [&](float4(&dst)[R][NQ], int sjx) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) dst[u] = valid[u] ? ldg_f4_stream(p + u * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = (int64_t)sjx * kSJRows + r * kJobRows + grp;
+            if (!TABLE && sjx < n_sj && row < a.n) {
+                const float* p = a.B + row * a.ldb + (int64_t)q0 * 4;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) dst[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < NQ; ++u) dst[r][u] = valid[u] ? ldg_f4_stream(p + u * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int u = 0; u < NQ; ++u) dst[r][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
     };
-    // per-thread constants of the epilogue: this lane's 16 bias values, the optional upstream scale, the Philox offset
-    float4 bias4[4];
+    // per-thread constants of the epilogue: this lane's bias values, the optional upstream scale
+    float4 bias4[NQ];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < NQ; ++u)
         bias4[u] = (epi.bias && valid[u]) ? __ldg(reinterpret_cast<const float4*>(epi.bias + (int64_t)(q0 + 8 * u) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float gscale = epi.out_scale ? __ldg(epi.out_scale) : 1.f;
-    const uint64_t rng_offset = (epi.drop_mode == 1 && epi.offset_dev) ? epi.offset + __ldg(epi.offset_dev) : epi.offset;
-    const int mask_words = a.doc_slices * 4;  // row stride of the bit-packed mask: four words per 128-column slice
-    auto load_bits = [&](int jobx) {
-        const int64_t row = (int64_t)jobx * kJobRows + grp;
-        if (a.keep_bits && jobx < a.n_jobs && row < a.n)
-            return __ldg(reinterpret_cast<const uint4*>(a.keep_bits + row * mask_words + slice * 4));
-        return make_uint4(0u, 0u, 0u, 0u);
+    // bit-packed mask: four words per 128 columns; chunk q lives in word q / 8 at bits 4 (q % 8) .. — this lane's NQ words
+    // of a row are the words slice * NQ + u
+    const int mask_words = ((a.n_chunks4 + 31) / 32) * 4;
+    struct Bits { uint32_t w[R][NQ]; };
+    auto load_bits = [&](int sjx) {
+        Bits b;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int u = 0; u < NQ; ++u) b.w[r][u] = 0u;
+            const int64_t row = (int64_t)sjx * kSJRows + r * kJobRows + grp;
+            if (a.keep_bits && sjx < n_sj && row < a.n) {
+                const uint32_t* p = a.keep_bits + row * mask_words + slice * NQ;
+                if (NQ == 4) {
+                    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+                    b.w[r][0] = t.x; b.w[r][1 % NQ] = t.y; b.w[r][2 % NQ] = t.z; b.w[r][3 % NQ] = t.w;
+                } else if (NQ == 2) {
+                    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+                    b.w[r][0] = t.x; b.w[r][1 % NQ] = t.y;
+                } else {
+                    b.w[r][0] = __ldg(p);
+                }
+            }
+        }
+        return b;
     };
-    float4 cur[4];
+    float4 cur[R][NQ];
     load_self(cur, dl);
-    uint4 kbits = load_bits(dl);
+    Bits kbits = load_bits(dl);
     mbar_wait(bhbar, 0);
     const unsigned char* BHl = smem + gl * 16;
-    int it = 0;
-    for (int job = dl; job < a.n_jobs; job += a.doc_lanes, ++it) {
+    // ring positions as running counters (stage, phase): consumer side s / ph, producer side (pf jobs ahead) sp / php
+    int s = 0, sp = pf;
+    unsigned ph = 0, php = 0;
+    if (sp >= ns) { sp -= ns; php ^= 1u; }
+    bool wrapped = false;  // the producer has gone round the ring once: stages must be released before they are refilled
+    for (int sj = dl; sj < n_sj; sj += a.doc_lanes) {
         if (tid == 0) {
-            const int itn = it + pf, jobn = job + pf * a.doc_lanes;
-            if (jobn < a.n_jobs) {
-                // the stage was last read by iteration itn - ns
-                if (itn >= ns) mbar_wait(&empty[itn % ns], (unsigned)(itn / ns - 1) & 1u);
-                issue(itn, jobn);
+            const int sjn = sj + pf * a.doc_lanes;
+            if (sjn < n_sj) {
+                // the stage was last read ns iterations before the one being issued
+                if (wrapped || php) mbar_wait(&empty[sp], php ^ 1u);
+                issue(sp, sjn);
             }
             // the rows of B the self loops of a later job need: into L2 now, so that the register prefetch one job ahead
             // sees L2 latency instead of HBM latency (bytes in flight per SM, not bandwidth, were the limit)
-            const int jobp = job + kL2PF * a.doc_lanes;
-            if (!TABLE && jobp < a.n_jobs) tma_prefetch_l2_2d(tmap_job, slice * kFT, jobp * kJobRows);
-        }
-        const int s = it % ns;
-        mbar_wait(&full[s], (unsigned)(it / ns) & 1u);
-        const unsigned char* base = ring + (size_t)s * st_bytes;
-        const int2 rd = reinterpret_cast<const int2*>(base + en_bytes)[grp];
-        const int n_tot = rd.y >> 16, n_nh = rd.y & 0xffff;
-        const int2* ent = reinterpret_cast<const int2*>(base) + rd.x;
-        const int64_t row = (int64_t)job * kJobRows + grp;
-        float4 acc[4];
+            const int sjp = sj + kL2PF * a.doc_lanes;
+            if (!TABLE && sjp < n_sj) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int p = 0; p < n_nh; ++p) {  // columns outside the hub set: the self loop (prefetched) or a global gather
-            const int2 en = ent[p];
-            const float v = __int_as_float(en.y);
-            if ((int64_t)en.x == row) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) fma4p(acc[u], v, cur[u]);
-            } else {
-                const float* src = a.B + (int64_t)en.x * a.ldb + (int64_t)q0 * 4;
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (valid[u]) fma4p(acc[u], v, ldg_f4(src + u * 32));
+                for (int r = 0; r < R; ++r) tma_prefetch_l2_2d(tmap_job, slice * kSliceCols, (sjp * R + r) * kJobRows);
             }
         }
-        load_self(cur, job + a.doc_lanes);  // next job's self-loop operand: in flight during the hub-column loop
-        int p = n_nh;
-#pragma unroll 1
-        for (; p + 2 <= n_tot; p += 2) {
-            const int2 e0 = ent[p], e1 = ent[p + 1];
-            const unsigned char* r0 = BHl + e0.x;
-            const unsigned char* r1 = BHl + e1.x;
-            const float4 b00 = lds128(r0), b01 = lds128(r0 + 128), b02 = lds128(r0 + 256), b03 = lds128(r0 + 384);
-            const float4 b10 = lds128(r1), b11 = lds128(r1 + 128), b12 = lds128(r1 + 256), b13 = lds128(r1 + 384);
-            const float v0 = __int_as_float(e0.y), v1 = __int_as_float(e1.y);
-            fma4p(acc[0], v0, b00); fma4p(acc[1], v0, b01); fma4p(acc[2], v0, b02); fma4p(acc[3], v0, b03);
-            fma4p(acc[0], v1, b10); fma4p(acc[1], v1, b11); fma4p(acc[2], v1, b12); fma4p(acc[3], v1, b13);
+        mbar_wait(&full[s], ph);
+        const unsigned char* base = ring + (size_t)s * st_bytes;
+        const int2* jds = reinterpret_cast<const int2*>(base + en_bytes + rd_bytes);
+        const int jbase0 = (R > 1) ? jds[0].x : 0;
+        const int2* ent[R];
+        int n_nh[R], n_hub[R];
+        bool produce[R];
+        int max_nh = 0, max_hub = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool live = sj * R + r < a.n_jobs;   // (a trailing super job may hold fewer than R plan jobs)
+            const int2 rd = live ? reinterpret_cast<const int2*>(base + en_bytes)[r * kJobRows + grp] : make_int2(0, kNotShort);
+            produce[r] = rd.y >= 0;  // hub rows and padding rows carry kNotShort; a row without entries is produced (epilogue of zero)
+            const int n_tot = produce[r] ? (rd.y >> 16) : 0;
+            n_nh[r] = produce[r] ? (rd.y & 0xffff) : 0;
+            n_hub[r] = n_tot - n_nh[r];
+            const int job_ofs = (R > 1 && live) ? jds[r].x - jbase0 : 0;
+            ent[r] = reinterpret_cast<const int2*>(base) + job_ofs + rd.x;
+            max_nh = max(max_nh, n_nh[r]);
+            max_hub = max(max_hub, n_hub[r]);
         }
-        if (p < n_tot) {
-            const int2 e0 = ent[p];
-            const unsigned char* r0 = BHl + e0.x;
-            const float v0 = __int_as_float(e0.y);
-            fma4p(acc[0], v0, lds128(r0)); fma4p(acc[1], v0, lds128(r0 + 128));
-            fma4p(acc[2], v0, lds128(r0 + 256)); fma4p(acc[3], v0, lds128(r0 + 384));
+        float4 acc[R][NQ];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int u = 0; u < NQ; ++u) acc[r][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // columns outside the hub set: the self loop (prefetched) or a global gather
+        for (int p = 0; p < max_nh; ++p) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (p < n_nh[r]) {
+                    const int2 en = ent[r][p];
+                    const float v = __int_as_float(en.y);
+                    const int64_t row = (int64_t)sj * kSJRows + r * kJobRows + grp;
+                    if ((int64_t)en.x == row) {
+#pragma unroll
+                        for (int u = 0; u < NQ; ++u) fma4p(acc[r][u], v, cur[r][u]);
+                    } else {
+                        const float* src = a.B + (int64_t)en.x * a.ldb + (int64_t)q0 * 4;
+#pragma unroll
+                        for (int u = 0; u < NQ; ++u)
+                            if (valid[u]) fma4p(acc[r][u], v, ldg_f4(src + u * 32));
+                    }
+                }
+            }
+        }
+        load_self(cur, sj + a.doc_lanes);  // next job's self-loop operand: in flight during the hub-column loop
+#pragma unroll
+        for (int r = 0; r < R; ++r) ent[r] += n_nh[r];
+        if (R == 1) {
+            // one row per group: two entries per trip
+            int p = 0;
+#pragma unroll 1
+            for (; p + 2 <= max_hub; p += 2) {
+                const int2 e0 = ent[0][p], e1 = ent[0][p + 1];
+                const unsigned char* r0 = BHl + e0.x * NQ;  // entries address hub row h as h * 128; a resident row is 128 * NQ bytes
+                const unsigned char* r1 = BHl + e1.x * NQ;
+                float4 b0[NQ], b1[NQ];
+#pragma unroll
+                for (int u = 0; u < NQ; ++u) { b0[u] = lds128(r0 + 128 * u); b1[u] = lds128(r1 + 128 * u); }
+                const float v0 = __int_as_float(e0.y), v1 = __int_as_float(e1.y);
+#pragma unroll
+                for (int u = 0; u < NQ; ++u) fma4p(acc[0][u], v0, b0[u]);
+#pragma unroll
+                for (int u = 0; u < NQ; ++u) fma4p(acc[0][u], v1, b1[u]);
+            }
+            if (p < max_hub) {
+                const int2 e0 = ent[0][p];
+                const unsigned char* r0 = BHl + e0.x * NQ;
+                const float v0 = __int_as_float(e0.y);
+#pragma unroll
+                for (int u = 0; u < NQ; ++u) fma4p(acc[0][u], v0, lds128(r0 + 128 * u));
+            }
+        } else {
+            // R rows in lock step, one entry of each per trip: R independent chains (rows of a graph have near-equal lengths)
+#pragma unroll 1
+            for (int p = 0; p < max_hub; ++p) {
+                int2 e[R];
+                float4 b[R][NQ];
+#pragma unroll
+                for (int r = 0; r < R; ++r) e[r] = (p < n_hub[r]) ? ent[r][p] : make_int2(0, 0);  // (hub row 0, weight 0: adds nothing)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const unsigned char* rp = BHl + e[r].x * NQ;
+#pragma unroll
+                    for (int u = 0; u < NQ; ++u) b[r][u] = lds128(rp + 128 * u);
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (p < n_hub[r]) {
+                        const float v = __int_as_float(e[r].y);
+#pragma unroll
+                        for (int u = 0; u < NQ; ++u) fma4p(acc[r][u], v, b[r][u]);
+                    }
+                }
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads the stage
-        const uint4 kb = kbits;
-        kbits = load_bits(job + a.doc_lanes);
-        if (n_tot > 0) {
+        if (++s == ns) { s = 0; ph ^= 1u; }
+        if (++sp == ns) { sp = 0; php ^= 1u; wrapped = true; }
+        const Bits kb = kbits;
+        kbits = load_bits(sj + a.doc_lanes);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!produce[r]) continue;
             // fused epilogue (EpiStore semantics, tg_epilogue.cuh) with the per-thread constants held in registers
+            const int64_t row = (int64_t)sj * kSJRows + r * kJobRows + grp;
             float* yrow = epi.Y + row * epi.ldy + (int64_t)q0 * 4;
             if (row >= epi.raw_row_begin) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (valid[u]) *reinterpret_cast<float4*>(yrow + u * 32) = acc[u];
+                for (int u = 0; u < NQ; ++u)
+                    if (valid[u]) *reinterpret_cast<float4*>(yrow + u * 32) = acc[r][u];
             } else {
-                Philox4 rnd = Philox4{0, 0, 0, 0};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < NQ; ++u) {
                     if (!valid[u]) continue;
-                    float y[4] = {acc[u].x, acc[u].y, acc[u].z, acc[u].w};
+                    float y[4] = {acc[r][u].x, acc[r][u].y, acc[r][u].z, acc[r][u].w};
                     const float bb[4] = {bias4[u].x, bias4[u].y, bias4[u].z, bias4[u].w};
                     if (epi.bias) {
 #pragma unroll
@@ -352,21 +490,10 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
                         for (int k = 0; k < 4; ++k) y[k] *= gscale;
                     }
                     const int q = q0 + 8 * u;
-                    if (a.keep_bits) {
-                        const uint32_t w = (u == 0 ? kb.x : u == 1 ? kb.y : u == 2 ? kb.z : kb.w) >> (4 * gl);
+                    if (a.keep_bits) {  // Philox dropout: the mask was drawn into the bit-packed side buffer (roles2_run)
+                        const uint32_t w = kb.w[r][u] >> (4 * gl);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) y[k] = ((w >> k) & 1u) ? y[k] * epi.scale : 0.f;
-                    } else if (epi.drop_mode == 1 && epi.keep_thr == kDropoutHalfThr) {
-                        if (u == 0) rnd = dropout_philox_half(row, (uint32_t)(q >> 5), epi.seed, rng_offset);  // one call per slice (u = 0 is valid whenever any chunk is)
-                        const uint32_t w = dropout_half_word(rnd, q) >> (4 * (q & 7));
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) y[k] = ((w >> k) & 1u) ? y[k] * epi.scale : 0.f;
-                    } else if (epi.drop_mode == 1) {
-                        if (!(u & 1)) rnd = dropout_philox(row, (uint32_t)(q & 7), (uint32_t)(q >> 4), epi.seed, rng_offset);
-                        uint32_t r16[4];
-                        dropout_u16x4(rnd, (q >> 3) & 1, r16);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) y[k] = (r16[k] < epi.keep_thr) ? y[k] * epi.scale : 0.f;
                     } else if (epi.drop_mode == 2) {
                         const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(epi.keep_mask + row * (int64_t)epi.n_feat + (int64_t)q * 4));
 #pragma unroll
@@ -435,21 +562,21 @@ __global__ void __launch_bounds__(256) r2_keep_bits_half_kernel(uint32_t* __rest
     }
 }
 
-template <bool TABLE>
+template <int NQ, bool TABLE>
 __global__ void __launch_bounds__(kThreads, 1) roles2_kernel(const R2Args a, const EpiStore epi, const __grid_constant__ CUtensorMap tmapB,
                                                             const __grid_constant__ CUtensorMap tmapJob) {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bars[2 * kStages + 2];
     // TMA destinations must be 128-byte aligned: align the dynamic base by hand (the launch requests 128 spare bytes)
     unsigned char* smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
-    const int n_hub_ctas = a.hub_slices * a.hub_lanes;
+    const int n_hub_ctas = a.hub_slices * a.groups * a.hub_lanes;
     const int bid = blockIdx.x;
     if (bid < n_hub_ctas) {
         if (a.only_role == 2) return;
         hub_role(a, &tmapB, smem, bars, bid);
     } else {
         if (a.only_role == 1) return;
-        doc_role<TABLE>(a, epi, &tmapJob, smem, bars, bid - n_hub_ctas);
+        doc_role<NQ, TABLE>(a, epi, &tmapJob, smem, bars, bid - n_hub_ctas);
     }
 }
 
@@ -463,8 +590,11 @@ __global__ void __launch_bounds__(kThreads, 1) roles2_kernel(const R2Args a, con
 //             because a group holds the whole row.
 // Entry offsets were precomputed for 512-byte rows (x = local row * 512): rescaled here to the F*4-byte rows.
 __device__ __forceinline__ void hub_role_narrow(const R2Args& a, const CUtensorMap* tmap, unsigned char* smem, uint64_t* bars,
-                                                int hl) {
+                                                int bid) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane & 7, g = lane >> 3;
+    const int grp = bid % a.groups, hl = bid / a.groups;  // slot group, chunk lane
+    const int4* __restrict__ cdesc = a.cdesc + (int64_t)grp * a.n_chunks;
+    const int32_t* __restrict__ htab = a.htab + (int64_t)grp * a.n_chunks * kHtW;
     const int n4 = a.n_chunks4;
     const int rowb = n4 * 16;
     const bool act = gl < n4;
@@ -493,7 +623,7 @@ __device__ __forceinline__ void hub_role_narrow(const R2Args& a, const CUtensorM
             tma_load_2d(base, tmap, 0, d.z, &full[buf]);
         }
         if (d.y) bulk_load_1d(base + bs_bytes, a.hent + d.x, (unsigned)d.y * 8u, &full[buf]);
-        bulk_load_1d(base + bs_bytes + he_bytes, a.htab + (int64_t)c * kHtW, (unsigned)(kHtW * 4), &full[buf]);
+        bulk_load_1d(base + bs_bytes + he_bytes, htab + (int64_t)c * kHtW, (unsigned)(kHtW * 4), &full[buf]);
     };
     // The slots of a warp are in descending weight order (plan: longest-first dealing).  The four heaviest are walked by the
     // whole warp, every group taking each fourth entry of the run; the other twelve are walked four at a time, one slot per
@@ -509,12 +639,12 @@ __device__ __forceinline__ void hub_role_narrow(const R2Args& a, const CUtensorM
         if (tid == 0) {
 #pragma unroll
             for (int i = 0; i < kNStages - 1; ++i)
-                if (c + i * a.hub_lanes < a.n_chunks) issue(i, c + i * a.hub_lanes, __ldg(a.cdesc + c + i * a.hub_lanes));
+                if (c + i * a.hub_lanes < a.n_chunks) issue(i, c + i * a.hub_lanes, __ldg(cdesc + c + i * a.hub_lanes));
         }
         for (int it = 0; c < a.n_chunks; c += a.hub_lanes, ++it) {
             const int buf = it % kNStages;
             const int cn = c + (kNStages - 1) * a.hub_lanes;  // its buffer was released by the barrier of iteration it - 1
-            if (tid == 0 && cn < a.n_chunks) issue((it + kNStages - 1) % kNStages, cn, __ldg(a.cdesc + cn));
+            if (tid == 0 && cn < a.n_chunks) issue((it + kNStages - 1) % kNStages, cn, __ldg(cdesc + cn));
             mbar_wait(&full[buf], (unsigned)(it / kNStages) & 1u);
             const unsigned char* base = smem + (size_t)buf * st_bytes;
             const unsigned char* Bl = base + lane_off;
@@ -556,7 +686,7 @@ __device__ __forceinline__ void hub_role_narrow(const R2Args& a, const CUtensorM
             __syncthreads();
         }
     }
-    float* dst = a.partials + ((int64_t)hl * kKv + warp * kKPW) * a.ldp + (int64_t)gl * 4;
+    float* dst = a.partials + ((int64_t)hl * a.Kv + grp * kKv + warp * kKPW) * a.ldp + (int64_t)gl * 4;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
         float4 v = accS[kk];
@@ -643,7 +773,8 @@ __device__ __forceinline__ void doc_role_narrow(const R2Args& a, const Epi& epi,
         mbar_wait(&full[s], (unsigned)(it / kNRing) & 1u);
         const unsigned char* base = ring + (size_t)s * st_bytes;
         const int2 rd = reinterpret_cast<const int2*>(base + en_bytes)[grp];
-        const int n_tot = rd.y >> 16, n_nh = rd.y & 0xffff;
+        const bool produce = rd.y >= 0;  // kNotShort: hub rows / padding; a row without entries still gets its epilogue
+        const int n_tot = produce ? (rd.y >> 16) : 0, n_nh = produce ? (rd.y & 0xffff) : 0;
         const int2* ent = reinterpret_cast<const int2*>(base) + rd.x;
         const int64_t row = (int64_t)job * kJobRows + grp;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -657,8 +788,8 @@ __device__ __forceinline__ void doc_role_narrow(const R2Args& a, const Epi& epi,
 #pragma unroll 1
         for (; p + 4 <= n_tot; p += 4) {
             const int2 e0 = ent[p], e1 = ent[p + 1], e2 = ent[p + 2], e3 = ent[p + 3];
-            const float4 b0 = lds128(BHl + ((e0.x * n4) >> 5)), b1 = lds128(BHl + ((e1.x * n4) >> 5));
-            const float4 b2 = lds128(BHl + ((e2.x * n4) >> 5)), b3 = lds128(BHl + ((e3.x * n4) >> 5));
+            const float4 b0 = lds128(BHl + ((e0.x * n4) >> 3)), b1 = lds128(BHl + ((e1.x * n4) >> 3));
+            const float4 b2 = lds128(BHl + ((e2.x * n4) >> 3)), b3 = lds128(BHl + ((e3.x * n4) >> 3));
             fma4p(acc, __int_as_float(e0.y), b0);
             fma4p(acc, __int_as_float(e1.y), b1);
             fma4p(acc, __int_as_float(e2.y), b2);
@@ -666,11 +797,11 @@ __device__ __forceinline__ void doc_role_narrow(const R2Args& a, const Epi& epi,
         }
         for (; p < n_tot; ++p) {
             const int2 e0 = ent[p];
-            fma4p(acc, __int_as_float(e0.y), lds128(BHl + ((e0.x * n4) >> 5)));
+            fma4p(acc, __int_as_float(e0.y), lds128(BHl + ((e0.x * n4) >> 3)));
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
-        if (n_tot > 0) {
+        if (produce) {
             Chunk<4> out[1];
             out[0].v[0] = acc.x; out[0].v[1] = acc.y; out[0].v[2] = acc.z; out[0].v[3] = acc.w;
             epi.template apply<4, 8, 1>(row, gl, gmask, n4, out);
@@ -683,13 +814,13 @@ __global__ void __launch_bounds__(kThreads, 1) roles2n_kernel(const R2Args a, co
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bars[2 * kNRing + 2];
     unsigned char* smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
-    const int bid = blockIdx.x;
-    if (bid < a.hub_lanes) {
+    const int bid = blockIdx.x, n_hub_ctas = a.groups * a.hub_lanes;
+    if (bid < n_hub_ctas) {
         if (a.only_role == 2) return;
         hub_role_narrow(a, &tmapB, smem, bars, bid);
     } else {
         if (a.only_role == 1) return;
-        doc_role_narrow(a, epi, smem, bars, bid - a.hub_lanes);
+        doc_role_narrow(a, epi, smem, bars, bid - n_hub_ctas);
     }
 }
 
@@ -763,7 +894,8 @@ __device__ __forceinline__ void doc_role_narrow_lane(const R2Args& a, const Epi&
         mbar_wait(&full[s], (unsigned)(it / kTeamStages) & 1u);
         const unsigned char* base = ring + (size_t)s * st_bytes;
         const int2 rd = reinterpret_cast<const int2*>(base + en_bytes)[tl];
-        const int n_tot = rd.y >> 16, n_nh = rd.y & 0xffff;
+        const bool produce = rd.y >= 0;
+        const int n_tot = produce ? (rd.y >> 16) : 0, n_nh = produce ? (rd.y & 0xffff) : 0;
         const int2* ent = reinterpret_cast<const int2*>(base) + rd.x;
         const int64_t row = (int64_t)job * kJobRows + tl;
         float4 acc[NV];
@@ -788,8 +920,8 @@ __device__ __forceinline__ void doc_role_narrow_lane(const R2Args& a, const Epi&
 #pragma unroll 1
         for (; p + 2 <= n_tot; p += 2) {
             const int2 e0 = ent[p], e1 = ent[p + 1];
-            const unsigned char* r0 = smem + ((e0.x * n4) >> 5);
-            const unsigned char* r1 = smem + ((e1.x * n4) >> 5);
+            const unsigned char* r0 = smem + ((e0.x * n4) >> 3);
+            const unsigned char* r1 = smem + ((e1.x * n4) >> 3);
             const float v0 = __int_as_float(e0.y), v1 = __int_as_float(e1.y);
 #pragma unroll
             for (int i = 0; i < NV; ++i)
@@ -801,7 +933,7 @@ __device__ __forceinline__ void doc_role_narrow_lane(const R2Args& a, const Epi&
         }
         if (p < n_tot) {
             const int2 e0 = ent[p];
-            const unsigned char* r0 = smem + ((e0.x * n4) >> 5);
+            const unsigned char* r0 = smem + ((e0.x * n4) >> 3);
             const float v0 = __int_as_float(e0.y);
 #pragma unroll
             for (int i = 0; i < NV; ++i)
@@ -809,7 +941,7 @@ __device__ __forceinline__ void doc_role_narrow_lane(const R2Args& a, const Epi&
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
-        if (n_tot > 0) {
+        if (produce) {
             Chunk<4> out[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) { out[i].v[0] = acc[i].x; out[i].v[1] = acc[i].y; out[i].v[2] = acc[i].z; out[i].v[3] = acc[i].w; }
@@ -823,13 +955,13 @@ __global__ void __launch_bounds__(kThreads, 1) roles2nl_kernel(const R2Args a, c
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bars[kTeams * 2 * kTeamStages + 2];
     unsigned char* smem = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
-    const int bid = blockIdx.x;
-    if (bid < a.hub_lanes) {
+    const int bid = blockIdx.x, n_hub_ctas = a.groups * a.hub_lanes;
+    if (bid < n_hub_ctas) {
         if (a.only_role == 2) return;
         hub_role_narrow(a, &tmapB, smem, bars, bid);
     } else {
         if (a.only_role == 1) return;
-        doc_role_narrow_lane<NV>(a, epi, smem, bars, bid - a.hub_lanes);
+        doc_role_narrow_lane<NV>(a, epi, smem, bars, bid - n_hub_ctas);
     }
 }
 
@@ -842,10 +974,11 @@ __global__ void r2_hub_deg_kernel(const int32_t* __restrict__ rowptr, const int3
     for (int p = s + threadIdx.x; p < e; p += blockDim.x) atomicAdd(deg + colidx[p], 1);
 }
 
-// one block per hub row: key = chunk * 256 + slot for each of its entries, in storage (column) order
+// one block per hub row: key = ((group * n_chunks) + chunk) * 256 + slot inside the group, for each of its entries, in
+// storage (column) order.  A heavy hub row is dealt over nv slots by column residue: every slot sees every chunk.
 __global__ void r2_hub_keys_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                    const int32_t* __restrict__ hub_rows, const int64_t* __restrict__ hub_ofs,
-                                   const int32_t* __restrict__ node_chunk, const int32_t* __restrict__ vmap,
+                                   const int32_t* __restrict__ node_chunk, int n_chunks, const int32_t* __restrict__ vmap,
                                    const int32_t* __restrict__ vcnt, uint32_t* __restrict__ keys, int32_t* __restrict__ src) {
     const int k = blockIdx.x;
     const int r = hub_rows[k];
@@ -854,25 +987,26 @@ __global__ void r2_hub_keys_kernel(const int32_t* __restrict__ rowptr, const int
     const int nv = vcnt[k];
     for (int p = s + threadIdx.x; p < e; p += blockDim.x) {
         const int c = colidx[p];
-        keys[o + (p - s)] = (uint32_t)node_chunk[c] * (uint32_t)kKv + (uint32_t)vmap[k * 8 + (c % nv)];
+        const uint32_t slot = (uint32_t)vmap[k * 8 + (c % nv)];
+        keys[o + (p - s)] = ((slot >> 8) * (uint32_t)n_chunks + (uint32_t)node_chunk[c]) * (uint32_t)kKv + (slot & 255u);
         src[o + (p - s)] = p;
     }
 }
 
 __global__ void r2_hub_gather_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ src,
                                      const int32_t* __restrict__ colidx, const float* __restrict__ vals, int64_t hub_nnz,
-                                     const int32_t* __restrict__ cstart, int2* __restrict__ hent) {
+                                     int n_chunks, const int32_t* __restrict__ cstart, int2* __restrict__ hent) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= hub_nnz) return;
     const int p = src[i];
-    const int c = (int)(keys[i] / (uint32_t)kKv);
+    const int c = (int)((keys[i] / (uint32_t)kKv) % (uint32_t)n_chunks);
     hent[i] = make_int2((colidx[p] - cstart[c]) * kRowBytes, __float_as_int(vals[p]));
 }
 
-// tab[c][s] = first sorted position with key >= c*256 + s   (s = 256 gives the start of chunk c+1)
-__global__ void r2_hub_table_kernel(const uint32_t* __restrict__ keys, int64_t hub_nnz, int n_chunks, int32_t* __restrict__ tab) {
+// tab[gc][s] = first sorted position with key >= gc*256 + s   (gc = group * n_chunks + chunk; s = 256: start of the next run)
+__global__ void r2_hub_table_kernel(const uint32_t* __restrict__ keys, int64_t hub_nnz, int n_runs, int32_t* __restrict__ tab) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)n_chunks * kHtW) return;
+    if (i >= (int64_t)n_runs * kHtW) return;
     const int c = (int)(i / kHtW);
     int s = (int)(i % kHtW);
     if (s > kKv) s = kKv;
@@ -886,15 +1020,15 @@ __global__ void r2_hub_table_kernel(const uint32_t* __restrict__ keys, int64_t h
     tab[i] = (int32_t)lo;
 }
 
-// offsets relative to the chunk's even-aligned base (16-byte aligned bulk copies) + chunk descriptors
-__global__ void r2_hub_rel_kernel(const int32_t* __restrict__ tab_abs, int n_chunks, const int32_t* __restrict__ cstart,
+// offsets relative to the run's even-aligned base (16-byte aligned bulk copies) + run descriptors
+__global__ void r2_hub_rel_kernel(const int32_t* __restrict__ tab_abs, int n_runs, int n_chunks, const int32_t* __restrict__ cstart,
                                   int32_t* __restrict__ tab, int4* __restrict__ cdesc) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)n_chunks * kHtW) return;
+    if (i >= (int64_t)n_runs * kHtW) return;
     const int c = (int)(i / kHtW), s = (int)(i % kHtW);
     const int base = tab_abs[(int64_t)c * kHtW] & ~1;
     tab[i] = tab_abs[i] - base;
-    if (s == 0) cdesc[c] = make_int4(base, ((tab_abs[(int64_t)c * kHtW + kKv] - base) + 1) & ~1, cstart[c], 0);
+    if (s == 0) cdesc[c] = make_int4(base, ((tab_abs[(int64_t)c * kHtW + kKv] - base) + 1) & ~1, cstart[c % n_chunks], 0);
 }
 
 __global__ void r2_row_len_kernel(const int32_t* __restrict__ rowptr, int64_t n, int64_t n_pad, int hub_threshold, int32_t* __restrict__ len) {
@@ -908,24 +1042,37 @@ __global__ void r2_row_len_kernel(const int32_t* __restrict__ rowptr, int64_t n,
     len[r] = l;
 }
 
-// compact copy of the short rows' entries (already reordered: other columns | hub columns) + row / job descriptors
-__global__ void r2_doc_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rsplit,
-                                   const int2* __restrict__ dent, const int32_t* __restrict__ start, int64_t n, int64_t n_pad,
+__global__ void r2_slot_kernel(const int32_t* __restrict__ hub_rows, int Kh, int32_t* __restrict__ slot_of) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < Kh) slot_of[hub_rows[k]] = k;
+}
+
+// Compact copy of the short rows' entries + row / job descriptors.  Each row lists its non-hub columns first ({column, value}:
+// the self loop, or a global gather) and its hub columns after ({hub index * 128, value}: the resident rows); within each
+// part the ascending column order of the CSR is kept, so a document row of a document-topic graph (self loop, then topics)
+// is summed in exactly the reference's storage order.
+__global__ void r2_doc_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                   const int32_t* __restrict__ slot_of, const int32_t* __restrict__ start, int64_t n, int64_t n_pad,
                                    int hub_threshold, int2* __restrict__ dent2, int2* __restrict__ rdesc, int2* __restrict__ jdesc) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_pad) return;
     const int64_t j0 = r / kJobRows * kJobRows;
     const int jbase = start[j0] & ~1;
-    int2 rd = make_int2(0, 0);
+    int2 rd = make_int2(0, kNotShort);
     if (r < n) {
         const int s = rowptr[r], e = rowptr[r + 1];
         const int len = e - s;
-        if (len > 0 && len <= hub_threshold) {
-            const int n_other = rsplit[r] - s;
+        if (len <= hub_threshold) {  // (a row without entries is a short row too: its output is the epilogue of zero)
             const int o = start[r];
-            for (int p = 0; p < len; ++p) {
-                const int2 en = dent[s + p];
-                dent2[o + p] = make_int2(p < n_other ? en.x : en.x * kRowBytes, en.y);
+            int w = o;
+            for (int p = s; p < e; ++p) {
+                const int c = colidx[p];
+                if (slot_of[c] < 0) dent2[w++] = make_int2(c, __float_as_int(vals[p]));
+            }
+            const int n_other = w - o;
+            for (int p = s; p < e; ++p) {
+                const int sl = slot_of[colidx[p]];
+                if (sl >= 0) dent2[w++] = make_int2(sl * kHubEnc, __float_as_int(vals[p]));
             }
             rd = make_int2(o - jbase, (len << 16) | n_other);
         }
@@ -945,8 +1092,74 @@ int env_int2(const char* name, int dflt) {
 size_t hub_smem(int T, int cap_hub) {
     return 2 * ((size_t)T * kRowBytes + align128((size_t)cap_hub * 8) + align128((size_t)kHtW * 4));
 }
-size_t doc_smem(int Kh, int cap_doc, int stages = kStages) {
-    return align128((size_t)Kh * kRowBytes) + (size_t)stages * (align128((size_t)cap_doc * 8) + (size_t)kJobRows * 8);
+size_t doc_smem(int Kh, int cap_doc, int nq, int stages) {
+    const int r = 4 / nq;  // plan jobs per super job (rows per group)
+    return align128((size_t)Kh * 128 * nq) + (size_t)stages * (align128((size_t)cap_doc * 8 * r) + (size_t)kJobRows * 8 * r + 128);
+}
+
+// float4 chunks per lane and ring depth of the document role: the widest slice whose resident rows leave room for a ring of
+// at least three stages, else two stages
+bool pick_doc_cfg(int Kh, int cap_doc, int force_nq, int* nq_out, int* stages_out) {
+    for (int min_stages = 3; min_stages >= 2; --min_stages)
+        for (int nq = 4; nq >= 1; nq >>= 1) {
+            if (force_nq > 0 && nq != force_nq) continue;
+            for (int stages = kStages; stages >= min_stages; --stages)
+                if (doc_smem(Kh, cap_doc, nq, stages) + 256 <= kSmemMax) {
+                    *nq_out = nq;
+                    *stages_out = stages;
+                    return true;
+                }
+        }
+    return false;
+}
+
+// Slots: split the heaviest hub rows into the spare slots of G groups, deal the pieces to the G * 16 warps longest-first.
+struct SlotDeal {
+    std::vector<int32_t> vcnt, vmap;
+    double max_warp = 0.0;
+};
+SlotDeal deal_slots(const std::vector<double>& len, int G) {
+    const int Kh = (int)len.size();
+    SlotDeal d;
+    d.vcnt.assign((size_t)Kh, 1);
+    d.vmap.assign((size_t)Kh * 8, 0);
+    int spare = G * kKv - Kh;
+    while (spare > 0) {
+        int best = -1;
+        for (int k = 0; k < Kh; ++k)
+            if (d.vcnt[(size_t)k] < 8 && (best < 0 || len[(size_t)k] / d.vcnt[(size_t)k] > len[(size_t)best] / d.vcnt[(size_t)best])) best = k;
+        if (best < 0) break;
+        d.vcnt[(size_t)best] += 1;
+        --spare;
+    }
+    struct Piece { double w; int k, j; };
+    std::vector<Piece> pieces;
+    for (int k = 0; k < Kh; ++k)
+        for (int j = 0; j < d.vcnt[(size_t)k]; ++j) pieces.push_back(Piece{len[(size_t)k] / d.vcnt[(size_t)k], k, j});
+    std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) { return x.w > y.w; });
+    const int W = G * kWarps;
+    std::vector<double> load((size_t)W, 0.0);
+    std::vector<int> used((size_t)W, 0);
+    for (const Piece& pc : pieces) {
+        int best = -1;
+        for (int w = 0; w < W; ++w)
+            if (used[(size_t)w] < kKPW && (best < 0 || load[(size_t)w] < load[(size_t)best])) best = w;
+        d.vmap[(size_t)pc.k * 8 + pc.j] = best * kKPW + used[(size_t)best];  // = group * 256 + warp * 16 + position
+        used[(size_t)best] += 1;
+        load[(size_t)best] += pc.w;
+    }
+    for (int w = 0; w < W; ++w) d.max_warp = std::max(d.max_warp, load[(size_t)w]);
+    return d;
+}
+
+void read_knobs(tg_plan* pl) {
+    pl->r2_min_rows = env_int2("TG_ROLES2_MIN_ROWS", 16384);
+    pl->r2_narrow_min_rows = env_int2("TG_ROLES2_NARROW_MIN_ROWS", 131072);
+    pl->r2_hub_pct = env_int2("TG_ROLES2_HUB_PCT", -1);
+    pl->r2_narrow_hub_pct = env_int2("TG_ROLES2_NARROW_HUB_PCT", -1);
+    pl->r2_only_role = env_int2("TG_ROLES_ONLY", 0);
+    pl->r2_narrow_lane = env_int2("TG_ROLES2_NARROW_LANE", 1);
+    pl->r2_narrow_ok = env_int2("TG_ROLES2_NARROW", 1) != 0;
 }
 
 }  // namespace
@@ -962,27 +1175,33 @@ void roles2_plan_free(tg_plan* pl) {
     pl->r2_rect = 0;
 }
 
-// Builds the sub-plan of the warp-per-slot kernels on top of the streaming sub-plan (which provides colidx2 / rsplit, the
-// per-row reordered entry copy).  d_slot_of: device [n] hub index of every node or -1; h_hub_rows: host [n_hub].
+// Builds the sub-plan of the role kernels.  h_hub_rows: host [n_hub].
 int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx, const float* vals, const int32_t* h_rowptr,
-                      const int32_t* d_slot_of, const int32_t* h_hub_rows, cudaStream_t st) {
-    (void)d_slot_of;
+                      const int32_t* h_hub_rows, cudaStream_t st) {
     pl->r2_ok = false;
+    read_knobs(pl);
     if (env_int2("TG_ROLES2", 1) == 0) return TG_OK;
     const bool all_hub = pl->r2_rect == 2;  // rectangular [K x N] operand whose rows are all hub rows: hub side only
-    if (pl->n_hub < 1 || pl->n_hub > kKv) return TG_OK;
-    if (!all_hub && (!pl->stream_ok || !pl->colidx2 || !pl->rsplit)) return TG_OK;
+    if (!colidx || !vals || pl->nnz == 0) return TG_OK;
+    if (pl->n_hub < 1 || pl->n_hub > kMaxGroups * kKv) return TG_OK;
+    if (pl->hub_threshold > 16383) return TG_OK;  // row descriptors keep the entry count of a short row in 15 bits
+    if (!all_hub) {
+        if (pl->n_rows != pl->n_cols) return TG_OK;
+        if (pl->hub_nnz * 8 < pl->nnz) return TG_OK;  // only worth it when the hub rows carry a real share of the entries
+    }
     const int64_t n = pl->n_rows;
     const int64_t n_nodes = pl->n_cols;     // nodes the hub role streams over (= n for the square graphs)
     const int Kh = pl->n_hub;
     const int64_t hub_nnz = pl->hub_nnz;
     if (hub_nnz >= (int64_t)0x7fffffff) return TG_OK;
 
-    // ---- slots: split the heaviest hub rows into the spare slots, deal the pieces to the 16 warps longest-first ----
-    std::vector<int32_t> vcnt((size_t)Kh, 1), vmap((size_t)Kh * 8, 0);
+    // ---- slot groups ------------------------------------------------------------------------------------------------------
+    // One more group than strictly needed buys spare slots for splitting the heavy rows (balance) at the price of one more
+    // reader of every tile of B.  Cost model in shared-memory wavefronts per 128-column slice, summed over the hub CTAs of a
+    // chunk lane: 5 per entry on the critical warp (x 16 warps that wait for it) + 4 per node for the TMA fill, per group.
     std::vector<int64_t> hub_ofs((size_t)Kh);
+    std::vector<double> len((size_t)Kh);
     {
-        std::vector<double> len((size_t)Kh);
         int64_t run = 0;
         for (int k = 0; k < Kh; ++k) {
             const int32_t r = h_hub_rows[k];
@@ -990,46 +1209,48 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
             len[(size_t)k] = (double)(h_rowptr[(size_t)r + 1] - h_rowptr[(size_t)r]);
             run += h_rowptr[(size_t)r + 1] - h_rowptr[(size_t)r];
         }
-        int spare = kKv - Kh;
-        while (spare > 0) {
-            int best = -1;
-            for (int k = 0; k < Kh; ++k)
-                if (vcnt[(size_t)k] < 8 && (best < 0 || len[(size_t)k] / vcnt[(size_t)k] > len[(size_t)best] / vcnt[(size_t)best])) best = k;
-            if (best < 0) break;
-            vcnt[(size_t)best] += 1;
-            --spare;
-        }
-        struct Piece { double w; int k, j; };
-        std::vector<Piece> pieces;
-        for (int k = 0; k < Kh; ++k)
-            for (int j = 0; j < vcnt[(size_t)k]; ++j) pieces.push_back(Piece{len[(size_t)k] / vcnt[(size_t)k], k, j});
-        std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) { return x.w > y.w; });
-        double load[kWarps] = {0};
-        int used[kWarps] = {0};
-        for (const Piece& pc : pieces) {
-            int best = -1;
-            for (int w = 0; w < kWarps; ++w)
-                if (used[w] < kKPW && (best < 0 || load[w] < load[best])) best = w;
-            vmap[(size_t)pc.k * 8 + pc.j] = best * kKPW + used[best];
-            used[best] += 1;
-            load[best] += pc.w;
+    }
+    const int g_min = (Kh + kKv - 1) / kKv;
+    const int g_force = env_int2("TG_ROLES2_GROUPS", 0);
+    SlotDeal deal;
+    int G = 0;
+    {
+        double best_cost = 0.0;
+        for (int g = g_min; g <= std::min(g_min + 1, kMaxGroups); ++g) {
+            if (g_force > 0 && g != g_force && g_force >= g_min && g_force <= kMaxGroups) continue;
+            SlotDeal d = deal_slots(len, g);
+            const double cost = (double)g * (5.0 * kWarps * d.max_warp + 4.0 * (double)n_nodes);
+            if (G == 0 || cost < best_cost) {
+                best_cost = cost;
+                G = g;
+                deal = std::move(d);
+            }
         }
     }
+    const std::vector<int32_t>& vcnt = deal.vcnt;
+    const std::vector<int32_t>& vmap = deal.vmap;
 
     int64_t* d_ofs = nullptr;
     uint32_t *keys_a = nullptr, *keys_b = nullptr;
-    int32_t *src_a = nullptr, *src_b = nullptr, *tab_abs = nullptr, *d_len = nullptr, *d_start = nullptr;
+    int32_t *src_a = nullptr, *src_b = nullptr, *tab_abs = nullptr, *d_len = nullptr, *d_start = nullptr, *d_slot = nullptr;
     void* tmp = nullptr;
     cudaError_t e = cudaSuccess;
     auto release_tmp = [&]() {
         cudaFree(d_ofs); cudaFree(keys_a); cudaFree(keys_b); cudaFree(src_a); cudaFree(src_b); cudaFree(tab_abs);
-        cudaFree(d_len); cudaFree(d_start); cudaFree(tmp);
-        d_ofs = nullptr; keys_a = keys_b = nullptr; src_a = src_b = tab_abs = d_len = d_start = nullptr; tmp = nullptr;
+        cudaFree(d_len); cudaFree(d_start); cudaFree(d_slot); cudaFree(tmp);
+        d_ofs = nullptr; keys_a = keys_b = nullptr; src_a = src_b = tab_abs = d_len = d_start = d_slot = nullptr; tmp = nullptr;
     };
     auto fail = [&](cudaError_t err, const char* what) {
         release_tmp();
         roles2_plan_free(pl);
         return cuda_fail(err, what, __FILE__, __LINE__);
+    };
+    auto give_up = [&]() {  // the layout does not apply: not an error
+        release_tmp();
+        const int32_t rect = pl->r2_rect;
+        roles2_plan_free(pl);
+        pl->r2_rect = rect;
+        return TG_OK;
     };
 #define TG_TRY(call) do { e = (call); if (e != cudaSuccess) return fail(e, #call); } while (0)
     TG_TRY(cudaMalloc((void**)&d_ofs, (size_t)Kh * sizeof(int64_t)));
@@ -1045,9 +1266,9 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     TG_TRY(cudaMalloc((void**)&pl->r2_hent, ((size_t)hub_nnz + 2) * sizeof(int2)));
 
     // ---- hub side: variable-height chunks ------------------------------------------------------------------------------
-    // A chunk is a run of consecutive nodes with at most T rows AND at most `cap` hub entries, so that its tile of B and
-    // its entries always fit one shared-memory stage: document ranges are cut by the row limit, the dense topic-topic
-    // block (every hub node carries Kh entries) by the entry limit.
+    // A chunk is a run of consecutive nodes with at most T rows AND at most `cap` hub entries (all groups together), so that
+    // its tile of B and the entries of any one group always fit one shared-memory stage: document ranges are cut by the row
+    // limit, the dense topic-topic block (every hub node carries Kh entries) by the entry limit.
     const double avg_deg = (double)hub_nnz / (double)n_nodes;
     static const int kTs[] = {192, 176, 160, 144, 128, 96, 64, 32};
     const int t_first = env_int2("TG_ROLES2_T", 192);
@@ -1061,11 +1282,7 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         cap = cap_fit;
         break;
     }
-    if (T == 0) {
-        release_tmp();
-        roles2_plan_free(pl);
-        return TG_OK;
-    }
+    if (T == 0) return give_up();
     std::vector<int32_t> h_deg((size_t)n_nodes), node_chunk((size_t)n_nodes), cstart;
     {
         int32_t* d_deg = nullptr;
@@ -1097,11 +1314,8 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     }
     const int n_chunks = (int)cstart.size();
     cstart.push_back((int32_t)n_nodes);
-    if ((uint64_t)n_chunks * (uint64_t)kKv >= 0xFFFFFFFFull) {
-        release_tmp();
-        roles2_plan_free(pl);
-        return TG_OK;
-    }
+    const int64_t n_runs = (int64_t)G * n_chunks;  // (group, chunk) runs of the entry list
+    if ((uint64_t)n_runs * (uint64_t)kKv >= 0xFFFFFFFFull) return give_up();
     {
         int32_t *d_node_chunk = nullptr, *d_cstart = nullptr;
         auto drop = [&]() { cudaFree(d_node_chunk); cudaFree(d_cstart); };
@@ -1110,25 +1324,25 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         TG_TRY2(cudaMalloc((void**)&d_cstart, (size_t)(n_chunks + 1) * sizeof(int32_t)));
         TG_TRY2(cudaMemcpyAsync(d_node_chunk, node_chunk.data(), (size_t)n_nodes * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         TG_TRY2(cudaMemcpyAsync(d_cstart, cstart.data(), (size_t)(n_chunks + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        r2_hub_keys_kernel<<<Kh, 256, 0, st>>>(rowptr, colidx, pl->hub_rows, d_ofs, d_node_chunk, pl->r2_vmap, pl->r2_vcnt, keys_a, src_a);
+        r2_hub_keys_kernel<<<Kh, 256, 0, st>>>(rowptr, colidx, pl->hub_rows, d_ofs, d_node_chunk, n_chunks, pl->r2_vmap, pl->r2_vcnt, keys_a, src_a);
         TG_TRY2(cudaGetLastError());
         size_t tmp_bytes = 0;
         int end_bit = 1;
-        while (end_bit < 32 && (1ull << end_bit) < (uint64_t)n_chunks * kKv) ++end_bit;
+        while (end_bit < 32 && (1ull << end_bit) < (uint64_t)n_runs * kKv) ++end_bit;
         TG_TRY2(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, src_a, src_b, (int)hub_nnz, 0, end_bit, st));
         TG_TRY2(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
-        // stable: inside a (chunk, slot) run the entries keep their column order
+        // stable: inside a (group, chunk, slot) run the entries keep their column order
         TG_TRY2(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_a, keys_b, src_a, src_b, (int)hub_nnz, 0, end_bit, st));
-        const int64_t tab_n = (int64_t)n_chunks * kHtW;
+        const int64_t tab_n = n_runs * kHtW;
         TG_TRY2(cudaMalloc((void**)&tab_abs, (size_t)tab_n * sizeof(int32_t)));
         TG_TRY2(cudaMalloc((void**)&pl->r2_htab, (size_t)tab_n * sizeof(int32_t)));
-        TG_TRY2(cudaMalloc((void**)&pl->r2_cdesc, (size_t)n_chunks * sizeof(int4)));
-        r2_hub_table_kernel<<<(unsigned)ceil_div64(tab_n, 256), 256, 0, st>>>(keys_b, hub_nnz, n_chunks, tab_abs);
+        TG_TRY2(cudaMalloc((void**)&pl->r2_cdesc, (size_t)n_runs * sizeof(int4)));
+        r2_hub_table_kernel<<<(unsigned)ceil_div64(tab_n, 256), 256, 0, st>>>(keys_b, hub_nnz, (int)n_runs, tab_abs);
         TG_TRY2(cudaGetLastError());
-        r2_hub_rel_kernel<<<(unsigned)ceil_div64(tab_n, 256), 256, 0, st>>>(tab_abs, n_chunks, d_cstart, pl->r2_htab, pl->r2_cdesc);
+        r2_hub_rel_kernel<<<(unsigned)ceil_div64(tab_n, 256), 256, 0, st>>>(tab_abs, (int)n_runs, n_chunks, d_cstart, pl->r2_htab, pl->r2_cdesc);
         TG_TRY2(cudaGetLastError());
         TG_TRY2(cudaMemsetAsync(pl->r2_hent, 0, ((size_t)hub_nnz + 2) * sizeof(int2), st));
-        r2_hub_gather_kernel<<<(unsigned)ceil_div64(hub_nnz, 256), 256, 0, st>>>(keys_b, src_b, colidx, vals, hub_nnz, d_cstart, pl->r2_hent);
+        r2_hub_gather_kernel<<<(unsigned)ceil_div64(hub_nnz, 256), 256, 0, st>>>(keys_b, src_b, colidx, vals, hub_nnz, n_chunks, d_cstart, pl->r2_hent);
         TG_TRY2(cudaGetLastError());
         TG_TRY2(cudaStreamSynchronize(st));
 #undef TG_TRY2
@@ -1136,7 +1350,11 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         pl->r2_T = T;
         pl->r2_n_chunks = n_chunks;
         pl->r2_cap_hub = cap;
+        pl->r2_groups = G;
     }
+    // the sort scratch is not needed any more: release it before the document side allocates
+    cudaFree(keys_a); cudaFree(keys_b); cudaFree(src_a); cudaFree(src_b); cudaFree(tab_abs); cudaFree(tmp);
+    keys_a = keys_b = nullptr; src_a = src_b = tab_abs = nullptr; tmp = nullptr;
 
     if (all_hub) {  // no short rows: the hub side is the whole plan
         release_tmp();
@@ -1148,13 +1366,16 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     const int64_t n_jobs = ceil_div64(n, kJobRows);
     const int64_t n_pad = n_jobs * kJobRows;
     const int64_t doc_nnz = pl->nnz - hub_nnz;
+    TG_TRY(cudaMalloc((void**)&d_slot, (size_t)n * sizeof(int32_t)));
+    TG_TRY(cudaMemsetAsync(d_slot, 0xff, (size_t)n * sizeof(int32_t), st));
+    r2_slot_kernel<<<(unsigned)ceil_div64(Kh, 256), 256, 0, st>>>(pl->hub_rows, Kh, d_slot);
+    TG_TRY(cudaGetLastError());
     TG_TRY(cudaMalloc((void**)&d_len, (size_t)(n_pad + 1) * sizeof(int32_t)));
     TG_TRY(cudaMalloc((void**)&d_start, (size_t)(n_pad + 1) * sizeof(int32_t)));
     r2_row_len_kernel<<<(unsigned)ceil_div64(n_pad + 1, 256), 256, 0, st>>>(rowptr, n, n_pad, pl->hub_threshold, d_len);
     TG_TRY(cudaGetLastError());
     size_t scan_bytes = 0;
     TG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_len, d_start, (int)(n_pad + 1), st));
-    cudaFree(tmp); tmp = nullptr;
     TG_TRY(cudaMalloc(&tmp, scan_bytes ? scan_bytes : 1));
     TG_TRY(cub::DeviceScan::ExclusiveSum(tmp, scan_bytes, d_len, d_start, (int)(n_pad + 1), st));
     TG_TRY(cudaMalloc((void**)&pl->r2_dent, ((size_t)doc_nnz + 2) * sizeof(int2)));
@@ -1162,9 +1383,8 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     TG_TRY(cudaMalloc((void**)&pl->r2_rdesc, (size_t)n_pad * sizeof(int2)));
     TG_TRY(cudaMalloc((void**)&pl->r2_jdesc, (size_t)(n_jobs + 8) * sizeof(int2)));  // padded: the lane-per-row kernel copies 8 at a time
     TG_TRY(cudaMemsetAsync(pl->r2_jdesc, 0, (size_t)(n_jobs + 8) * sizeof(int2), st));
-    r2_doc_fill_kernel<<<(unsigned)ceil_div64(n_pad, 256), 256, 0, st>>>(rowptr, pl->rsplit, reinterpret_cast<const int2*>(pl->colidx2),
-                                                                          d_start, n, n_pad, pl->hub_threshold, pl->r2_dent,
-                                                                          pl->r2_rdesc, pl->r2_jdesc);
+    r2_doc_fill_kernel<<<(unsigned)ceil_div64(n_pad, 256), 256, 0, st>>>(rowptr, colidx, vals, d_slot, d_start, n, n_pad, pl->hub_threshold,
+                                                                          pl->r2_dent, pl->r2_rdesc, pl->r2_jdesc);
     TG_TRY(cudaGetLastError());
     std::vector<int2> h_jdesc((size_t)n_jobs);
     TG_TRY(cudaMemcpyAsync(h_jdesc.data(), pl->r2_jdesc, (size_t)n_jobs * sizeof(int2), cudaMemcpyDeviceToHost, st));
@@ -1175,21 +1395,20 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     release_tmp();
     pl->r2_n_jobs = (int32_t)n_jobs;
     pl->r2_cap_doc = cap_doc;
-    if (doc_smem(Kh, cap_doc) + 256 > kSmemMax) {
-        roles2_plan_free(pl);
-        return TG_OK;
-    }
+    int nq = 0, stages = 0;
+    if (!pick_doc_cfg(Kh, cap_doc, env_int2("TG_ROLES2_NQ", 0), &nq, &stages)) return give_up();
+    pl->r2_nq = nq;
+    pl->r2_stages = stages;
     pl->r2_ok = true;
     return TG_OK;
 }
 
 bool roles2_applicable(const tg_plan* pl, const StreamCall& c) {
     if (!pl || !pl->r2_ok || pl->r2_rect != 0) return false;
-    if (env_int2("TG_ROLES2", 1) == 0) return false;
     if (c.n_feat < 64 || c.n_feat % 4 != 0 || c.n_feat > 1024) return false;
     // below ~16 K rows a launch is a few microseconds of work and the 148-CTA prologue (resident hub rows, barriers, TMA
-    // descriptors) costs more than it saves: R8 shape 0.150 vs 0.113 ms per captured step with the first-generation kernels
-    if (pl->n_rows < (int64_t)env_int2("TG_ROLES2_MIN_ROWS", 16384)) return false;
+    // descriptors) costs more than it saves (R8 shape: 0.150 vs 0.113 ms per captured step on the gather kernel)
+    if (pl->n_rows < (int64_t)pl->r2_min_rows) return false;
     if (c.ldb % 4 != 0 || !aligned16(c.B) || !encode_tiled_fn()) return false;
     return true;
 }
@@ -1197,76 +1416,125 @@ bool roles2_applicable(const tg_plan* pl, const StreamCall& c) {
 size_t roles2_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
     if (!pl || !pl->r2_ok) return 0;
     if (pl->r2_rect == 1) return 16;
-    if (pl->r2_rect == 2) return (size_t)kNumSM * kKv * ((size_t)((n_feat + 3) / 4) * 4) * sizeof(float) + 16;
     const size_t ld = (size_t)((n_feat + 3) / 4) * 4;
-    // per-CTA hub partials + the bit-packed dropout keep mask (n x n_feat / 8 bytes)
-    return (size_t)kNumSM * kKv * ld * sizeof(float) + 16 + (size_t)pl->n_rows * (((ld + kFT - 1) / kFT) * 16) + 256;
+    // per-CTA hub partials: (chunk lanes x groups) <= 148 CTAs of 256 slots each
+    const size_t part = (size_t)kNumSM * kKv * ld * sizeof(float) + 16;
+    if (pl->r2_rect == 2) return part;
+    // + the bit-packed dropout keep mask (four words per row and 128 columns)
+    return part + (size_t)pl->n_rows * (((ld + kFT - 1) / kFT) * 16) + 256;
 }
 
-int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st) {
-    R2Args a;
+int roles2_launches(const tg_plan* pl, const StreamCall& c, bool philox) {
+    if (roles2_rect_applicable(pl, c) && !(pl->r2_rect == 1 && philox)) return pl->r2_rect;  // resident-table product: one kernel; all-hub product: hub role + finish
+    if (roles2_applicable(pl, c)) return 2 + (philox ? 1 : 0);
+    if (roles2_narrow_applicable(pl, c)) return 2;
+    return 0;
+}
+
+namespace {
+
+// Split of the 148 SMs between the roles.  Both roles are bound by the shared-memory pipe, so the split follows their
+// wavefront counts (128-byte shared-memory transactions per 128 columns): hub role 5 per entry (row of B + broadcast
+// entry) + 4 per node and group (TMA fill), document role 4 per hub-column entry + ~14 per row and slice (entries, self loop,
+// store), weighted by the pipe utilisation each role reaches (82 % / 67 %, profiles/r01_roles2_*_only_full.md).  C3: 44 %
+// hub CTAs, the measured optimum.  hub_unit / doc_unit: CTAs per chunk lane / job lane.
+void split_sms(double hub_w, double doc_w, int hub_unit, int doc_unit, int n_chunks, int n_jobs, int forced_pct, int* hub_lanes_out,
+               int* doc_lanes_out) {
+    int best_h = 1, best_d = 1;
+    double best = -1.0;
+    if (forced_pct >= 0) {
+        best_h = std::max(1, (kNumSM * forced_pct / 100) / hub_unit);
+        best_d = std::max(1, (kNumSM - best_h * hub_unit) / doc_unit);
+    } else {
+        for (int h = 1; h * hub_unit + doc_unit <= kNumSM; ++h) {
+            const int d = (kNumSM - h * hub_unit) / doc_unit;
+            const double t = std::max(hub_w / (double)(h * hub_unit), doc_w / (double)(d * doc_unit));
+            if (best < 0.0 || t < best) {
+                best = t;
+                best_h = h;
+                best_d = d;
+            }
+        }
+    }
+    *hub_lanes_out = std::min(best_h, std::max(n_chunks, 1));
+    *doc_lanes_out = std::min(best_d, std::max(n_jobs, 1));
+}
+
+template <int NQ>
+int launch_wide(const R2Args& a, const EpiStore& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem, unsigned grid,
+                cudaStream_t st) {
+    TG_CUDA(cudaFuncSetAttribute(roles2_kernel<NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roles2_kernel<NQ, false><<<grid, kThreads, smem, st>>>(a, epi, tmap, tmap_job);
+    TG_LAUNCH_CHECK();
+    return TG_OK;
+}
+template <int NQ>
+int launch_table(const R2Args& a, const EpiStore& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem, unsigned grid,
+                 cudaStream_t st) {
+    TG_CUDA(cudaFuncSetAttribute(roles2_kernel<NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roles2_kernel<NQ, true><<<grid, kThreads, smem, st>>>(a, epi, tmap, tmap_job);
+    TG_LAUNCH_CHECK();
+    return TG_OK;
+}
+
+void fill_common(R2Args& a, const tg_plan* pl, const StreamCall& c) {
+    memset(&a, 0, sizeof(a));
     a.hent = pl->r2_hent; a.htab = pl->r2_htab; a.cdesc = pl->r2_cdesc;
     a.T = pl->r2_T; a.n_chunks = pl->r2_n_chunks; a.cap_hub = pl->r2_cap_hub;
+    a.groups = pl->r2_groups; a.Kv = pl->r2_groups * kKv;
     a.dent = pl->r2_dent; a.rdesc = pl->r2_rdesc; a.jdesc = pl->r2_jdesc;
     a.n_jobs = pl->r2_n_jobs; a.cap_doc = pl->r2_cap_doc;
     a.hub_rows = pl->hub_rows; a.Kh = pl->n_hub;
     a.B = c.B; a.ldb = c.ldb; a.n = pl->n_rows; a.n_chunks4 = c.n_feat / 4;
     a.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(c.workspace) + 15u) & ~(uintptr_t)15u);
     a.ldp = (int64_t)((c.n_feat + 3) / 4) * 4;
-    const int slices = (c.n_feat + kFT - 1) / kFT;
-    a.hub_slices = a.doc_slices = slices;
+    a.keep_bits = nullptr;
+    a.n_stages = pl->r2_stages;
+    a.only_role = pl->r2_only_role;
+}
+
+}  // namespace
+
+int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st) {
+    R2Args a;
+    fill_common(a, pl, c);
+    const int nq = pl->r2_nq;
+    const int slices = (c.n_feat + kFT - 1) / kFT;               // hub role: 128-column slices
+    const int dslices = (c.n_feat + 32 * nq - 1) / (32 * nq);    // document role: 32 * nq columns
+    a.hub_slices = slices;
+    a.doc_slices = dslices;
     // Philox dropout: the keep mask is drawn by a separate ALU-bound kernel into a bit-packed side buffer (1 bit per
     // element) instead of inside the document role, whose CTAs have no issue slots to spare (ncu: the in-kernel RNG
     // cost 0.4 ms at 1M x 256).  Same mask, bit for bit, as the in-kernel definition (tg_common.cuh).
-    a.keep_bits = nullptr;
-    a.table_mode = 0;
-    a.n_stages = kStages;
-    if (epi.drop_mode == 1 && env_int2("TG_ROLES2_BITMASK", 1) != 0) {
+    if (epi.drop_mode == 1) {
         const size_t part_bytes = ((size_t)kNumSM * kKv * a.ldp * sizeof(float) + 16 + 255) & ~(size_t)255;
-        const size_t mask_bytes = (size_t)pl->n_rows * (size_t)slices * 16;  // four words per row and 128-column slice
-        if (c.workspace_bytes >= part_bytes + mask_bytes + 16) {
-            uint32_t* bits = reinterpret_cast<uint32_t*>(
-                (reinterpret_cast<uintptr_t>(c.workspace) + part_bytes + 15u) & ~(uintptr_t)15u);
-            const int n_blk = slices * 2;  // 64-column blocks, padded to whole slices
+        const size_t mask_bytes = (size_t)pl->n_rows * (size_t)slices * 16;  // four words per row and 128 columns
+        TG_REQUIRE(c.workspace_bytes >= part_bytes + mask_bytes + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B (dropout mask)",
+                   c.workspace_bytes, part_bytes + mask_bytes + 16);
+        uint32_t* bits = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(c.workspace) + part_bytes + 15u) & ~(uintptr_t)15u);
+        if (epi.keep_thr == kDropoutHalfThr) {
+            const int n_words = slices * 4;
+            const int64_t th = pl->n_rows * (int64_t)((n_words + 3) / 4);
+            r2_keep_bits_half_kernel<<<(unsigned)ceil_div64(th, 256), 256, 0, st>>>(bits, pl->n_rows, n_words, epi.seed, epi.offset, epi.offset_dev);
+        } else {
+            const int n_blk = slices * 2;  // 64-column blocks, padded to whole 128-column slices
             const int64_t threads = pl->n_rows * (int64_t)n_blk * 8;
-            if (epi.keep_thr == kDropoutHalfThr) {
-                const int n_words = slices * 4;
-                const int64_t th = pl->n_rows * (int64_t)((n_words + 3) / 4);
-                r2_keep_bits_half_kernel<<<(unsigned)ceil_div64(th, 256), 256, 0, st>>>(bits, pl->n_rows, n_words, epi.seed, epi.offset,
-                                                                                        epi.offset_dev);
-            } else {
             int blk_shift = -1;
             for (int sh = 0; sh < 8; ++sh)
                 if ((1 << sh) == n_blk) blk_shift = sh;
             r2_keep_bits_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, st>>>(bits, pl->n_rows, n_blk, blk_shift, epi.keep_thr, epi.seed,
                                                                                     epi.offset, epi.offset_dev);
-            }
-            TG_LAUNCH_CHECK();
-            a.keep_bits = bits;
         }
+        TG_LAUNCH_CHECK();
+        a.keep_bits = bits;
     }
-    // share of the SMs given to the hub role (both fronts must advance together so that the second reader of a row of B
-    // hits L2); the document role also runs the Philox dropout when the epilogue draws the mask itself
-    // Both roles are bound by the shared-memory pipe, so the split follows their wavefront counts (128-byte shared-memory
-    // transactions per column slice): hub role 5 per entry (row of B + broadcast entry) + 4 per node (TMA fill), document
-    // role 4 per hub-column entry + ~14 per row (entries, self loop, store), weighted by the pipe utilisation each role
-    // reaches (82 % / 67 %, profiles/r01_roles2_*_only_full.md).  C3: 44 %, the measured optimum.
-    const double hub_w = (5.0 * (double)pl->hub_nnz + 4.0 * (double)pl->n_rows) / 0.82;
-    const double doc_w = (4.0 * (double)(pl->nnz - pl->hub_nnz - pl->n_rows) + 14.0 * (double)pl->n_rows) / 0.67;
-    int auto_pct = (int)(100.0 * hub_w / (hub_w + doc_w) + 0.5);
-    auto_pct = auto_pct < 10 ? 10 : (auto_pct > 90 ? 90 : auto_pct);
-    if (epi.drop_mode == 1 && !a.keep_bits) auto_pct = auto_pct > 16 ? auto_pct - 6 : auto_pct;  // in-kernel Philox loads the document role
-    const int hub_pct = env_int2("TG_ROLES2_HUB_PCT", auto_pct);
-    int hub_lanes = (kNumSM * hub_pct / 100) / slices;
-    if (hub_lanes < 1) hub_lanes = 1;
-    if (hub_lanes > a.n_chunks) hub_lanes = a.n_chunks;
-    int doc_lanes = (kNumSM - hub_lanes * slices) / slices;
-    if (doc_lanes < 1) doc_lanes = 1;
-    if (doc_lanes > a.n_jobs) doc_lanes = a.n_jobs;
-    a.hub_lanes = hub_lanes;
-    a.doc_lanes = doc_lanes;
-    a.only_role = env_int2("TG_ROLES_ONLY", 0);
-    const size_t need = (size_t)hub_lanes * kKv * a.ldp * sizeof(float);
+    // share of the SMs given to the hub role: both fronts must advance together so that the second reader of a row of B
+    // hits L2 (split_sms)
+    const double hub_w = (5.0 * (double)pl->hub_nnz + 4.0 * (double)a.groups * (double)pl->n_rows) / 0.82;
+    const double doc_w = (4.0 * (double)(pl->nnz - pl->hub_nnz - pl->n_rows) + 14.0 * (4.0 / nq) * (double)pl->n_rows) / 0.67;
+    split_sms(hub_w * slices, doc_w * slices, slices * a.groups, dslices, a.n_chunks, (a.n_jobs + 4 / nq - 1) / (4 / nq), pl->r2_hub_pct,
+              &a.hub_lanes, &a.doc_lanes);
+    const size_t need = (size_t)a.hub_lanes * a.Kv * a.ldp * sizeof(float);
     TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
                c.workspace_bytes, need + 16);
     CUtensorMap tmap;
@@ -1275,14 +1543,16 @@ int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cuda
                "cuTensorMapEncodeTiled failed (TMA tile of the dense operand)");
     CUtensorMap tmap_job;
     memset(&tmap_job, 0, sizeof(tmap_job));
-    TG_REQUIRE(make_tensor_map(&tmap_job, a.B, a.n, c.n_feat, a.ldb, kJobRows, kFT), TG_ERR_UNSUPPORTED,
+    TG_REQUIRE(make_tensor_map(&tmap_job, a.B, a.n, c.n_feat, a.ldb, kJobRows, 32 * nq), TG_ERR_UNSUPPORTED,
                "cuTensorMapEncodeTiled failed (L2 prefetch tile of the dense operand)");
-    size_t smem = std::max(hub_smem(a.T, a.cap_hub), doc_smem(a.Kh, a.cap_doc)) + 128;
-    TG_CUDA(cudaFuncSetAttribute(roles2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((hub_lanes + doc_lanes) * slices);
-    roles2_kernel<false><<<grid, kThreads, smem, st>>>(a, epi, tmap, tmap_job);
-    TG_LAUNCH_CHECK();
-    FinishArgs f{a.partials, a.ldp, hub_lanes, a.Kh, kKv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
+    const size_t smem = std::max(hub_smem(a.T, a.cap_hub), doc_smem(a.Kh, a.cap_doc, nq, a.n_stages)) + 128;
+    const unsigned grid = (unsigned)(a.hub_lanes * a.groups * slices + a.doc_lanes * dslices);
+    int rc = TG_ERR_UNSUPPORTED;
+    if (nq == 4) rc = launch_wide<4>(a, epi, tmap, tmap_job, smem, grid, st);
+    else if (nq == 2) rc = launch_wide<2>(a, epi, tmap, tmap_job, smem, grid, st);
+    else if (nq == 1) rc = launch_wide<1>(a, epi, tmap, tmap_job, smem, grid, st);
+    if (rc != TG_OK) return rc;
+    FinishArgs f{a.partials, a.ldp, a.hub_lanes, a.Kh, a.Kv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
     return finish_run(f, epi, st);
 }
 
@@ -1295,11 +1565,10 @@ static void narrow_smem(const tg_plan* pl, int n_feat, size_t* hub_s, size_t* do
 }
 
 bool roles2_narrow_applicable(const tg_plan* pl, const StreamCall& c) {
-    if (!pl || !pl->r2_ok || pl->r2_rect != 0) return false;
-    if (env_int2("TG_ROLES2", 1) == 0 || env_int2("TG_ROLES2_NARROW", 1) == 0) return false;
+    if (!pl || !pl->r2_ok || pl->r2_rect != 0 || !pl->r2_narrow_ok) return false;
     if (c.n_feat < 4 || c.n_feat > 32 || c.n_feat % 4 != 0) return false;
     // a narrow operand of a small graph is L2 resident and the gather kernel is faster (20NG shape: 0.033 vs 0.052 ms)
-    if (pl->n_rows < (int64_t)env_int2("TG_ROLES2_NARROW_MIN_ROWS", 131072)) return false;
+    if (pl->n_rows < (int64_t)pl->r2_narrow_min_rows) return false;
     if (c.ldb % 4 != 0 || !aligned16(c.B) || !encode_tiled_fn()) return false;
     size_t hub_s, doc_s, lane_s;
     narrow_smem(pl, c.n_feat, &hub_s, &doc_s, &lane_s);
@@ -1309,31 +1578,20 @@ bool roles2_narrow_applicable(const tg_plan* pl, const StreamCall& c) {
 template <class Epi>
 static int roles2_narrow_run_t(const tg_plan* pl, const StreamCall& c, const Epi& epi, cudaStream_t st) {
     R2Args a;
-    a.hent = pl->r2_hent; a.htab = pl->r2_htab; a.cdesc = pl->r2_cdesc;
-    a.T = pl->r2_T; a.n_chunks = pl->r2_n_chunks; a.cap_hub = pl->r2_cap_hub;
-    a.dent = pl->r2_dent; a.rdesc = pl->r2_rdesc; a.jdesc = pl->r2_jdesc;
-    a.n_jobs = pl->r2_n_jobs; a.cap_doc = pl->r2_cap_doc;
-    a.hub_rows = pl->hub_rows; a.Kh = pl->n_hub;
-    a.B = c.B; a.ldb = c.ldb; a.n = pl->n_rows; a.n_chunks4 = c.n_feat / 4;
-    a.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(c.workspace) + 15u) & ~(uintptr_t)15u);
-    a.ldp = (int64_t)((c.n_feat + 3) / 4) * 4;
+    fill_common(a, pl, c);
     a.hub_slices = a.doc_slices = 1;
-    a.keep_bits = nullptr;
-    a.table_mode = 0;
-    a.n_stages = kStages;
     // measured balance points at C3, F = 20: 57 % hub CTAs for the plain product, 52 % when the document role also runs the
     // log-softmax / cross-entropy epilogue
-    const int hub_pct = env_int2("TG_ROLES2_NARROW_HUB_PCT", std::is_same<Epi, EpiLoss>::value ? 52 : 57);
-    int hub_lanes = kNumSM * hub_pct / 100;
+    const int hub_pct = pl->r2_narrow_hub_pct >= 0 ? pl->r2_narrow_hub_pct : (std::is_same<Epi, EpiLoss>::value ? 52 : 57);
+    int hub_lanes = (kNumSM * hub_pct / 100) / a.groups;
     if (hub_lanes < 1) hub_lanes = 1;
     if (hub_lanes > a.n_chunks) hub_lanes = a.n_chunks;
-    int doc_lanes = kNumSM - hub_lanes;
+    int doc_lanes = kNumSM - hub_lanes * a.groups;
     if (doc_lanes < 1) doc_lanes = 1;
     if (doc_lanes > a.n_jobs) doc_lanes = a.n_jobs;
     a.hub_lanes = hub_lanes;
     a.doc_lanes = doc_lanes;
-    a.only_role = env_int2("TG_ROLES_ONLY", 0);
-    const size_t need = (size_t)hub_lanes * kKv * a.ldp * sizeof(float);
+    const size_t need = (size_t)hub_lanes * a.Kv * a.ldp * sizeof(float);
     TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
                c.workspace_bytes, need + 16);
     CUtensorMap tmap;
@@ -1342,8 +1600,8 @@ static int roles2_narrow_run_t(const tg_plan* pl, const StreamCall& c, const Epi
                "cuTensorMapEncodeTiled failed (TMA tile of the narrow dense operand)");
     size_t hub_s, doc_s, lane_s;
     narrow_smem(pl, c.n_feat, &hub_s, &doc_s, &lane_s);
-    const bool lane_rows = c.ldb == c.n_feat && std::max(hub_s, lane_s) + 256 <= kSmemMax && env_int2("TG_ROLES2_NARROW_LANE", 1) != 0;
-    const unsigned grid = (unsigned)(hub_lanes + doc_lanes);
+    const bool lane_rows = c.ldb == c.n_feat && std::max(hub_s, lane_s) + 256 <= kSmemMax && pl->r2_narrow_lane != 0;
+    const unsigned grid = (unsigned)(hub_lanes * a.groups + doc_lanes);
     if (lane_rows) {
         const size_t smem = std::max(hub_s, lane_s) + 128;
         const int n4 = a.n_chunks4;
@@ -1361,7 +1619,7 @@ static int roles2_narrow_run_t(const tg_plan* pl, const StreamCall& c, const Epi
         roles2n_kernel<Epi><<<grid, kThreads, smem, st>>>(a, epi, tmap);
     }
     TG_LAUNCH_CHECK();
-    FinishArgs f{a.partials, a.ldp, hub_lanes, a.Kh, kKv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
+    FinishArgs f{a.partials, a.ldp, hub_lanes, a.Kh, a.Kv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
     return finish_run(f, epi, st);
 }
 
@@ -1373,7 +1631,7 @@ int roles2_narrow_run(const tg_plan* pl, const StreamCall& c, const EpiLoss& epi
 }
 
 // ---- rectangular operands ---------------------------------------------------------------------------------------------------
-// table mode: every entry of a row addresses the resident table (rows of B = the dense weight): {column * 512, value}
+// table mode: every entry of a row addresses the resident table (rows of B = the dense weight): {column * 128, value}
 __global__ void r2_table_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                                      const int32_t* __restrict__ start, int64_t n, int64_t n_pad, int2* __restrict__ dent2,
                                      int2* __restrict__ rdesc, int2* __restrict__ jdesc) {
@@ -1381,14 +1639,12 @@ __global__ void r2_table_fill_kernel(const int32_t* __restrict__ rowptr, const i
     if (r >= n_pad) return;
     const int64_t j0 = r / kJobRows * kJobRows;
     const int jbase = start[j0] & ~1;
-    int2 rd = make_int2(0, 0);
+    int2 rd = make_int2(0, kNotShort);
     if (r < n) {
         const int s = rowptr[r], len = rowptr[r + 1] - s;
-        if (len > 0) {
-            const int o = start[r];
-            for (int p = 0; p < len; ++p) dent2[o + p] = make_int2(colidx[s + p] * kRowBytes, __float_as_int(vals[s + p]));
-            rd = make_int2(o - jbase, len << 16);
-        }
+        const int o = start[r];
+        for (int p = 0; p < len; ++p) dent2[o + p] = make_int2(colidx[s + p] * kHubEnc, __float_as_int(vals[s + p]));
+        rd = make_int2(o - jbase, len << 16);  // (an all-zero feature row is produced too: the epilogue of zero)
     }
     rdesc[r] = rd;
     if (r == j0) {
@@ -1402,26 +1658,28 @@ __global__ void r2_iota_kernel(int32_t* __restrict__ out, int n) {
     if (i < n) out[i] = i;
 }
 
-// Sub-plans for the two products of a sparse feature matrix X [n x nfeat], nfeat <= 256 (reference layer.py:102 with the
+// Sub-plans for the two products of a sparse feature matrix X [n x nfeat], nfeat <= 1280 (reference layer.py:102 with the
 // topic features of trainer.py:197-238, and its autograd transpose product):
 //   X * W      (plan of X):   every column's row of W is resident in shared memory -> the document role alone;
 //   X^T * dS   (plan of X^T): every row is a hub row                               -> the hub role alone + finish.
 int roles2_rect_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx, const float* vals, const int32_t* h_rowptr,
                            cudaStream_t st) {
+    read_knobs(pl);
     if (pl->r2_ok || env_int2("TG_ROLES2", 1) == 0 || env_int2("TG_ROLES2_RECT", 1) == 0) return TG_OK;
     if (!colidx || !vals || pl->nnz == 0 || pl->nnz >= (int64_t)0x7fffffff) return TG_OK;
-    const int64_t min_rows = env_int2("TG_ROLES2_MIN_ROWS", 16384);
-    if (pl->n_rows <= kKv && pl->n_hub == pl->n_rows && pl->n_cols >= min_rows && pl->n_cols > pl->n_rows) {
+    const int64_t min_rows = pl->r2_min_rows;
+    const int max_k = kMaxGroups * kKv;
+    if (pl->n_rows <= max_k && pl->n_hub == pl->n_rows && pl->n_cols >= min_rows && pl->n_cols > pl->n_rows) {
         // ---- all-hub mode: the hub side of the square plan, over the columns of this matrix ----
         std::vector<int32_t> hub_rows((size_t)pl->n_rows);
         for (int64_t i = 0; i < pl->n_rows; ++i) hub_rows[(size_t)i] = (int32_t)i;
         pl->r2_rect = 2;
-        const int rc = roles2_plan_build(pl, rowptr, colidx, vals, h_rowptr, nullptr, hub_rows.data(), st);
+        const int rc = roles2_plan_build(pl, rowptr, colidx, vals, h_rowptr, hub_rows.data(), st);
         if (rc != TG_OK || !pl->r2_ok) pl->r2_rect = 0;
         return rc;
     }
-    if (pl->n_cols <= kKv && pl->n_hub == 0 && pl->n_rows >= min_rows && pl->n_rows > pl->n_cols) {
-        // ---- table mode: compact entries + row / job descriptors, the ring depth that fits next to the table ----
+    if (pl->n_cols <= max_k && pl->n_hub == 0 && pl->n_rows >= min_rows && pl->n_rows > pl->n_cols && pl->max_row_nnz <= 16383) {
+        // ---- table mode: compact entries + row / job descriptors, the slice width and ring depth that fit next to the table ----
         const int64_t n = pl->n_rows;
         const int64_t n_jobs = ceil_div64(n, kJobRows), n_pad = n_jobs * kJobRows;
         int32_t *d_len = nullptr, *d_start = nullptr;
@@ -1461,13 +1719,12 @@ int roles2_rect_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* co
         for (const int2& d : h_jdesc) cap_doc = std::max(cap_doc, d.y);
         pl->r2_n_jobs = (int32_t)n_jobs;
         pl->r2_cap_doc = cap_doc;
-        int stages = 0;
-        for (int sgs = kStages; sgs >= 2; --sgs)
-            if (doc_smem((int)pl->n_cols, cap_doc, sgs) + 256 <= kSmemMax) { stages = sgs; break; }
-        if (stages == 0) {
+        int nq = 0, stages = 0;
+        if (!pick_doc_cfg((int)pl->n_cols, cap_doc, env_int2("TG_ROLES2_NQ", 0), &nq, &stages)) {
             roles2_plan_free(pl);
             return TG_OK;
         }
+        pl->r2_nq = nq;
         pl->r2_stages = stages;
         pl->r2_rect = 1;
         pl->r2_ok = true;
@@ -1477,7 +1734,6 @@ int roles2_rect_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* co
 
 bool roles2_rect_applicable(const tg_plan* pl, const StreamCall& c) {
     if (!pl || !pl->r2_ok || pl->r2_rect == 0) return false;
-    if (env_int2("TG_ROLES2", 1) == 0 || env_int2("TG_ROLES2_RECT", 1) == 0) return false;
     if (c.n_feat < 64 || c.n_feat % 4 != 0 || c.n_feat > 1024) return false;
     if (c.ldb % 4 != 0 || !aligned16(c.B) || !encode_tiled_fn()) return false;
     return true;
@@ -1485,56 +1741,48 @@ bool roles2_rect_applicable(const tg_plan* pl, const StreamCall& c) {
 
 int roles2_rect_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st) {
     R2Args a;
-    memset(&a, 0, sizeof(a));
-    a.B = c.B; a.ldb = c.ldb; a.n = pl->n_rows; a.n_chunks4 = c.n_feat / 4;
-    a.partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(c.workspace) + 15u) & ~(uintptr_t)15u);
-    a.ldp = (int64_t)((c.n_feat + 3) / 4) * 4;
-    const int slices = (c.n_feat + kFT - 1) / kFT;
-    a.hub_slices = a.doc_slices = slices;
-    a.keep_bits = nullptr;
+    fill_common(a, pl, c);
     a.only_role = 0;
+    const int slices = (c.n_feat + kFT - 1) / kFT;
     CUtensorMap tmap, tmap_job;
     memset(&tmap, 0, sizeof(tmap));
     memset(&tmap_job, 0, sizeof(tmap_job));
     if (pl->r2_rect == 1) {
         // X * W: the rows of W (c.B, n_cols of them) are the resident table; all CTAs run the document role
-        a.dent = pl->r2_dent; a.rdesc = pl->r2_rdesc; a.jdesc = pl->r2_jdesc;
-        a.n_jobs = pl->r2_n_jobs; a.cap_doc = pl->r2_cap_doc;
+        const int nq = pl->r2_nq;
+        const int dslices = (c.n_feat + 32 * nq - 1) / (32 * nq);
+        a.hub_slices = slices;
+        a.doc_slices = dslices;
         a.hub_rows = pl->r2_ident; a.Kh = (int32_t)pl->n_cols;
-        a.table_mode = 1;
-        a.n_stages = pl->r2_stages;
+        a.groups = 1; a.Kv = kKv;
         a.hub_lanes = 0;
-        int doc_lanes = kNumSM / slices;
+        int doc_lanes = kNumSM / dslices;
+        const int n_sj = (a.n_jobs + 4 / nq - 1) / (4 / nq);
         if (doc_lanes < 1) doc_lanes = 1;
-        if (doc_lanes > a.n_jobs) doc_lanes = a.n_jobs;
+        if (doc_lanes > n_sj) doc_lanes = n_sj;
         a.doc_lanes = doc_lanes;
-        const size_t smem = doc_smem(a.Kh, a.cap_doc, a.n_stages) + 128;
-        TG_CUDA(cudaFuncSetAttribute(roles2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        roles2_kernel<true><<<(unsigned)(doc_lanes * slices), kThreads, smem, st>>>(a, epi, tmap, tmap_job);
-        TG_LAUNCH_CHECK();
-        return TG_OK;
+        const size_t smem = doc_smem(a.Kh, a.cap_doc, nq, a.n_stages) + 128;
+        const unsigned grid = (unsigned)(doc_lanes * dslices);
+        if (nq == 4) return launch_table<4>(a, epi, tmap, tmap_job, smem, grid, st);
+        if (nq == 2) return launch_table<2>(a, epi, tmap, tmap_job, smem, grid, st);
+        return launch_table<1>(a, epi, tmap, tmap_job, smem, grid, st);
     }
     // X^T * dS: every row of this matrix is a hub row; all CTAs run the hub role over the rows of c.B, then the finish
-    a.hent = pl->r2_hent; a.htab = pl->r2_htab; a.cdesc = pl->r2_cdesc;
-    a.T = pl->r2_T; a.n_chunks = pl->r2_n_chunks; a.cap_hub = pl->r2_cap_hub;
-    a.hub_rows = pl->hub_rows; a.Kh = pl->n_hub;
-    a.table_mode = 0;
-    a.n_stages = kStages;
+    a.hub_slices = a.doc_slices = slices;
     a.doc_lanes = 0;
-    int hub_lanes = kNumSM / slices;
+    int hub_lanes = kNumSM / (slices * a.groups);
     if (hub_lanes < 1) hub_lanes = 1;
     if (hub_lanes > a.n_chunks) hub_lanes = a.n_chunks;
     a.hub_lanes = hub_lanes;
-    const size_t need = (size_t)hub_lanes * kKv * a.ldp * sizeof(float);
+    const size_t need = (size_t)hub_lanes * a.Kv * a.ldp * sizeof(float);
     TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
                c.workspace_bytes, need + 16);
     TG_REQUIRE(make_tensor_map(&tmap, a.B, pl->n_cols, c.n_feat, a.ldb, a.T, kFT), TG_ERR_UNSUPPORTED,
                "cuTensorMapEncodeTiled failed (TMA tile of the dense operand)");
     const size_t smem = hub_smem(a.T, a.cap_hub) + 128;
-    TG_CUDA(cudaFuncSetAttribute(roles2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    roles2_kernel<false><<<(unsigned)(hub_lanes * slices), kThreads, smem, st>>>(a, epi, tmap, tmap_job);
-    TG_LAUNCH_CHECK();
-    FinishArgs f{a.partials, a.ldp, hub_lanes, a.Kh, kKv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
+    const int rc = launch_wide<4>(a, epi, tmap, tmap_job, smem, (unsigned)(hub_lanes * a.groups * slices), st);
+    if (rc != TG_OK) return rc;
+    FinishArgs f{a.partials, a.ldp, hub_lanes, a.Kh, a.Kv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
     return finish_run(f, epi, st);
 }
 

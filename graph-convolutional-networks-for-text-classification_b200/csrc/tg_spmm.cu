@@ -18,7 +18,7 @@
 #include "tg_epilogue.cuh"
 #include <type_traits>
 
-#include "tg_stream.cuh"
+#include "tg_roles.cuh"
 
 namespace tg {
 
@@ -280,15 +280,6 @@ static int rowwise_loss_vec(const float* Z, int64_t ldz, int64_t n_rows, int n_c
     return TG_ERR_UNSUPPORTED;
 }
 
-static inline int stream_dispatch(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st) {
-    return stream_spmm_store(pl, c, epi, st);
-}
-static inline int stream_dispatch(const tg_plan* pl, const StreamCall& c, const EpiLoss& epi, cudaStream_t st) {
-    return stream_spmm_loss(pl, c, epi, st);
-}
-template <class Epi> struct EpiTraits { static constexpr bool whole_row = false; };
-template <> struct EpiTraits<EpiLoss> { static constexpr bool whole_row = true; };
-
 template <class Epi>
 static int run_spmm(const tg_plan* pl, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                     const float* B, int64_t ldb, int32_t n_feat, bool out_vec4_ok, const Epi& epi, void* workspace,
@@ -298,16 +289,18 @@ static int run_spmm(const tg_plan* pl, const int32_t* rowptr, const int32_t* col
     TG_REQUIRE(n_feat > 0, TG_ERR_INVALID_ARG, "n_feat must be positive");
     TG_REQUIRE(ldb >= n_feat, TG_ERR_INVALID_ARG, "ldb < n_feat");
     const size_t need = tg_plan_workspace_bytes(pl, n_feat);
-    TG_REQUIRE((pl->n_seg == 0 && !pl->stream_ok) || (workspace && workspace_bytes >= need), TG_ERR_WORKSPACE,
+    TG_REQUIRE((pl->n_seg == 0 && !pl->r2_ok) || (workspace && workspace_bytes >= need), TG_ERR_WORKSPACE,
                "workspace %zu B < required %zu B", workspace_bytes, need);
-    {
-        // column-chunk streaming kernel (tg_stream.cu) when the plan carries the sub-plan and the operands qualify
+    if (out_vec4_ok) {
+        // role-specialised streaming kernels (tg_roles2.cu) when the plan carries their sub-plan and the operands qualify
         StreamCall sc{rowptr, vals, B, ldb, n_feat, workspace, workspace_bytes};
         if constexpr (std::is_same<Epi, EpiStore>::value) {
-            // rectangular operands (sparse feature matrix x weight, and the transpose product): one role of tg_roles2.cu
-            if (out_vec4_ok && roles2_rect_applicable(pl, sc)) return roles2_rect_run(pl, sc, epi, st);
+            // rectangular operands (sparse feature matrix x weight, and the transpose product): one role each
+            // (the resident-table kernel has no Philox path: a dropout epilogue on X * W takes the gather kernel)
+            if (roles2_rect_applicable(pl, sc) && !(pl->r2_rect == 1 && epi.drop_mode == 1)) return roles2_rect_run(pl, sc, epi, st);
+            if (roles2_applicable(pl, sc)) return roles2_run(pl, sc, epi, st);
         }
-        if (stream_applicable(pl, sc, out_vec4_ok, EpiTraits<Epi>::whole_row)) return stream_dispatch(pl, sc, epi, st);
+        if (roles2_narrow_applicable(pl, sc)) return roles2_narrow_run(pl, sc, epi, st);
     }
     SpmmArgs a;
     a.rowptr = rowptr; a.colidx = colidx; a.vals = vals; a.B = B; a.ldb = ldb;

@@ -12,8 +12,6 @@ from __future__ import annotations
 
 from typing import Optional
 
-import os
-
 import torch
 
 from . import _native as N
@@ -55,29 +53,12 @@ class _call:
         return False
 
 
-def roles2_path(csr, n_feat: int):
-    """Which warp-per-slot kernel (csrc/tg_roles2.cu) a product with `n_feat` columns runs on this matrix: "wide", "narrow"
-    or None (first-generation streaming / gather kernels).  Mirrors roles2_applicable / roles2_narrow_applicable."""
-    if not getattr(csr, "roles2", False) or os.environ.get("TG_ROLES2", "1") == "0" or n_feat % 4 != 0:
-        return None
-    if 64 <= n_feat <= 1024 and csr.n_rows >= int(os.environ.get("TG_ROLES2_MIN_ROWS", "16384")):
-        return "wide"
-    if (n_feat <= 32 and os.environ.get("TG_ROLES2_NARROW", "1") != "0"
-            and csr.n_rows >= int(os.environ.get("TG_ROLES2_NARROW_MIN_ROWS", "131072"))):
-        return "narrow"
-    return None
-
-
-def _spmm_launches(csr, n_feat: int, philox: bool = False) -> int:
+def _spmm_launches(csr, B: torch.Tensor, n_feat: int, philox: bool = False, out: Optional[torch.Tensor] = None) -> int:
     """Kernels one SpMM-type call launches: the product itself, the finishing kernel of the streaming paths (hub rows =
-    fixed-order sum of the per-CTA partials + epilogue) and, for Philox dropout on the warp-per-slot path, the kernel
-    that draws the bit-packed keep mask."""
-    rect = int(getattr(csr, "roles2_rect", 0))
-    if rect and 64 <= n_feat <= 1024 and n_feat % 4 == 0 and os.environ.get("TG_ROLES2_RECT", "1") != "0":
-        return rect  # resident-table product: one kernel; all-hub product: hub role + finish
-    path = roles2_path(csr, n_feat)
-    streamed = bool(getattr(csr, "streaming", False)) and (n_feat > 32 or path == "narrow")
-    return 1 + int(streamed) + int(philox and path == "wide")
+    fixed-order sum of the per-CTA partials + epilogue) and, for Philox dropout on the wide streaming path, the kernel
+    that draws the bit-packed keep mask.  Asked of the library (tg_plan_spmm_launches), not mirrored here."""
+    ok4 = out is None or (out.data_ptr() % 16 == 0 and (out.shape[0] <= 1 or out.stride(0) % 4 == 0))
+    return csr.spmm_launches(B, n_feat, philox, ok4)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -125,7 +106,7 @@ def spmm(csr: DeviceCSR, B: torch.Tensor, bias: Optional[torch.Tensor] = None,
     if out is None:
         out = torch.empty((csr.n_rows, F), dtype=torch.float32, device=B.device)
     ws, ws_bytes = csr.workspace(F)
-    with torch.cuda.device(B.device), _call("spmm", _spmm_launches(csr, F), n_feat=F, csr=csr):
+    with torch.cuda.device(B.device), _call("spmm", _spmm_launches(csr, B, F, out=out), n_feat=F, csr=csr):
         N.check(N.lib().tg_spmm_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(B), _ld(B),
                                     N.ptr(out), _ld(out), F, N.ptr(bias), N.ptr(out_scale), ws, ws_bytes, _stream()),
                 "tg_spmm_f32")
@@ -150,7 +131,7 @@ def gc1_forward(csr: DeviceCSR, S: torch.Tensor, bias: Optional[torch.Tensor], p
     if out is None:
         out = torch.empty((csr.n_rows, F), dtype=torch.float32, device=S.device)
     ws, ws_bytes = csr.workspace(F)
-    with torch.cuda.device(S.device), _call("gc1_fwd", _spmm_launches(csr, F, philox=bool(training) and keep_mask is None and p > 0.0), n_feat=F, csr=csr):
+    with torch.cuda.device(S.device), _call("gc1_fwd", _spmm_launches(csr, S, F, philox=bool(training) and keep_mask is None and p > 0.0, out=out), n_feat=F, csr=csr):
         N.check(N.lib().tg_gc1_fwd_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(S), _ld(S),
                                        N.ptr(bias), N.ptr(out), _ld(out), F, float(p), int(bool(training)),
                                        N.ptr(keep_mask), int(seed) & (2**64 - 1), int(offset) & (2**64 - 1),
@@ -230,7 +211,7 @@ def gc2_loss_forward(csr: DeviceCSR, S2: torch.Tensor, bias: Optional[torch.Tens
     dZ2 = torch.empty((csr.n_rows, Cc), dtype=torch.float32, device=dev) if want_grad else None
     row_loss = torch.empty(csr.n_rows, dtype=torch.float32, device=dev)
     ws, ws_bytes = csr.workspace(Cc)
-    with torch.cuda.device(dev), _call("gc2_loss_fwd", _spmm_launches(csr, Cc), n_feat=Cc, csr=csr):
+    with torch.cuda.device(dev), _call("gc2_loss_fwd", _spmm_launches(csr, S2, Cc), n_feat=Cc, csr=csr):
         N.check(N.lib().tg_gc2_loss_fwd_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(S2),
                                             _ld(S2), N.ptr(bias), N.ptr(row_label), float(inv_count), N.ptr(logits),
                                             Cc, N.ptr(dZ2), Cc, N.ptr(row_loss), Cc, ws, ws_bytes, _stream()),

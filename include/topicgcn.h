@@ -88,12 +88,18 @@ int tg_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* va
                    int32_t segment_nnz /*<=0: default*/, tg_plan** plan_out, void* stream);
 void tg_plan_destroy(tg_plan* plan);
 /* info: [0]=n_hub_rows [1]=n_segments [2]=hub_nnz [3]=max_row_nnz [4]=hub_threshold [5]=segment_nnz
- *       [6]=bit 0: streaming layout present, bit 1: warp-per-slot role kernels available (hub rows <= 256),
+ *       [6]=bits 0-1: role-specialised streaming kernels available (square graph, hub rows <= 1280),
  *           bits 2-3: rectangular sub-plan (1 = resident-table product X*W, 2 = all-hub product X^T*dS)
- *       [7]=nodes per chunk */
+ *       [7]=nodes per hub chunk | hub slot groups << 16 | float4 chunks per lane of the document role << 24 */
 int tg_plan_info(const tg_plan* plan, int64_t info_host[8]);
 /* bytes of scratch a tg_spmm* / tg_gc* call with `n_feat` columns needs (partials of split hub rows) */
 size_t tg_plan_workspace_bytes(const tg_plan* plan, int32_t n_feat);
+/* number of kernels a tg_spmm* / tg_gc* call on this plan launches for a dense operand B (device pointer, only its
+ * alignment is inspected) with leading dimension ldb and `n_feat` columns; philox: the call draws a Philox dropout mask;
+ * out_vec4_ok: outputs / bias are 16-byte aligned with leading dimensions that are multiples of 4.  Instrumentation
+ * only (the launch counter of bench.py); mirrors the kernel selection of the compute entry points exactly. */
+int tg_plan_spmm_launches(const tg_plan* plan, const float* B, int64_t ldb, int32_t n_feat, int32_t philox,
+                          int32_t out_vec4_ok);
 
 /* ------------------------------------------------------------------------------------------------
  * Y[n_rows x F] = A_csr * B[n_cols x F]  (+ bias)            replaces layer.py:106 (+ :109-110)

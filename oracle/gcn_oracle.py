@@ -151,6 +151,16 @@ def spmm_f64(coo: Coo, B: np.ndarray) -> np.ndarray:
     return Y
 
 
+def row_dot_f32(vals: np.ndarray, rows_of_B: np.ndarray) -> np.ndarray:
+    """One output row of `spmm`: sum_p vals[p] * rows_of_B[p] accumulated serially in fp32, storage order (the same loop,
+    run on a one-row matrix)."""
+    m = int(vals.size)
+    one = Coo(np.zeros(m, dtype=np.int64), np.arange(m, dtype=np.int64), np.asarray(vals, dtype=np.float32), (1, max(m, 1)))
+    if m == 0:
+        return np.zeros(rows_of_B.shape[1], dtype=np.float32)
+    return spmm(one, rows_of_B)[0]
+
+
 def spmm_csr(rowptr, colidx, vals, B: np.ndarray, n_threads: int = 0) -> np.ndarray:
     """Row-parallel form of the same loop (bit-identical for row-major sorted input); the CPU baseline."""
     B = np.ascontiguousarray(B, dtype=np.float32)
@@ -227,8 +237,15 @@ def _philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 def philox_keep_mask(n_rows: int, n_feat: int, p: float, seed: int, offset: int) -> np.ndarray:
     """The counter-based keep mask of the CUDA library (definition in csrc/tg_common.cuh), restated in numpy."""
+    return philox_keep_mask_rows(np.arange(n_rows, dtype=np.uint64), n_feat, p, seed, offset)
+
+
+def philox_keep_mask_rows(row_ids, n_feat: int, p: float, seed: int, offset: int) -> np.ndarray:
+    """The keep mask of the given rows only (the mask is a pure function of (row, column, seed, offset))."""
+    row_ids = np.asarray(row_ids, dtype=np.uint64)
+    n_rows = int(row_ids.size)
     thr = int(min(max((1.0 - np.float32(p)) * np.float32(65536.0) + np.float32(0.5), 0.0), 65536.0))
-    row = np.repeat(np.arange(n_rows, dtype=np.uint64), n_feat)
+    row = np.repeat(row_ids, n_feat)
     col = np.tile(np.arange(n_feat, dtype=np.uint64), n_rows)
     q = col >> np.uint64(2)
     slot, j, half = q & np.uint64(7), q >> np.uint64(4), (q >> np.uint64(3)) & np.uint64(1)

@@ -98,17 +98,26 @@ def test_csr_edge_cases(tg):
 # ---------------------------------------------------------------------------------------------------------------
 # SpMM
 # ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("roles", [False, True])
 @pytest.mark.parametrize("F", [1, 2, 3, 8, 20, 23, 52, 64, 100, 200, 256, 300, 512])
-def test_spmm_small_golden_shapes(tg, small_golden, F):
+def test_spmm_small_golden_shapes(tg, small_golden, monkeypatch, F, roles):
+    """Every width class on the small golden graph.  roles=True lifts the size thresholds (read once, at plan creation) so
+    that the role-specialised streaming kernels run on this tiny graph wherever they apply (F % 4 == 0)."""
+    if roles:
+        monkeypatch.setenv("TG_ROLES2_MIN_ROWS", "0")
+        monkeypatch.setenv("TG_ROLES2_NARROW_MIN_ROWS", "0")
     coo = golden_adj(small_golden)
     rng = np.random.default_rng(F)
     B = rng.normal(size=(coo.shape[1], F)).astype(np.float32)
     ref = O.spmm(coo, B)
-    # plans: default; split rows + column-chunk streaming forced on a tiny graph; the same without streaming
+    # plans: default; split rows + streaming layout forced on a tiny graph; the same without the streaming layout
     for kw in ({}, {"hub_threshold": 16, "segment_nnz": 8}, {"hub_threshold": 16, "segment_nnz": 8, "streaming": False}):
         csr = to_csr(tg, coo, **kw)
         if "streaming" not in kw and kw:
             assert csr.streaming
+            Bd = torch.tensor(B, device=dev())
+            want = 1 if not roles or F % 4 or 32 < F < 64 else 2
+            assert csr.spmm_launches(Bd, F) == want, (F, roles)
         y = tg.spmm(csr, torch.tensor(B, device=dev())).cpu().numpy()
         assert rel_err(y, ref) <= SPMM_RTOL, (F, kw)
         bias = rng.normal(size=F).astype(np.float32)
@@ -158,22 +167,6 @@ def test_spmm_deterministic_and_split_rows(tg, streaming):
     e_ref = rel_err(ref[nd:], ref64[nd:])
     assert rel_err(y[nd:], ref64[nd:]) <= e_ref + 2e-7
     assert rel_err(y[nd:], ref[nd:]) <= max(SPMM_RTOL, 2 * e_ref)
-
-
-def test_narrow_streaming_kernel_env_knob(tg, small_golden, monkeypatch):
-    """TG_STREAM_NARROW=1 routes F <= 32 through the lane-per-row streaming kernel (default: gather kernel)."""
-    coo = golden_adj(small_golden)
-    csr = to_csr(tg, coo, hub_threshold=16, segment_nnz=8)
-    assert csr.streaming
-    rng = np.random.default_rng(0)
-    for F in (8, 20, 32):
-        B = rng.normal(size=(coo.shape[1], F)).astype(np.float32)
-        ref = O.spmm(coo, B)
-        monkeypatch.setenv("TG_STREAM_NARROW", "1")
-        y1 = tg.spmm(csr, torch.tensor(B, device=dev())).cpu().numpy()
-        monkeypatch.setenv("TG_STREAM_NARROW", "0")
-        y0 = tg.spmm(csr, torch.tensor(B, device=dev())).cpu().numpy()
-        assert rel_err(y1, ref) <= SPMM_RTOL and rel_err(y0, ref) <= SPMM_RTOL
 
 
 def test_spmm_textgcn_skew(tg):
@@ -485,14 +478,15 @@ def test_captured_train_step_matches_eager(tg, small_golden):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# warp-per-slot role kernels (tg_roles2.cu): 64 <= F <= 1024 (wide) or F <= 32 (narrow), <= 256 hub rows
+# role-specialised streaming kernels (tg_roles2.cu): 64 <= F <= 1024 (wide) or F <= 32 (narrow), <= 1280 hub rows
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n_docs,n_topics,F,thr", [(3000, 64, 128, 64), (9000, 256, 256, 48), (777, 37, 384, 24),
-                                                    (20000, 100, 256, 256), (5000, 50, 200, 64), (2000, 20, 72, 32)])
+                                                    (20000, 100, 256, 256), (5000, 50, 200, 64), (2000, 20, 72, 32),
+                                                    (30000, 400, 256, 48), (40000, 600, 200, 48), (60000, 1024, 256, 64),
+                                                    (30000, 1100, 136, 16)])
 def test_roles2_kernel_parity(tg, monkeypatch, n_docs, n_topics, F, thr):
-    """Plain product, fused layer-1 epilogue (eval / explicit mask / Philox via the bit-packed side mask / in-kernel
-    Philox) and the raw-row (document-sharded) mode of the warp-per-slot kernels against the oracle; bitwise
-    reproducible; agrees with the first-generation role kernel."""
+    """Plain product, fused layer-1 epilogue (eval / explicit mask / Philox via the bit-packed side mask) and the raw-row
+    (document-sharded) mode of the role kernels against the oracle; bitwise reproducible; agrees with the gather kernel."""
     monkeypatch.setenv("TG_ROLES2_MIN_ROWS", "0")          # (the kernels are reserved for large graphs by default)
     monkeypatch.setenv("TG_ROLES2_NARROW_MIN_ROWS", "0")
     from topicgcn_b200 import graphgen, ops
@@ -525,24 +519,17 @@ def test_roles2_kernel_parity(tg, monkeypatch, n_docs, n_topics, F, thr):
     assert rel_err(h5.cpu().numpy(), want5) <= SPMM_RTOL
     assert np.array_equal(h5.cpu().numpy() != 0, want5 != 0)
     assert 0.49 < pm5.mean() < 0.51
-    monkeypatch.setenv("TG_ROLES2_BITMASK", "0")                               # Philox drawn inside the kernel
-    h5_in = ops.gc1_forward(csr, B, bias, 0.5, True, seed=7, offset=3)
-    assert torch.equal(h5_in[:n_docs], h5[:n_docs]) and torch.equal(h5_in != 0, h5 != 0)
-    h_in = ops.gc1_forward(csr, B, bias, 0.3, True, seed=42, offset=9)
-    assert torch.equal(h_in[:n_docs], h_bits[:n_docs])    # hub rows: the SM split (hence the partial grouping) differs
-    assert torch.equal(h_in != 0, h_bits != 0)
-    assert float((h_in - h_bits).abs().max() / h_bits.abs().max()) <= SPMM_RTOL
-    monkeypatch.delenv("TG_ROLES2_BITMASK")
     h_raw = ops.gc1_forward(csr, B, bias, 0.5, False, raw_row_begin=n_docs).cpu().numpy()   # document-sharded mode
     assert rel_err(h_raw[:n_docs], np.maximum(z[:n_docs], 0)) <= SPMM_RTOL
     assert rel_err(h_raw[n_docs:], ref[n_docs:]) <= SPMM_RTOL
-    monkeypatch.setenv("TG_ROLES2", "0")                                       # first-generation role kernel
-    y_old = tg.spmm(csr, B)
-    monkeypatch.delenv("TG_ROLES2")
+    csr_g = tg.DeviceCSR(csr.rowptr, csr.colidx, csr.vals, g.n, g.n, hub_threshold=thr, segment_nnz=max(8, thr // 2), streaming=False)
+    assert not csr_g.streaming and csr_g.spmm_launches(B, F) == 1              # gather kernel
+    y_old = tg.spmm(csr_g, B)
     assert float((y_old - y).abs().max() / y.abs().max()) <= SPMM_RTOL
 
 
-@pytest.mark.parametrize("n_docs,n_topics,thr", [(3000, 64, 64), (9000, 256, 48), (20000, 100, 256)])
+@pytest.mark.parametrize("n_docs,n_topics,thr", [(3000, 64, 64), (9000, 256, 48), (20000, 100, 256), (40000, 600, 48),
+                                                 (60000, 1024, 64)])
 @pytest.mark.parametrize("C", [8, 20, 32])
 def test_roles2_narrow_kernel_parity(tg, monkeypatch, n_docs, n_topics, thr, C):
     """Class-sized operands (F <= 32) through the narrow variant of the warp-per-slot kernels: plain product and the fused
@@ -564,9 +551,10 @@ def test_roles2_narrow_kernel_parity(tg, monkeypatch, n_docs, n_topics, thr, C):
     assert rel_err(y.cpu().numpy(), ref) <= SPMM_RTOL
     assert rel_err(y.cpu().numpy()[n_docs:], ref[n_docs:]) <= SPMM_RTOL
     assert torch.equal(y, tg.spmm(csr, S2d))
-    monkeypatch.setenv("TG_ROLES2_NARROW", "0")
-    y_g = tg.spmm(csr, S2d)
-    monkeypatch.delenv("TG_ROLES2_NARROW")
+    csr_g = tg.DeviceCSR(csr.rowptr, csr.colidx, csr.vals, g.n, g.n, hub_threshold=thr, segment_nnz=max(8, thr // 2), streaming=False)
+    y_g = tg.spmm(csr_g, S2d)
+    # (1 024 resident hub rows of 32 columns + the 8-deep ring do not fit shared memory: that one case takes the gather kernel)
+    assert csr.spmm_launches(S2d, C) == (1 if (n_topics == 1024 and C == 32) else 2) and csr_g.spmm_launches(S2d, C) == 1
     assert float((y_g - y).abs().max() / y.abs().max()) <= SPMM_RTOL
     target = rng.integers(0, C, size=n_docs)
     index = np.sort(rng.choice(n_docs, size=n_docs * 2 // 3, replace=False))
@@ -716,11 +704,13 @@ def test_edge_list_ingest_on_device(tg):
     assert rel_err(logits, want) <= 2e-5
 
 
-@pytest.mark.parametrize("n_rows,n_feat_in,H,row_nnz", [(20000, 100, 256, 40), (17000, 256, 200, 12), (30000, 37, 128, 37)])
+@pytest.mark.parametrize("n_rows,n_feat_in,H,row_nnz", [(20000, 100, 256, 40), (17000, 256, 200, 12), (30000, 37, 128, 37),
+                                                        (20000, 350, 256, 30), (60000, 1100, 128, 16)])
 def test_rectangular_products_of_a_sparse_feature_matrix(tg, monkeypatch, n_rows, n_feat_in, H, row_nnz):
-    """The two products of the reference's real feature mode (X sparse [n x nfeat <= 256], trainer.py:197-238):
+    """The two products of the reference's real feature mode (X sparse [n x nfeat <= 1280], trainer.py:197-238; 350 = 50
+    topics + a 300-d embedding needs two hub slot groups and 64-column document slices, 1100 five groups and 32 columns):
     X @ W through the resident-table plan (document role only) and X^T @ dS through the all-hub plan (hub role only),
-    against the oracle; deterministic; the gather kernel (TG_ROLES2_RECT=0) agrees."""
+    against the oracle; deterministic; the gather kernel agrees."""
     gen = torch.Generator(device="cuda:0").manual_seed(n_rows)
     cols = torch.rand(n_rows, n_feat_in, device=dev(), generator=gen).topk(row_nnz, dim=1).indices.sort(dim=1).values
     vals = torch.randn(n_rows, row_nnz, device=dev(), generator=gen)
@@ -739,8 +729,215 @@ def test_rectangular_products_of_a_sparse_feature_matrix(tg, monkeypatch, n_rows
     assert rel_err(g.cpu().numpy(), ref_g64) <= rel_err(ref_g, ref_g64) + 2e-7   # long rows: not worse than the reference's sum
     assert rel_err(g.cpu().numpy(), ref_g) <= 2e-5
     assert torch.equal(y, tg.spmm(X, W)) and torch.equal(g, tg.spmm(XT, dS))
-    monkeypatch.setenv("TG_ROLES2_RECT", "0")
-    y0, g0 = tg.spmm(X, W), tg.spmm(XT, dS)
-    monkeypatch.delenv("TG_ROLES2_RECT")
+    X0 = tg.DeviceCSR(X.rowptr, X.colidx, X.vals, n_rows, n_feat_in, streaming=False)
+    XT0 = tg.DeviceCSR(XT.rowptr, XT.colidx, XT.vals, n_feat_in, n_rows, streaming=False)
+    assert X0.roles2_rect == 0 and XT0.roles2_rect == 0
+    y0, g0 = tg.spmm(X0, W), tg.spmm(XT0, dS)
     assert float((y0 - y).abs().max() / y.abs().max()) <= SPMM_RTOL
     assert float((g0 - g).abs().max() / g.abs().max()) <= 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K = 1024 topics (the C4 shape of BASELINE.json): hub slot groups + 32-column document slices
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c4_small(tg):
+    """200 K documents x 1 024 topics, 8 topic entries per document, dense topic-topic block: the C4 graph at 1/31 of a
+    shard, with the DEFAULT plan parameters (hub threshold 512) and size thresholds."""
+    from topicgcn_b200 import graphgen
+    g = graphgen.doc_topic_topic_graph(200_000, 1024, deg_lo=8, deg_hi=8, dense_topics=True, seed=1, device="cuda:0")
+    csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n)
+    coo = O.Coo(g.rows.cpu().numpy(), g.cols.cpu().numpy(), g.vals.cpu().numpy(), (g.n, g.n))
+    return g, csr, coo
+
+
+def test_c4_shape_plan(tg, c4_small):
+    g, csr, _ = c4_small
+    assert csr.n_hub_rows == 1024 and csr.streaming and csr.roles2
+    assert csr.hub_groups in (4, 5) and csr.doc_nq == 1
+    assert csr.is_symmetric
+
+
+@pytest.mark.parametrize("F", [256, 200])
+def test_c4_shape_wide_products(tg, c4_small, F):
+    """Plain product, fused layer-1 forward (eval, Philox exact-half and 16-bit, explicit mask), raw topic rows, the
+    out_scale epilogue of the backward — against the oracle, with the kernel selection asserted; bitwise deterministic."""
+    from topicgcn_b200 import ops
+    g, csr, coo = c4_small
+    nd = g.n_docs
+    gen = torch.Generator(device="cuda:0").manual_seed(F)
+    B = torch.randn(g.n, F, device=dev(), generator=gen)
+    bias = torch.randn(F, device=dev(), generator=gen)
+    assert csr.spmm_launches(B, F) == 2 and csr.spmm_launches(B, F, philox=True) == 3
+    Bn = B.cpu().numpy()
+    ref, ref64 = O.spmm(coo, Bn), O.spmm_f64(coo, Bn)
+    y = tg.spmm(csr, B)
+    yn = y.cpu().numpy()
+    assert rel_err(yn[:nd], ref[:nd]) <= SPMM_RTOL
+    e_ref = rel_err(ref[nd:], ref64[nd:])
+    assert rel_err(yn[nd:], ref64[nd:]) <= e_ref + 2e-7       # topic rows (~1 600 entries + the dense block)
+    assert rel_err(yn[nd:], ref[nd:]) <= max(SPMM_RTOL, 2 * e_ref)
+    for _ in range(2):
+        assert torch.equal(y, tg.spmm(csr, B))
+    z = ref + bias.cpu().numpy()
+    assert rel_err(ops.gc1_forward(csr, B, bias, 0.5, False).cpu().numpy(), np.maximum(z, 0)) <= SPMM_RTOL
+    for p, seed, off in ((0.5, 7, 3), (0.3, 42, 9)):
+        pm = O.philox_keep_mask(g.n, F, p, seed, off)
+        want = np.maximum(z, 0) * pm / (1.0 - p)
+        h = ops.gc1_forward(csr, B, bias, p, True, seed=seed, offset=off).cpu().numpy()
+        assert rel_err(h, want) <= SPMM_RTOL
+        assert np.array_equal(h != 0, want != 0)
+    mask = (torch.rand(g.n, F, device=dev(), generator=gen) < 0.5).to(torch.uint8)
+    h_m = ops.gc1_forward(csr, B, bias, 0.5, True, keep_mask=mask).cpu().numpy()
+    assert rel_err(h_m, np.maximum(z, 0) * mask.cpu().numpy() * 2.0) <= SPMM_RTOL
+    h_raw = ops.gc1_forward(csr, B, bias, 0.5, False, raw_row_begin=nd).cpu().numpy()
+    assert rel_err(h_raw[:nd], np.maximum(z[:nd], 0)) <= SPMM_RTOL
+    assert np.array_equal(h_raw[nd:], yn[nd:])                 # raw topic rows = the plain sums, bit for bit
+    s = torch.tensor(0.37, device=dev())
+    ys = tg.spmm(csr, B, out_scale=s).cpu().numpy()
+    assert rel_err(ys, ref * np.float32(0.37)) <= SPMM_RTOL
+
+
+@pytest.mark.parametrize("C", [20, 8])
+def test_c4_shape_narrow_products(tg, c4_small, C):
+    """Class-sized products on the K = 1 024 graph: plain and with the fused loss epilogue, against the oracle."""
+    from topicgcn_b200 import ops
+    g, csr, coo = c4_small
+    nd = g.n_docs
+    rng = np.random.default_rng(C)
+    S2 = rng.normal(size=(g.n, C)).astype(np.float32)
+    b2 = rng.normal(size=C).astype(np.float32)
+    S2d = torch.tensor(S2, device=dev())
+    ref, ref64 = O.spmm(coo, S2), O.spmm_f64(coo, S2)
+    y = tg.spmm(csr, S2d)
+    yn = y.cpu().numpy()
+    assert rel_err(yn[:nd], ref[:nd]) <= SPMM_RTOL
+    assert rel_err(yn[nd:], ref64[nd:]) <= rel_err(ref[nd:], ref64[nd:]) + 2e-7
+    assert torch.equal(y, tg.spmm(csr, S2d))
+    index = np.sort(rng.choice(nd, size=nd * 2 // 3, replace=False))
+    target = rng.integers(0, C, size=nd)
+    logits_ref = ref64 + b2
+    loss_ref, dz_ref = O.masked_cross_entropy(logits_ref.astype(np.float32), target, index)
+    row_label = ops.make_row_label(g.n, torch.tensor(target, device=dev()), torch.tensor(index, device=dev()))
+    loss, logits, dz = ops.gc2_loss_forward(csr, S2d, torch.tensor(b2, device=dev()), row_label, 1.0 / index.size)
+    assert rel_err(logits.cpu().numpy()[:nd], logits_ref[:nd]) <= SPMM_RTOL
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    assert rel_err(dz.cpu().numpy(), dz_ref) <= 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rows without stored entries (ADVICE r1): every path must write epilogue(0) for them, never leave the output untouched
+# ---------------------------------------------------------------------------------------------------------------
+def _drop_rows(g, drop):
+    keep = ~torch.isin(g.rows, drop)
+    return g.rows[keep], g.cols[keep], g.vals[keep]
+
+
+@pytest.mark.parametrize("n_docs,n_topics", [(20000, 100), (140000, 64), (30000, 600)])
+def test_empty_rows_on_the_role_kernels(tg, monkeypatch, n_docs, n_topics):
+    from topicgcn_b200 import graphgen, ops
+    monkeypatch.setenv("TG_ROLES2_NARROW_MIN_ROWS", "16384")
+    g = graphgen.doc_topic_topic_graph(n_docs, n_topics, deg_lo=2, deg_hi=13, dense_topics=True, seed=9, device="cuda:0")
+    gen = torch.Generator(device="cuda:0").manual_seed(1)
+    drop = torch.unique(torch.randint(0, n_docs, (n_docs // 50,), device=dev(), generator=gen))
+    drop = torch.cat([drop, torch.tensor([0, 63, 64, n_docs - 1], device=dev())])        # first / last rows of jobs
+    rows, cols, vals = _drop_rows(g, drop)
+    csr = tg.DeviceCSR.from_coo(rows, cols, vals, g.n, g.n, hub_threshold=64, segment_nnz=32)
+    assert csr.roles2 and csr.n_hub_rows == n_topics
+    coo = O.Coo(rows.cpu().numpy(), cols.cpu().numpy(), vals.cpu().numpy(), (g.n, g.n))
+    dropn = drop.cpu().numpy()
+    for F in (128, 20):
+        B = torch.randn(g.n, F, device=dev(), generator=gen)
+        bias = torch.randn(F, device=dev(), generator=gen)
+        assert csr.spmm_launches(B, F) == 2
+        ref = O.spmm(coo, B.cpu().numpy())
+        out = torch.full((g.n, F), float("nan"), device=dev())    # poisoned output buffer
+        y = tg.spmm(csr, B, bias, out=out).cpu().numpy()
+        assert np.isfinite(y).all()
+        assert rel_err(y, ref + bias.cpu().numpy()) <= SPMM_RTOL
+        assert np.array_equal(y[dropn], np.broadcast_to(bias.cpu().numpy(), (dropn.size, F)))
+    # fused layer-1 forward: relu(b) on the empty rows; fused loss: the loss of logits = b2 on labelled empty rows
+    F = 128
+    B = torch.randn(g.n, F, device=dev(), generator=gen)
+    bias = torch.randn(F, device=dev(), generator=gen)
+    h = ops.gc1_forward(csr, B, bias, 0.5, False, out=torch.full((g.n, F), float("nan"), device=dev())).cpu().numpy()
+    assert np.array_equal(h[dropn], np.broadcast_to(np.maximum(bias.cpu().numpy(), 0), (dropn.size, F)))
+    C = 20
+    rng = np.random.default_rng(0)
+    S2 = rng.normal(size=(g.n, C)).astype(np.float32)
+    b2 = rng.normal(size=C).astype(np.float32)
+    target = rng.integers(0, C, size=n_docs)
+    index = np.arange(n_docs)
+    row_label = ops.make_row_label(g.n, torch.tensor(target, device=dev()), torch.tensor(index, device=dev()))
+    loss, logits, dz = ops.gc2_loss_forward(csr, torch.tensor(S2, device=dev()), torch.tensor(b2, device=dev()), row_label,
+                                            1.0 / index.size)
+    logits_ref = O.spmm(coo, S2) + b2
+    loss_ref, dz_ref = O.masked_cross_entropy(logits_ref, target, index)
+    assert np.isfinite(float(loss)) and abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    assert rel_err(logits.cpu().numpy(), logits_ref) <= SPMM_RTOL and rel_err(dz.cpu().numpy(), dz_ref) <= 2e-5
+
+
+def test_empty_rows_in_a_sparse_feature_matrix(tg):
+    """X @ W through the resident-table plan with all-zero feature rows (and all-zero feature columns for X^T @ dS)."""
+    n_rows, nfeat, H, row_nnz = 20000, 100, 128, 10
+    gen = torch.Generator(device="cuda:0").manual_seed(2)
+    cols = torch.rand(n_rows, nfeat - 3, device=dev(), generator=gen).topk(row_nnz, dim=1).indices.sort(dim=1).values  # last 3 features unused
+    vals = torch.randn(n_rows, row_nnz, device=dev(), generator=gen)
+    rows = torch.arange(n_rows, device=dev()).unsqueeze(1).expand(-1, row_nnz)
+    keep = (rows % 37 != 5).reshape(-1)                                                        # rows 5, 42, ... are empty
+    r, c, v = rows.reshape(-1)[keep], cols.reshape(-1)[keep], vals.reshape(-1)[keep]
+    X = tg.DeviceCSR.from_coo(r, c, v, n_rows, nfeat)
+    assert X.roles2_rect == 1
+    W = torch.randn(nfeat, H, device=dev(), generator=gen)
+    y = tg.spmm(X, W, out=torch.full((n_rows, H), float("nan"), device=dev())).cpu().numpy()
+    coo = O.Coo(r.cpu().numpy(), c.cpu().numpy(), v.cpu().numpy(), (n_rows, nfeat))
+    assert np.isfinite(y).all() and rel_err(y, O.spmm(coo, W.cpu().numpy())) <= SPMM_RTOL
+    assert not y[5::37].any()
+    XT = X.transpose()                                  # three empty rows: not an all-hub matrix -> gather kernel, still exact
+    dS = torch.randn(n_rows, H, device=dev(), generator=gen)
+    gq = tg.spmm(XT, dS, out=torch.full((nfeat, H), float("nan"), device=dev())).cpu().numpy()
+    assert np.isfinite(gq).all() and not gq[-3:].any()
+    assert rel_err(gq, O.spmm_f64(coo.transpose(), dS.cpu().numpy())) <= 2e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the benchmarked configuration itself: C3 at full size, F = 256, default plan, against float64 on a row sample
+# ---------------------------------------------------------------------------------------------------------------
+def test_c3_full_size_against_float64_on_a_row_sample(tg):
+    """1 M documents x 256 topics, F = 256, default thresholds (what bench.py times): all 256 topic rows and 5 000 random
+    document rows of the plain product and of the fused layer-1 forward are recomputed on the CPU in float64 from the CSR."""
+    from topicgcn_b200 import graphgen, ops
+    g, hidden, _ = graphgen.make_config("c3_1m_docs_256_topics", device="cuda:0")
+    csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n)
+    F = hidden
+    gen = torch.Generator(device="cuda:0").manual_seed(0)
+    B = torch.randn(g.n, F, device=dev(), generator=gen)
+    bias = torch.randn(F, device=dev(), generator=gen)
+    assert csr.spmm_launches(B, F) == 2
+    y = tg.spmm(csr, B)
+    h = ops.gc1_forward(csr, B, bias, 0.5, True, seed=11, offset=2)
+    rp, ci, va = csr.rowptr.cpu().numpy(), csr.colidx.cpu().numpy(), csr.vals.cpu().numpy()
+    Bn = B.cpu().numpy()
+    rng = np.random.default_rng(0)
+    sample = np.concatenate([np.arange(g.n_docs, g.n), np.sort(rng.choice(g.n_docs, 5000, replace=False))])
+    ref32 = np.empty((sample.size, F), dtype=np.float32)
+    ref64 = np.empty((sample.size, F))
+    for i, r in enumerate(sample):
+        s, e = rp[r], rp[r + 1]
+        rows_b = Bn[ci[s:e]]
+        ref64[i] = va[s:e].astype(np.float64) @ rows_b.astype(np.float64)
+        ref32[i] = O.row_dot_f32(va[s:e], rows_b)               # the reference's serial fp32 order
+    got = y[torch.tensor(sample, device=dev())].cpu().numpy()
+    nk = g.n_hubs
+    assert rel_err(got[nk:], ref64[nk:]) <= SPMM_RTOL                                   # document rows
+    assert rel_err(got[nk:], ref32[nk:]) <= SPMM_RTOL
+    e_ref = rel_err(ref32[:nk], ref64[:nk])
+    assert rel_err(got[:nk], ref64[:nk]) <= e_ref + 2e-7                                # topic rows (~31 000 entries)
+    pm = O.philox_keep_mask_rows(sample, F, 0.5, 11, 2)
+    want = np.maximum(ref64 + bias.cpu().numpy().astype(np.float64), 0) * pm * 2.0
+    hg = h[torch.tensor(sample, device=dev())].cpu().numpy()
+    # entries within rounding of the relu threshold may differ in sign between fp32 and fp64: compare where |z| is not tiny
+    z = ref64 + bias.cpu().numpy()
+    safe = np.abs(z) > 1e-4
+    assert np.abs(hg - want)[safe].max() <= 2e-5 * np.abs(want).max()
+    assert np.array_equal((hg != 0)[safe], (want != 0)[safe])

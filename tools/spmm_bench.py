@@ -2,7 +2,7 @@
 """Micro-benchmark of the SpMM kernels on a named synthetic workload (GPU box).
 
     python tools/spmm_bench.py [--workload c3] [--feat 256,20] [--reps 20]
-Env knobs of the library (TG_STREAM, TG_STREAM_CHUNK, TG_STREAM_GW) apply.  Prints GB/s against the algorithmic bytes.
+Env knobs of the library (TG_ROLES2_*, read at plan creation) apply.  Prints GB/s against the algorithmic bytes.
 """
 import argparse
 import json
