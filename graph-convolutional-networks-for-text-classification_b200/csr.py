@@ -60,6 +60,7 @@ class DeviceCSR:
         self.chunk_rows = int(info[7]) & 0xFFFF
         self.hub_groups = (int(info[7]) >> 16) & 0xFF   # hub slot groups of 256 (K = 1024 topics: 4-5)
         self.doc_nq = (int(info[7]) >> 24) & 0xFF       # float4 chunks per lane of the document role (slice = 32 * nq columns)
+        self.hub_gs = (int(info[7]) >> 32) & 0xFF       # lanes per hub slot sub-group (32 / 16 / 8: 256 / 512 / 1024 slots per group)
 
     def spmm_launches(self, B: torch.Tensor, n_feat: int, philox: bool = False, out_vec4_ok: bool = True) -> int:
         """Kernels one tg_spmm* / tg_gc* call on this matrix launches (tg_plan_spmm_launches: the library's own kernel

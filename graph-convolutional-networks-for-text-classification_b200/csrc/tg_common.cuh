@@ -52,16 +52,17 @@ struct tg_plan {
     int32_t* seg_order = nullptr;    // [n_seg]   execution order: segments sorted by their first column (L2 reuse of B)
 
     // ---- role-specialised column-chunk streaming kernels (tg_roles2.cu) ----------------------------------------------
-    // Square graphs with a compact hub set (<= 1280 hub rows: the document-topic-topic graphs).  Hub slots are cut into
-    // GROUPS of 256 (one hub CTA owns one group of one 128-column slice); the document role keeps all hub rows of B
+    // Square graphs with a compact hub set (the document-topic-topic graphs, up to ~1 400 topic rows).  A hub CTA owns a
+    // GROUP of 256 * 32 / r2_gs slots of one column slice of 4 * r2_gs columns; the document role keeps all hub rows of B
     // resident in shared memory and therefore works on column slices of 32 * r2_nq columns (r2_nq = 4 / 2 / 1 for up to
-    // 256 / 512 / 1280 hub rows).
+    // ~368 / ~736 / ~1 400 hub rows).
     bool r2_ok = false;
     // rectangular operands (sparse feature matrices X [n x nfeat] and their transposes):
     //   1 = "table": every column's row of B is resident (document role only: X * W)
     //   2 = "all hub": every row is a hub row (hub role only: X^T * dS)
     int32_t r2_rect = 0;
-    int32_t r2_groups = 1;           // hub slot groups (256 slots each)
+    int32_t r2_gs = 32;              // lanes per hub slot sub-group (hub_role<GS>): 32 / 16 / 8 -> 256 / 512 / 1024 slots per group, 128 / 64 / 32-column slices
+    int32_t r2_groups = 1;           // hub slot groups (one hub CTA per group, slice and chunk lane)
     int32_t r2_nq = 4;               // float4 chunks per lane of the document role (slice = 32 * r2_nq columns)
     int32_t r2_stages = 4;           // document-role ring depth that fits next to the resident rows
     int32_t* r2_ident = nullptr;     // [n_cols] 0,1,2,... (the table rows of mode 1)

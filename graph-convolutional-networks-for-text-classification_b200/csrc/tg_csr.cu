@@ -389,7 +389,7 @@ int tg_plan_info(const tg_plan* pl, int64_t info[8]) {
     info[3] = pl->max_row_nnz; info[4] = pl->hub_threshold; info[5] = pl->segment_nnz;
     // bit 0 / 1: role kernels on the square graph, bits 2-3: rectangular mode; info[7]: nodes per hub chunk | groups << 16 | nq << 24
     info[6] = ((pl->r2_ok && pl->r2_rect == 0) ? 3 : 0) | ((pl->r2_ok && pl->r2_rect != 0) ? 4 * pl->r2_rect : 0);
-    info[7] = pl->r2_ok ? ((int64_t)pl->r2_T | ((int64_t)pl->r2_groups << 16) | ((int64_t)pl->r2_nq << 24)) : 0;
+    info[7] = pl->r2_ok ? ((int64_t)pl->r2_T | ((int64_t)pl->r2_groups << 16) | ((int64_t)pl->r2_nq << 24) | ((int64_t)pl->r2_gs << 32)) : 0;
     return TG_OK;
 }
 

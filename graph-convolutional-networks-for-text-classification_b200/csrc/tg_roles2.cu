@@ -40,10 +40,11 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kKPW = 16;              // hub slots per warp
 constexpr int kKv = kWarps * kKPW;    // 256 slots per hub CTA = one slot group
-constexpr int kMaxGroups = 5;         // up to 1280 slots (1024 hub rows + 256 spare slots for splitting the heavy ones)
-constexpr int kHtW = kKv + 4;         // offset-table row: 257 offsets padded to a multiple of 16 bytes
-constexpr int kFT = 128;              // columns per hub-CTA slice
-constexpr int kRowBytes = kFT * 4;    // bytes of a row of the staged hub tile
+constexpr int kMaxGroups = 5;         // slot groups of one plan (one hub CTA per group, slice and chunk lane)
+constexpr int kMaxHubRows = 4096;     // hub rows the hub role handles (the document role's resident rows set a tighter limit: ~1 400)
+constexpr int kHtW = kKv + 4;         // offset-table row of the 256-slot layout: 257 offsets padded to a multiple of 16 bytes
+constexpr int kFT = 128;              // columns per 128-column slice (mask layout, narrow kernels' hub tile encoding)
+constexpr int kRowBytes = kFT * 4;
 constexpr int kHubEnc = 128;          // document-role entries address hub row h as h * kHubEnc (scaled by NQ in the kernel)
 constexpr int kJobRows = 64;          // document role: rows per job = row groups per CTA
 constexpr int kStages = 4;            // document role: entry ring depth (maximum)
@@ -101,17 +102,33 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c
 __device__ __forceinline__ float4 lds128(const unsigned char* p) { return *reinterpret_cast<const float4*>(p); }
 
 // =============================================== hub role ===============================================================
+// GS lanes per slot sub-group: the 32 lanes of a warp form NSUB = 32 / GS sub-groups; a sub-group owns 16 hub slots and its
+// GS lanes cover a slice of 4 GS columns with one float4 each (sixteen float4 accumulators per lane, whatever GS is).
+//   GS = 32: a warp per slot, 128-column slices, 256 slots per CTA    (K <= 256 topics)
+//   GS = 16: two slots per warp step, 64-column slices, 512 slots     (K <= 512)
+//   GS =  8: four slots per warp step, 32-column slices, 1 024 slots  (K <= 1 024; more hub rows: several slot groups)
+// With narrower slices a tile of B holds more nodes for the same shared memory (T up to 512), so that a (chunk, slot) run
+// stays a few entries long when the entries of a chunk spread over 1 024 slots, every tile is read by ONE CTA per slice
+// instead of one per 256 slots, and the sub-groups of a warp walk their runs in lock step (the plan deals slots of similar
+// weight to the same position, so the runs of a step have similar lengths).
+template <int GS>
 __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tmap, unsigned char* smem, uint64_t* bars,
                                          int bid) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NSUB = 32 / GS;
+    constexpr int kSlots = kKv * NSUB;          // slots per CTA (one slot group)
+    constexpr int kHtWg = kSlots + 4;           // offset-table row, padded to a multiple of 16 bytes
+    constexpr int kCols = 4 * GS;               // columns per CTA slice
+    constexpr int kRowB = kCols * 4;            // bytes of a row of the staged tile
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gl = lane % GS, sub = lane / GS;
     // CTA = (chunk lane hl, slot group grp, column slice): the CTAs that share a chunk sequence are neighbours in the
     // grid, so the groups x slices readers of a node range run at the same time and share its rows of B in L2
     const int slice = bid % a.hub_slices, grp = (bid / a.hub_slices) % a.groups, hl = bid / (a.hub_slices * a.groups);
     const int4* __restrict__ cdesc = a.cdesc + (int64_t)grp * a.n_chunks;
-    const int32_t* __restrict__ htab = a.htab + (int64_t)grp * a.n_chunks * kHtW;
-    const size_t bs_bytes = (size_t)a.T * kRowBytes;
+    const int32_t* __restrict__ htab = a.htab + (int64_t)grp * a.n_chunks * kHtWg;
+    const size_t bs_bytes = (size_t)a.T * kRowB;
     const size_t he_bytes = align128((size_t)a.cap_hub * 8);
-    const size_t st_bytes = bs_bytes + he_bytes + align128((size_t)kHtW * 4);
+    const size_t st_bytes = bs_bytes + he_bytes + align128((size_t)kHtWg * 4);
+    const int box_rows = a.T < 256 ? a.T : 256;  // a TMA box holds at most 256 rows: taller tiles are several boxes
     uint64_t* full = bars;
     if (tid == 0) {
         mbar_init(&full[0], 1);
@@ -119,15 +136,18 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
         mbar_fence_init();
     }
     __syncthreads();
-    // one thread moves a whole stage: the T x 128 tile of B (zero filled past the matrix), the chunk's run of hub entries
+    // one thread moves a whole stage: the T x 4 GS tile of B (zero filled past the matrix), the chunk's run of hub entries
     // and its offset-table row
     auto issue = [&](int buf, int c, const int4 d) {
         unsigned char* base = smem + (size_t)buf * st_bytes;
         fence_proxy_async();  // the buffer was last read through the generic proxy (ordered by the block barrier)
-        mbar_expect_tx(&full[buf], (unsigned)bs_bytes + (unsigned)d.y * 8u + (unsigned)(kHtW * 4));
-        tma_load_2d(base, tmap, slice * kFT, d.z, &full[buf]);
+        mbar_expect_tx(&full[buf], (unsigned)bs_bytes + (unsigned)d.y * 8u + (unsigned)(kHtWg * 4));
+        for (int r0 = 0; r0 < a.T; r0 += box_rows) tma_load_2d(base + (size_t)r0 * kRowB, tmap, slice * kCols, d.z + r0, &full[buf]);
         if (d.y) bulk_load_1d(base + bs_bytes, a.hent + d.x, (unsigned)d.y * 8u, &full[buf]);
-        bulk_load_1d(base + bs_bytes + he_bytes, htab + (int64_t)c * kHtW, (unsigned)(kHtW * 4), &full[buf]);
+        bulk_load_1d(base + bs_bytes + he_bytes, htab + (int64_t)c * kHtWg, (unsigned)(kHtWg * 4), &full[buf]);
+    };
+    auto prefetch = [&](int row0) {
+        for (int r0 = 0; r0 < a.T; r0 += box_rows) tma_prefetch_l2_2d(tmap, slice * kCols, row0 + r0);
     };
     float4 acc[kKPW];
 #pragma unroll
@@ -140,12 +160,12 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
             issue(0, c, __ldg(cdesc + c));
             if (c + a.hub_lanes < a.n_chunks) d_next = __ldg(cdesc + c + a.hub_lanes);
             if (grp == 0) {
-                // the tiles of the next steps: into L2 now, so that the TMA loads one step ahead see L2 latency, not HBM latency
-                // (with one to two entries per slot and chunk a stage is ~1 us of work and the double buffer alone does not
-                // cover an HBM round trip); one slot group per chunk lane prefetches for all of them
+                // the tiles of the next steps: into L2 now, so that the TMA loads one step ahead see L2 latency, not HBM
+                // latency (the double buffer alone does not cover an HBM round trip when a stage is ~1 us of work); one
+                // slot group per chunk lane prefetches for all of them
 #pragma unroll
                 for (int i = 2; i < kHubL2PF; ++i)
-                    if (c + i * a.hub_lanes < a.n_chunks) tma_prefetch_l2_2d(tmap, slice * kFT, __ldg(cdesc + c + i * a.hub_lanes).z);
+                    if (c + i * a.hub_lanes < a.n_chunks) prefetch(__ldg(cdesc + c + i * a.hub_lanes).z);
                 if (c + kHubL2PF * a.hub_lanes < a.n_chunks) d_pf = __ldg(cdesc + c + kHubL2PF * a.hub_lanes).z;
             }
         }
@@ -158,55 +178,80 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
             }
             if (tid == 0 && grp == 0) {
                 const int cp = c + kHubL2PF * a.hub_lanes;
-                if (cp < a.n_chunks) tma_prefetch_l2_2d(tmap, slice * kFT, d_pf);
+                if (cp < a.n_chunks) prefetch(d_pf);
                 if (cp + a.hub_lanes < a.n_chunks) d_pf = __ldg(cdesc + cp + a.hub_lanes).z;
             }
             mbar_wait(&full[buf], (unsigned)(it >> 1) & 1u);
             const unsigned char* base = smem + (size_t)buf * st_bytes;
-            const unsigned char* Bl = base + lane * 16;
+            const unsigned char* Bl = base + gl * 16;
             const int2* he = reinterpret_cast<const int2*>(base + bs_bytes);
-            const int32_t* ht = reinterpret_cast<const int32_t*>(base + bs_bytes + he_bytes);
-            // the warp's 17 slot offsets: four broadcast LDS.128 + one LDS.32 (the table row and warp * 16 ints are 16-byte aligned)
+            const int32_t* ht = reinterpret_cast<const int32_t*>(base + bs_bytes + he_bytes) + (warp * NSUB + sub) * kKPW;
+            // the sub-group's 17 slot offsets: four LDS.128 + one LDS.32 (the table row and 16-int steps are 16-byte aligned)
             int hofs[kKPW + 1];
             {
-                const int4* ht4 = reinterpret_cast<const int4*>(ht + warp * kKPW);
+                const int4* ht4 = reinterpret_cast<const int4*>(ht);
 #pragma unroll
                 for (int i = 0; i < kKPW / 4; ++i) {
                     const int4 t = ht4[i];
                     hofs[4 * i] = t.x; hofs[4 * i + 1] = t.y; hofs[4 * i + 2] = t.z; hofs[4 * i + 3] = t.w;
                 }
-                hofs[kKPW] = ht[warp * kKPW + kKPW];
+                hofs[kKPW] = ht[kKPW];
             }
+            if (NSUB == 1) {
 #pragma unroll
-            for (int kk = 0; kk < kKPW; ++kk) {
-                int q = hofs[kk];
-                const int h1 = hofs[kk + 1];
+                for (int kk = 0; kk < kKPW; ++kk) {
+                    int q = hofs[kk];
+                    const int h1 = hofs[kk + 1];
 #pragma unroll 1
-                for (; q + 4 <= h1; q += 4) {
-                    const int2 e0 = he[q], e1 = he[q + 1], e2 = he[q + 2], e3 = he[q + 3];
-                    const float4 b0 = lds128(Bl + e0.x), b1 = lds128(Bl + e1.x), b2 = lds128(Bl + e2.x), b3 = lds128(Bl + e3.x);
-                    fma4p(acc[kk], __int_as_float(e0.y), b0);
-                    fma4p(acc[kk], __int_as_float(e1.y), b1);
-                    fma4p(acc[kk], __int_as_float(e2.y), b2);
-                    fma4p(acc[kk], __int_as_float(e3.y), b3);
+                    for (; q + 4 <= h1; q += 4) {
+                        const int2 e0 = he[q], e1 = he[q + 1], e2 = he[q + 2], e3 = he[q + 3];
+                        const float4 b0 = lds128(Bl + e0.x), b1 = lds128(Bl + e1.x), b2 = lds128(Bl + e2.x), b3 = lds128(Bl + e3.x);
+                        fma4p(acc[kk], __int_as_float(e0.y), b0);
+                        fma4p(acc[kk], __int_as_float(e1.y), b1);
+                        fma4p(acc[kk], __int_as_float(e2.y), b2);
+                        fma4p(acc[kk], __int_as_float(e3.y), b3);
+                    }
+                    if (q + 2 <= h1) {
+                        const int2 e0 = he[q], e1 = he[q + 1];
+                        const float4 b0 = lds128(Bl + e0.x), b1 = lds128(Bl + e1.x);
+                        fma4p(acc[kk], __int_as_float(e0.y), b0);
+                        fma4p(acc[kk], __int_as_float(e1.y), b1);
+                        q += 2;
+                    }
+                    if (q < h1) {
+                        const int2 e0 = he[q];
+                        fma4p(acc[kk], __int_as_float(e0.y), lds128(Bl + e0.x));
+                    }
                 }
-                if (q + 2 <= h1) {
-                    const int2 e0 = he[q], e1 = he[q + 1];
-                    const float4 b0 = lds128(Bl + e0.x), b1 = lds128(Bl + e1.x);
-                    fma4p(acc[kk], __int_as_float(e0.y), b0);
-                    fma4p(acc[kk], __int_as_float(e1.y), b1);
-                    q += 2;
-                }
-                if (q < h1) {
-                    const int2 e0 = he[q];
-                    fma4p(acc[kk], __int_as_float(e0.y), lds128(Bl + e0.x));
+            } else {
+                // NSUB sub-groups in lock step: the warp makes as many trips as the longest of its NSUB runs needs, two entries
+                // per trip; a sub-group past the end of its run sits the trip out.  Predicated, not branched: the sub-groups
+                // disagree on the predicates and a branch would serialise them (measured: 22 ms against 16 ms at the
+                // 6.25 M x 1 024 shard).  Walking two positions per trip for more chains in flight did not help (8.9 vs 8.5 ms).
+#pragma unroll
+                for (int kk = 0; kk < kKPW; ++kk) {
+                    int q = hofs[kk];
+                    const int h1 = hofs[kk + 1];
+                    const int n_trip = (__reduce_max_sync(0xffffffffu, h1 - q) + 1) >> 1;
+#pragma unroll 1
+                    for (int t = 0; t < n_trip; ++t, q += 2) {
+                        const bool p0 = q < h1, p1 = q + 1 < h1;
+                        int2 e0 = make_int2(0, 0), e1 = make_int2(0, 0);
+                        if (p0) e0 = he[q];
+                        if (p1) e1 = he[q + 1];
+                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                        if (p0) b0 = lds128(Bl + e0.x);
+                        if (p1) b1 = lds128(Bl + e1.x);
+                        if (p0) fma4p(acc[kk], __int_as_float(e0.y), b0);
+                        if (p1) fma4p(acc[kk], __int_as_float(e1.y), b1);
+                    }
                 }
             }
             __syncthreads();
         }
     }
-    float* dst = a.partials + ((int64_t)hl * a.Kv + grp * kKv + warp * kKPW) * a.ldp + (int64_t)(slice * 32 + lane) * 4;
-    if (slice * 32 + lane < a.n_chunks4) {  // (the last slice of a width that is no multiple of 128 is narrower; TMA zero-fills it)
+    float* dst = a.partials + ((int64_t)hl * a.Kv + grp * kSlots + (warp * NSUB + sub) * kKPW) * a.ldp + (int64_t)(slice * GS + gl) * 4;
+    if (slice * GS + gl < a.n_chunks4) {  // (the last slice of a width that is no multiple of the slice width is narrower; TMA zero-fills it)
 #pragma unroll
         for (int kk = 0; kk < kKPW; ++kk) *reinterpret_cast<float4*>(dst + (int64_t)kk * a.ldp) = acc[kk];
     }
@@ -286,12 +331,17 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
                 }
         }
     }
-    auto load_self = [&](float4(&dst)[R][NQ], int sjx) {
+    // the self-loop operand of (super job sjx, row r) is at selfp + r * jrow_stride once selfp has been advanced to sjx:
+    // running pointers instead of a 64-bit multiply per row and job
+    const int64_t jrow_stride = (int64_t)kJobRows * a.ldb;
+    const int64_t sj_stride = (int64_t)a.doc_lanes * kSJRows * a.ldb;
+    const int n32 = (int)a.n;
+    auto load_self = [&](float4(&dst)[R][NQ], int sjx, const float* selfp) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int64_t row = (int64_t)sjx * kSJRows + r * kJobRows + grp;
-            if (!TABLE && sjx < n_sj && row < a.n) {
-                const float* p = a.B + row * a.ldb + (int64_t)q0 * 4;
+            const int row = sjx * kSJRows + r * kJobRows + grp;
+            if (!TABLE && sjx < n_sj && row < n32) {
+                const float* p = selfp + r * jrow_stride;
 #pragma unroll
                 for (int u = 0; u < NQ; ++u) dst[r][u] = valid[u] ? ldg_f4_stream(p + u * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
@@ -313,12 +363,15 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
     auto load_bits = [&](int sjx) {
         Bits b;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int u = 0; u < NQ; ++u) b.w[r][u] = 0u;
-            const int64_t row = (int64_t)sjx * kSJRows + r * kJobRows + grp;
-            if (a.keep_bits && sjx < n_sj && row < a.n) {
-                const uint32_t* p = a.keep_bits + row * mask_words + slice * NQ;
+        if (!a.keep_bits) return b;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = sjx * kSJRows + r * kJobRows + grp;
+            if (sjx < n_sj && row < n32) {
+                const uint32_t* p = a.keep_bits + (int64_t)row * mask_words + slice * NQ;
                 if (NQ == 4) {
                     const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
                     b.w[r][0] = t.x; b.w[r][1 % NQ] = t.y; b.w[r][2 % NQ] = t.z; b.w[r][3 % NQ] = t.w;
@@ -332,8 +385,14 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
         }
         return b;
     };
+    const float* selfp = a.B + ((int64_t)dl * kSJRows + grp) * a.ldb + (int64_t)q0 * 4;
+    float* yp = epi.Y + ((int64_t)dl * kSJRows + grp) * epi.ldy + (int64_t)q0 * 4;
+    const int64_t yrow_stride = (int64_t)kJobRows * epi.ldy;
+    const int64_t ysj_stride = (int64_t)a.doc_lanes * kSJRows * epi.ldy;
+    // nothing to do after the sums: plain product without bias / activation / scale / dropout
+    const bool plain = !epi.bias && !epi.relu && !epi.out_scale && !a.keep_bits && epi.drop_mode != 2;
     float4 cur[R][NQ];
-    load_self(cur, dl);
+    load_self(cur, dl, selfp);
     Bits kbits = load_bits(dl);
     mbar_wait(bhbar, 0);
     const unsigned char* BHl = smem + gl * 16;
@@ -391,8 +450,7 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
                 if (p < n_nh[r]) {
                     const int2 en = ent[r][p];
                     const float v = __int_as_float(en.y);
-                    const int64_t row = (int64_t)sj * kSJRows + r * kJobRows + grp;
-                    if ((int64_t)en.x == row) {
+                    if (en.x == sj * kSJRows + r * kJobRows + grp) {
 #pragma unroll
                         for (int u = 0; u < NQ; ++u) fma4p(acc[r][u], v, cur[r][u]);
                     } else {
@@ -404,7 +462,8 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
                 }
             }
         }
-        load_self(cur, sj + a.doc_lanes);  // next job's self-loop operand: in flight during the hub-column loop
+        selfp += sj_stride;
+        load_self(cur, sj + a.doc_lanes, selfp);  // next job's self-loop operand: in flight during the hub-column loop
 #pragma unroll
         for (int r = 0; r < R; ++r) ent[r] += n_nh[r];
         if (R == 1) {
@@ -432,13 +491,19 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
                 for (int u = 0; u < NQ; ++u) fma4p(acc[0][u], v0, lds128(r0 + 128 * u));
             }
         } else {
-            // R rows in lock step, one entry of each per trip: R independent chains (rows of a graph have near-equal lengths)
+            // R rows in lock step, one entry of each per trip: R independent chains.  Rows of one graph have near-equal
+            // lengths: up to the shortest row of the WARP the trips carry no predicates at all; the few entries beyond
+            // it are walked row by row.
+            int min_hub = n_hub[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) min_hub = min(min_hub, n_hub[r]);
+            min_hub = __reduce_min_sync(0xffffffffu, min_hub);
 #pragma unroll 1
-            for (int p = 0; p < max_hub; ++p) {
+            for (int p = 0; p < min_hub; ++p) {
                 int2 e[R];
                 float4 b[R][NQ];
 #pragma unroll
-                for (int r = 0; r < R; ++r) e[r] = (p < n_hub[r]) ? ent[r][p] : make_int2(0, 0);  // (hub row 0, weight 0: adds nothing)
+                for (int r = 0; r < R; ++r) e[r] = ent[r][p];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const unsigned char* rp = BHl + e[r].x * NQ;
@@ -447,11 +512,19 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
                 }
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    if (p < n_hub[r]) {
-                        const float v = __int_as_float(e[r].y);
+                    const float v = __int_as_float(e[r].y);
 #pragma unroll
-                        for (int u = 0; u < NQ; ++u) fma4p(acc[r][u], v, b[r][u]);
-                    }
+                    for (int u = 0; u < NQ; ++u) fma4p(acc[r][u], v, b[r][u]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                for (int p = min_hub; p < n_hub[r]; ++p) {
+                    const int2 e0 = ent[r][p];
+                    const unsigned char* rp = BHl + e0.x * NQ;
+                    const float v = __int_as_float(e0.y);
+#pragma unroll
+                    for (int u = 0; u < NQ; ++u) fma4p(acc[r][u], v, lds128(rp + 128 * u));
                 }
             }
         }
@@ -466,8 +539,8 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
             if (!produce[r]) continue;
             // fused epilogue (EpiStore semantics, tg_epilogue.cuh) with the per-thread constants held in registers
             const int64_t row = (int64_t)sj * kSJRows + r * kJobRows + grp;
-            float* yrow = epi.Y + row * epi.ldy + (int64_t)q0 * 4;
-            if (row >= epi.raw_row_begin) {
+            float* yrow = yp + r * yrow_stride;
+            if (plain || row >= epi.raw_row_begin) {
 #pragma unroll
                 for (int u = 0; u < NQ; ++u)
                     if (valid[u]) *reinterpret_cast<float4*>(yrow + u * 32) = acc[r][u];
@@ -503,6 +576,7 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
                 }
             }
         }
+        yp += ysj_stride;
     }
 }
 
@@ -562,7 +636,7 @@ __global__ void __launch_bounds__(256) r2_keep_bits_half_kernel(uint32_t* __rest
     }
 }
 
-template <int NQ, bool TABLE>
+template <int GS, int NQ, bool TABLE>
 __global__ void __launch_bounds__(kThreads, 1) roles2_kernel(const R2Args a, const EpiStore epi, const __grid_constant__ CUtensorMap tmapB,
                                                             const __grid_constant__ CUtensorMap tmapJob) {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
@@ -573,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) roles2_kernel(const R2Args a, con
     const int bid = blockIdx.x;
     if (bid < n_hub_ctas) {
         if (a.only_role == 2) return;
-        hub_role(a, &tmapB, smem, bars, bid);
+        hub_role<GS>(a, &tmapB, smem, bars, bid);
     } else {
         if (a.only_role == 1) return;
         doc_role<NQ, TABLE>(a, epi, &tmapJob, smem, bars, bid - n_hub_ctas);
@@ -974,43 +1048,46 @@ __global__ void r2_hub_deg_kernel(const int32_t* __restrict__ rowptr, const int3
     for (int p = s + threadIdx.x; p < e; p += blockDim.x) atomicAdd(deg + colidx[p], 1);
 }
 
-// one block per hub row: key = ((group * n_chunks) + chunk) * 256 + slot inside the group, for each of its entries, in
-// storage (column) order.  A heavy hub row is dealt over nv slots by column residue: every slot sees every chunk.
+// one block per hub row: key = ((group * n_chunks) + chunk) * S + slot inside the group (S = slots per group, a power of
+// two), for each of its entries, in storage (column) order.  A heavy hub row is dealt over nv slots by column residue:
+// every slot sees every chunk.
 __global__ void r2_hub_keys_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                    const int32_t* __restrict__ hub_rows, const int64_t* __restrict__ hub_ofs,
-                                   const int32_t* __restrict__ node_chunk, int n_chunks, const int32_t* __restrict__ vmap,
+                                   const int32_t* __restrict__ node_chunk, int n_chunks, int s_shift, const int32_t* __restrict__ vmap,
                                    const int32_t* __restrict__ vcnt, uint32_t* __restrict__ keys, int32_t* __restrict__ src) {
     const int k = blockIdx.x;
     const int r = hub_rows[k];
     const int s = rowptr[r], e = rowptr[r + 1];
     const int64_t o = hub_ofs[k];
     const int nv = vcnt[k];
+    const uint32_t s_mask = (1u << s_shift) - 1u;
     for (int p = s + threadIdx.x; p < e; p += blockDim.x) {
         const int c = colidx[p];
         const uint32_t slot = (uint32_t)vmap[k * 8 + (c % nv)];
-        keys[o + (p - s)] = ((slot >> 8) * (uint32_t)n_chunks + (uint32_t)node_chunk[c]) * (uint32_t)kKv + (slot & 255u);
+        keys[o + (p - s)] = (((slot >> s_shift) * (uint32_t)n_chunks + (uint32_t)node_chunk[c]) << s_shift) | (slot & s_mask);
         src[o + (p - s)] = p;
     }
 }
 
 __global__ void r2_hub_gather_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ src,
                                      const int32_t* __restrict__ colidx, const float* __restrict__ vals, int64_t hub_nnz,
-                                     int n_chunks, const int32_t* __restrict__ cstart, int2* __restrict__ hent) {
+                                     int n_chunks, int s_shift, int row_bytes, const int32_t* __restrict__ cstart, int2* __restrict__ hent) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= hub_nnz) return;
     const int p = src[i];
-    const int c = (int)((keys[i] / (uint32_t)kKv) % (uint32_t)n_chunks);
-    hent[i] = make_int2((colidx[p] - cstart[c]) * kRowBytes, __float_as_int(vals[p]));
+    const int c = (int)((keys[i] >> s_shift) % (uint32_t)n_chunks);
+    hent[i] = make_int2((colidx[p] - cstart[c]) * row_bytes, __float_as_int(vals[p]));
 }
 
-// tab[gc][s] = first sorted position with key >= gc*256 + s   (gc = group * n_chunks + chunk; s = 256: start of the next run)
-__global__ void r2_hub_table_kernel(const uint32_t* __restrict__ keys, int64_t hub_nnz, int n_runs, int32_t* __restrict__ tab) {
+// tab[gc][s] = first sorted position with key >= gc*S + s   (gc = group * n_chunks + chunk; s = S: start of the next run)
+__global__ void r2_hub_table_kernel(const uint32_t* __restrict__ keys, int64_t hub_nnz, int n_runs, int S, int32_t* __restrict__ tab) {
+    const int W = S + 4;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)n_runs * kHtW) return;
-    const int c = (int)(i / kHtW);
-    int s = (int)(i % kHtW);
-    if (s > kKv) s = kKv;
-    const uint64_t want = (uint64_t)c * kKv + s;
+    if (i >= (int64_t)n_runs * W) return;
+    const int c = (int)(i / W);
+    int s = (int)(i % W);
+    if (s > S) s = S;
+    const uint64_t want = (uint64_t)c * S + s;
     int64_t lo = 0, hi = hub_nnz;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
@@ -1021,14 +1098,15 @@ __global__ void r2_hub_table_kernel(const uint32_t* __restrict__ keys, int64_t h
 }
 
 // offsets relative to the run's even-aligned base (16-byte aligned bulk copies) + run descriptors
-__global__ void r2_hub_rel_kernel(const int32_t* __restrict__ tab_abs, int n_runs, int n_chunks, const int32_t* __restrict__ cstart,
+__global__ void r2_hub_rel_kernel(const int32_t* __restrict__ tab_abs, int n_runs, int n_chunks, int S, const int32_t* __restrict__ cstart,
                                   int32_t* __restrict__ tab, int4* __restrict__ cdesc) {
+    const int W = S + 4;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)n_runs * kHtW) return;
-    const int c = (int)(i / kHtW), s = (int)(i % kHtW);
-    const int base = tab_abs[(int64_t)c * kHtW] & ~1;
+    if (i >= (int64_t)n_runs * W) return;
+    const int c = (int)(i / W), s = (int)(i % W);
+    const int base = tab_abs[(int64_t)c * W] & ~1;
     tab[i] = tab_abs[i] - base;
-    if (s == 0) cdesc[c] = make_int4(base, ((tab_abs[(int64_t)c * kHtW + kKv] - base) + 1) & ~1, cstart[c % n_chunks], 0);
+    if (s == 0) cdesc[c] = make_int4(base, ((tab_abs[(int64_t)c * W + S] - base) + 1) & ~1, cstart[c % n_chunks], 0);
 }
 
 __global__ void r2_row_len_kernel(const int32_t* __restrict__ rowptr, int64_t n, int64_t n_pad, int hub_threshold, int32_t* __restrict__ len) {
@@ -1089,8 +1167,9 @@ int env_int2(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-size_t hub_smem(int T, int cap_hub) {
-    return 2 * ((size_t)T * kRowBytes + align128((size_t)cap_hub * 8) + align128((size_t)kHtW * 4));
+size_t hub_smem(int T, int cap_hub, int gs) {
+    const size_t slots = (size_t)kKv * (32 / gs);
+    return 2 * ((size_t)T * 16 * gs + align128((size_t)cap_hub * 8) + align128((slots + 4) * 4));
 }
 size_t doc_smem(int Kh, int cap_doc, int nq, int stages) {
     const int r = 4 / nq;  // plan jobs per super job (rows per group)
@@ -1118,12 +1197,12 @@ struct SlotDeal {
     std::vector<int32_t> vcnt, vmap;
     double max_warp = 0.0;
 };
-SlotDeal deal_slots(const std::vector<double>& len, int G) {
+SlotDeal deal_slots(const std::vector<double>& len, int G, int nsub) {
     const int Kh = (int)len.size();
     SlotDeal d;
     d.vcnt.assign((size_t)Kh, 1);
     d.vmap.assign((size_t)Kh * 8, 0);
-    int spare = G * kKv - Kh;
+    int spare = G * kKv * nsub - Kh;
     while (spare > 0) {
         int best = -1;
         for (int k = 0; k < Kh; ++k)
@@ -1137,17 +1216,21 @@ SlotDeal deal_slots(const std::vector<double>& len, int G) {
     for (int k = 0; k < Kh; ++k)
         for (int j = 0; j < d.vcnt[(size_t)k]; ++j) pieces.push_back(Piece{len[(size_t)k] / d.vcnt[(size_t)k], k, j});
     std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) { return x.w > y.w; });
-    const int W = G * kWarps;
+    // units of 16 slots: a warp (GS = 32) or a sub-group of a warp; unit u = (group * 16 + warp) * nsub + sub.  Pieces go
+    // longest-first to the least loaded unit, so position p of every unit holds pieces of similar weight: the sub-groups of
+    // a warp, which walk position p in lock step, then have runs of similar length.
+    const int W = G * kWarps * nsub;
     std::vector<double> load((size_t)W, 0.0);
     std::vector<int> used((size_t)W, 0);
     for (const Piece& pc : pieces) {
         int best = -1;
         for (int w = 0; w < W; ++w)
             if (used[(size_t)w] < kKPW && (best < 0 || load[(size_t)w] < load[(size_t)best])) best = w;
-        d.vmap[(size_t)pc.k * 8 + pc.j] = best * kKPW + used[(size_t)best];  // = group * 256 + warp * 16 + position
+        d.vmap[(size_t)pc.k * 8 + pc.j] = best * kKPW + used[(size_t)best];  // = group * S + (warp * nsub + sub) * 16 + position
         used[(size_t)best] += 1;
         load[(size_t)best] += pc.w;
     }
+    // the pace of a warp is set by its slowest sub-group
     for (int w = 0; w < W; ++w) d.max_warp = std::max(d.max_warp, load[(size_t)w]);
     return d;
 }
@@ -1183,7 +1266,7 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     if (env_int2("TG_ROLES2", 1) == 0) return TG_OK;
     const bool all_hub = pl->r2_rect == 2;  // rectangular [K x N] operand whose rows are all hub rows: hub side only
     if (!colidx || !vals || pl->nnz == 0) return TG_OK;
-    if (pl->n_hub < 1 || pl->n_hub > kMaxGroups * kKv) return TG_OK;
+    if (pl->n_hub < 1 || pl->n_hub > kMaxHubRows) return TG_OK;
     if (pl->hub_threshold > 16383) return TG_OK;  // row descriptors keep the entry count of a short row in 15 bits
     if (!all_hub) {
         if (pl->n_rows != pl->n_cols) return TG_OK;
@@ -1195,10 +1278,20 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     const int64_t hub_nnz = pl->hub_nnz;
     if (hub_nnz >= (int64_t)0x7fffffff) return TG_OK;
 
-    // ---- slot groups ------------------------------------------------------------------------------------------------------
+    // ---- lanes per slot sub-group (hub_role<GS>) and slot groups -----------------------------------------------------------
+    // Up to 256 hub rows a warp per slot and 128-column slices; more hub rows: narrower slices, 512 / 1 024 slots per CTA.
     // One more group than strictly needed buys spare slots for splitting the heavy rows (balance) at the price of one more
-    // reader of every tile of B.  Cost model in shared-memory wavefronts per 128-column slice, summed over the hub CTAs of a
+    // reader of every tile of B.  Cost model in shared-memory wavefronts per 128 columns, summed over the hub CTAs of a
     // chunk lane: 5 per entry on the critical warp (x 16 warps that wait for it) + 4 per node for the TMA fill, per group.
+    int gs = Kh <= kKv ? 32 : (Kh <= 2 * kKv ? 16 : 8);
+    {
+        const int gs_force = env_int2("TG_ROLES2_GS", 0);
+        if (gs_force == 32 || gs_force == 16 || gs_force == 8) gs = gs_force;
+    }
+    const int nsub = 32 / gs;
+    const int S = kKv * nsub;  // slots per group
+    int s_shift = 8;
+    while ((1 << s_shift) < S) ++s_shift;
     std::vector<int64_t> hub_ofs((size_t)Kh);
     std::vector<double> len((size_t)Kh);
     {
@@ -1210,21 +1303,23 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
             run += h_rowptr[(size_t)r + 1] - h_rowptr[(size_t)r];
         }
     }
-    const int g_min = (Kh + kKv - 1) / kKv;
+    const int g_min = (Kh + S - 1) / S;
+    if (g_min > kMaxGroups) return TG_OK;
     const int g_force = env_int2("TG_ROLES2_GROUPS", 0);
+    // The minimum number of groups unless its best deal leaves the slowest unit more than 50 % above the mean load: a second
+    // reader of every tile and twice the (slot, chunk) visits cost more than a moderate imbalance (measured at K = 1 024:
+    // one group of 1 024 slots 20 % faster than two groups with the heavy rows split).
     SlotDeal deal;
     int G = 0;
     {
-        double best_cost = 0.0;
+        double total = 0.0;
+        for (double l : len) total += l;
         for (int g = g_min; g <= std::min(g_min + 1, kMaxGroups); ++g) {
-            if (g_force > 0 && g != g_force && g_force >= g_min && g_force <= kMaxGroups) continue;
-            SlotDeal d = deal_slots(len, g);
-            const double cost = (double)g * (5.0 * kWarps * d.max_warp + 4.0 * (double)n_nodes);
-            if (G == 0 || cost < best_cost) {
-                best_cost = cost;
-                G = g;
-                deal = std::move(d);
-            }
+            if (g_force >= g_min && g_force <= kMaxGroups && g != g_force) continue;
+            deal = deal_slots(len, g, nsub);
+            G = g;
+            const double mean_unit = total / (double)(g * kWarps * nsub);
+            if (deal.max_warp <= 1.5 * mean_unit) break;
         }
     }
     const std::vector<int32_t>& vcnt = deal.vcnt;
@@ -1270,14 +1365,15 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     // its tile of B and the entries of any one group always fit one shared-memory stage: document ranges are cut by the row
     // limit, the dense topic-topic block (every hub node carries Kh entries) by the entry limit.
     const double avg_deg = (double)hub_nnz / (double)n_nodes;
-    static const int kTs[] = {192, 176, 160, 144, 128, 96, 64, 32};
-    const int t_first = env_int2("TG_ROLES2_T", 192);
+    static const int kTs[] = {512, 256, 192, 176, 160, 144, 128, 96, 64, 32};  // (taller than a TMA box of 256 rows: whole boxes)
+    const int t_first = env_int2("TG_ROLES2_T", 512);
+    const int row_bytes = 16 * gs;  // bytes of a row of the staged tile
     int T = 0, cap = 0;
     for (int t : kTs) {
         if (t > t_first) continue;
-        const int64_t room = (int64_t)(kSmemMax - 256) / 2 - (int64_t)t * kRowBytes - (int64_t)align128((size_t)kHtW * 4);
+        const int64_t room = (int64_t)(kSmemMax - 256) / 2 - (int64_t)t * row_bytes - (int64_t)align128((size_t)(S + 4) * 4);
         const int cap_fit = (int)std::min<int64_t>(room / 8, 1 << 20) & ~1;
-        if (cap_fit < Kh + 2 || (double)cap_fit < 1.25 * avg_deg * t + 32) continue;
+        if (room <= 0 || cap_fit < Kh + 2 || (double)cap_fit < 1.25 * avg_deg * t + 32) continue;
         T = t;
         cap = cap_fit;
         break;
@@ -1315,7 +1411,7 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     const int n_chunks = (int)cstart.size();
     cstart.push_back((int32_t)n_nodes);
     const int64_t n_runs = (int64_t)G * n_chunks;  // (group, chunk) runs of the entry list
-    if ((uint64_t)n_runs * (uint64_t)kKv >= 0xFFFFFFFFull) return give_up();
+    if ((uint64_t)n_runs * (uint64_t)S >= 0xFFFFFFFFull) return give_up();
     {
         int32_t *d_node_chunk = nullptr, *d_cstart = nullptr;
         auto drop = [&]() { cudaFree(d_node_chunk); cudaFree(d_cstart); };
@@ -1324,25 +1420,27 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         TG_TRY2(cudaMalloc((void**)&d_cstart, (size_t)(n_chunks + 1) * sizeof(int32_t)));
         TG_TRY2(cudaMemcpyAsync(d_node_chunk, node_chunk.data(), (size_t)n_nodes * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         TG_TRY2(cudaMemcpyAsync(d_cstart, cstart.data(), (size_t)(n_chunks + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        r2_hub_keys_kernel<<<Kh, 256, 0, st>>>(rowptr, colidx, pl->hub_rows, d_ofs, d_node_chunk, n_chunks, pl->r2_vmap, pl->r2_vcnt, keys_a, src_a);
+        r2_hub_keys_kernel<<<Kh, 256, 0, st>>>(rowptr, colidx, pl->hub_rows, d_ofs, d_node_chunk, n_chunks, s_shift, pl->r2_vmap, pl->r2_vcnt,
+                                               keys_a, src_a);
         TG_TRY2(cudaGetLastError());
         size_t tmp_bytes = 0;
         int end_bit = 1;
-        while (end_bit < 32 && (1ull << end_bit) < (uint64_t)n_runs * kKv) ++end_bit;
+        while (end_bit < 32 && (1ull << end_bit) < (uint64_t)n_runs * S) ++end_bit;
         TG_TRY2(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, src_a, src_b, (int)hub_nnz, 0, end_bit, st));
         TG_TRY2(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
         // stable: inside a (group, chunk, slot) run the entries keep their column order
         TG_TRY2(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_a, keys_b, src_a, src_b, (int)hub_nnz, 0, end_bit, st));
-        const int64_t tab_n = n_runs * kHtW;
+        const int64_t tab_n = n_runs * (S + 4);
         TG_TRY2(cudaMalloc((void**)&tab_abs, (size_t)tab_n * sizeof(int32_t)));
         TG_TRY2(cudaMalloc((void**)&pl->r2_htab, (size_t)tab_n * sizeof(int32_t)));
         TG_TRY2(cudaMalloc((void**)&pl->r2_cdesc, (size_t)n_runs * sizeof(int4)));
-        r2_hub_table_kernel<<<(unsigned)ceil_div64(tab_n, 256), 256, 0, st>>>(keys_b, hub_nnz, (int)n_runs, tab_abs);
+        r2_hub_table_kernel<<<(unsigned)ceil_div64(tab_n, 256), 256, 0, st>>>(keys_b, hub_nnz, (int)n_runs, S, tab_abs);
         TG_TRY2(cudaGetLastError());
-        r2_hub_rel_kernel<<<(unsigned)ceil_div64(tab_n, 256), 256, 0, st>>>(tab_abs, (int)n_runs, n_chunks, d_cstart, pl->r2_htab, pl->r2_cdesc);
+        r2_hub_rel_kernel<<<(unsigned)ceil_div64(tab_n, 256), 256, 0, st>>>(tab_abs, (int)n_runs, n_chunks, S, d_cstart, pl->r2_htab, pl->r2_cdesc);
         TG_TRY2(cudaGetLastError());
         TG_TRY2(cudaMemsetAsync(pl->r2_hent, 0, ((size_t)hub_nnz + 2) * sizeof(int2), st));
-        r2_hub_gather_kernel<<<(unsigned)ceil_div64(hub_nnz, 256), 256, 0, st>>>(keys_b, src_b, colidx, vals, hub_nnz, n_chunks, d_cstart, pl->r2_hent);
+        r2_hub_gather_kernel<<<(unsigned)ceil_div64(hub_nnz, 256), 256, 0, st>>>(keys_b, src_b, colidx, vals, hub_nnz, n_chunks, s_shift, row_bytes,
+                                                                                 d_cstart, pl->r2_hent);
         TG_TRY2(cudaGetLastError());
         TG_TRY2(cudaStreamSynchronize(st));
 #undef TG_TRY2
@@ -1351,6 +1449,7 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         pl->r2_n_chunks = n_chunks;
         pl->r2_cap_hub = cap;
         pl->r2_groups = G;
+        pl->r2_gs = gs;
     }
     // the sort scratch is not needed any more: release it before the document side allocates
     cudaFree(keys_a); cudaFree(keys_b); cudaFree(src_a); cudaFree(src_b); cudaFree(tab_abs); cudaFree(tmp);
@@ -1413,12 +1512,21 @@ bool roles2_applicable(const tg_plan* pl, const StreamCall& c) {
     return true;
 }
 
+// bytes of the per-CTA hub partials: (chunk lanes x groups x slices) <= 148 CTAs, one row of `ld` floats per slot and chunk lane
+static size_t partial_bytes(const tg_plan* pl, int32_t n_feat) {
+    const size_t ld = (size_t)((n_feat + 3) / 4) * 4;
+    const int nsub = 32 / pl->r2_gs;
+    const size_t slots = (size_t)pl->r2_groups * kKv * nsub;
+    const int slices = n_feat <= 32 ? 1 : (n_feat + 4 * pl->r2_gs - 1) / (4 * pl->r2_gs);
+    const size_t lanes_max = std::max<size_t>(1, (size_t)kNumSM / ((size_t)pl->r2_groups * slices));
+    return ((lanes_max * slots * ld * sizeof(float) + 16) + 255) & ~(size_t)255;
+}
+
 size_t roles2_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
     if (!pl || !pl->r2_ok) return 0;
     if (pl->r2_rect == 1) return 16;
     const size_t ld = (size_t)((n_feat + 3) / 4) * 4;
-    // per-CTA hub partials: (chunk lanes x groups) <= 148 CTAs of 256 slots each
-    const size_t part = (size_t)kNumSM * kKv * ld * sizeof(float) + 16;
+    const size_t part = partial_bytes(pl, n_feat);
     if (pl->r2_rect == 2) return part;
     // + the bit-packed dropout keep mask (four words per row and 128 columns)
     return part + (size_t)pl->n_rows * (((ld + kFT - 1) / kFT) * 16) + 256;
@@ -1460,28 +1568,39 @@ void split_sms(double hub_w, double doc_w, int hub_unit, int doc_unit, int n_chu
     *doc_lanes_out = std::min(best_d, std::max(n_jobs, 1));
 }
 
-template <int NQ>
-int launch_wide(const R2Args& a, const EpiStore& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem, unsigned grid,
-                cudaStream_t st) {
-    TG_CUDA(cudaFuncSetAttribute(roles2_kernel<NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    roles2_kernel<NQ, false><<<grid, kThreads, smem, st>>>(a, epi, tmap, tmap_job);
+template <int GS, int NQ, bool TABLE>
+int launch_roles(const R2Args& a, const EpiStore& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem, unsigned grid,
+                 cudaStream_t st) {
+    TG_CUDA(cudaFuncSetAttribute(roles2_kernel<GS, NQ, TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roles2_kernel<GS, NQ, TABLE><<<grid, kThreads, smem, st>>>(a, epi, tmap, tmap_job);
     TG_LAUNCH_CHECK();
     return TG_OK;
 }
-template <int NQ>
-int launch_table(const R2Args& a, const EpiStore& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem, unsigned grid,
-                 cudaStream_t st) {
-    TG_CUDA(cudaFuncSetAttribute(roles2_kernel<NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    roles2_kernel<NQ, true><<<grid, kThreads, smem, st>>>(a, epi, tmap, tmap_job);
-    TG_LAUNCH_CHECK();
-    return TG_OK;
+template <int GS>
+int launch_wide_gs(int nq, const R2Args& a, const EpiStore& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem,
+                   unsigned grid, cudaStream_t st) {
+    if (nq == 4) return launch_roles<GS, 4, false>(a, epi, tmap, tmap_job, smem, grid, st);
+    if (nq == 2) return launch_roles<GS, 2, false>(a, epi, tmap, tmap_job, smem, grid, st);
+    return launch_roles<GS, 1, false>(a, epi, tmap, tmap_job, smem, grid, st);
+}
+int launch_wide(int gs, int nq, const R2Args& a, const EpiStore& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem,
+                unsigned grid, cudaStream_t st) {
+    if (gs == 32) return launch_wide_gs<32>(nq, a, epi, tmap, tmap_job, smem, grid, st);
+    if (gs == 16) return launch_wide_gs<16>(nq, a, epi, tmap, tmap_job, smem, grid, st);
+    return launch_wide_gs<8>(nq, a, epi, tmap, tmap_job, smem, grid, st);
+}
+int launch_table(int nq, const R2Args& a, const EpiStore& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem,
+                 unsigned grid, cudaStream_t st) {
+    if (nq == 4) return launch_roles<32, 4, true>(a, epi, tmap, tmap_job, smem, grid, st);
+    if (nq == 2) return launch_roles<32, 2, true>(a, epi, tmap, tmap_job, smem, grid, st);
+    return launch_roles<32, 1, true>(a, epi, tmap, tmap_job, smem, grid, st);
 }
 
 void fill_common(R2Args& a, const tg_plan* pl, const StreamCall& c) {
     memset(&a, 0, sizeof(a));
     a.hent = pl->r2_hent; a.htab = pl->r2_htab; a.cdesc = pl->r2_cdesc;
     a.T = pl->r2_T; a.n_chunks = pl->r2_n_chunks; a.cap_hub = pl->r2_cap_hub;
-    a.groups = pl->r2_groups; a.Kv = pl->r2_groups * kKv;
+    a.groups = pl->r2_groups; a.Kv = pl->r2_groups * kKv * (32 / pl->r2_gs);
     a.dent = pl->r2_dent; a.rdesc = pl->r2_rdesc; a.jdesc = pl->r2_jdesc;
     a.n_jobs = pl->r2_n_jobs; a.cap_doc = pl->r2_cap_doc;
     a.hub_rows = pl->hub_rows; a.Kh = pl->n_hub;
@@ -1498,26 +1617,27 @@ void fill_common(R2Args& a, const tg_plan* pl, const StreamCall& c) {
 int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st) {
     R2Args a;
     fill_common(a, pl, c);
-    const int nq = pl->r2_nq;
-    const int slices = (c.n_feat + kFT - 1) / kFT;               // hub role: 128-column slices
-    const int dslices = (c.n_feat + 32 * nq - 1) / (32 * nq);    // document role: 32 * nq columns
-    a.hub_slices = slices;
+    const int nq = pl->r2_nq, gs = pl->r2_gs, nsub = 32 / gs;
+    const int slices128 = (c.n_feat + kFT - 1) / kFT;            // mask layout: four words per 128 columns
+    const int hslices = (c.n_feat + 4 * gs - 1) / (4 * gs);      // hub role: slices of 4 * gs columns
+    const int dslices = (c.n_feat + 32 * nq - 1) / (32 * nq);    // document role: slices of 32 * nq columns
+    a.hub_slices = hslices;
     a.doc_slices = dslices;
     // Philox dropout: the keep mask is drawn by a separate ALU-bound kernel into a bit-packed side buffer (1 bit per
     // element) instead of inside the document role, whose CTAs have no issue slots to spare (ncu: the in-kernel RNG
-    // cost 0.4 ms at 1M x 256).  Same mask, bit for bit, as the in-kernel definition (tg_common.cuh).
+    // cost 0.4 ms at 1M x 256).  Same mask, bit for bit, as the definition in tg_common.cuh.
     if (epi.drop_mode == 1) {
-        const size_t part_bytes = ((size_t)kNumSM * kKv * a.ldp * sizeof(float) + 16 + 255) & ~(size_t)255;
-        const size_t mask_bytes = (size_t)pl->n_rows * (size_t)slices * 16;  // four words per row and 128 columns
+        const size_t part_bytes = partial_bytes(pl, c.n_feat);
+        const size_t mask_bytes = (size_t)pl->n_rows * (size_t)slices128 * 16;
         TG_REQUIRE(c.workspace_bytes >= part_bytes + mask_bytes + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B (dropout mask)",
                    c.workspace_bytes, part_bytes + mask_bytes + 16);
         uint32_t* bits = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(c.workspace) + part_bytes + 15u) & ~(uintptr_t)15u);
         if (epi.keep_thr == kDropoutHalfThr) {
-            const int n_words = slices * 4;
+            const int n_words = slices128 * 4;
             const int64_t th = pl->n_rows * (int64_t)((n_words + 3) / 4);
             r2_keep_bits_half_kernel<<<(unsigned)ceil_div64(th, 256), 256, 0, st>>>(bits, pl->n_rows, n_words, epi.seed, epi.offset, epi.offset_dev);
         } else {
-            const int n_blk = slices * 2;  // 64-column blocks, padded to whole 128-column slices
+            const int n_blk = slices128 * 2;  // 64-column blocks, padded to whole 128-column slices
             const int64_t threads = pl->n_rows * (int64_t)n_blk * 8;
             int blk_shift = -1;
             for (int sh = 0; sh < 8; ++sh)
@@ -1529,28 +1649,27 @@ int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cuda
         a.keep_bits = bits;
     }
     // share of the SMs given to the hub role: both fronts must advance together so that the second reader of a row of B
-    // hits L2 (split_sms)
-    const double hub_w = (5.0 * (double)pl->hub_nnz + 4.0 * (double)a.groups * (double)pl->n_rows) / 0.82;
+    // hits L2 (split_sms).  Weights in shared-memory wavefronts / issue slots per 128 columns (measured per role, profiles/):
+    // lock-stepped sub-groups and one-float4 document slices pay more instructions per entry and row.
+    // (narrow-slice hub role: ~3x the instructions per entry — thin (slot, chunk) runs walked in lock step; measured per role)
+    const double hub_w = ((nsub > 1 ? 14.0 : 5.0) * (double)pl->hub_nnz + 4.0 * (double)a.groups * (double)pl->n_rows) / 0.82;
     const double doc_w = (4.0 * (double)(pl->nnz - pl->hub_nnz - pl->n_rows) + 14.0 * (4.0 / nq) * (double)pl->n_rows) / 0.67;
-    split_sms(hub_w * slices, doc_w * slices, slices * a.groups, dslices, a.n_chunks, (a.n_jobs + 4 / nq - 1) / (4 / nq), pl->r2_hub_pct,
-              &a.hub_lanes, &a.doc_lanes);
+    split_sms(hub_w, doc_w, hslices * a.groups, dslices, a.n_chunks, (a.n_jobs + 4 / nq - 1) / (4 / nq), pl->r2_hub_pct, &a.hub_lanes,
+              &a.doc_lanes);
     const size_t need = (size_t)a.hub_lanes * a.Kv * a.ldp * sizeof(float);
     TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
                c.workspace_bytes, need + 16);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    TG_REQUIRE(make_tensor_map(&tmap, a.B, a.n, c.n_feat, a.ldb, a.T, kFT), TG_ERR_UNSUPPORTED,
+    TG_REQUIRE(make_tensor_map(&tmap, a.B, a.n, c.n_feat, a.ldb, std::min(a.T, 256), 4 * gs), TG_ERR_UNSUPPORTED,
                "cuTensorMapEncodeTiled failed (TMA tile of the dense operand)");
     CUtensorMap tmap_job;
     memset(&tmap_job, 0, sizeof(tmap_job));
     TG_REQUIRE(make_tensor_map(&tmap_job, a.B, a.n, c.n_feat, a.ldb, kJobRows, 32 * nq), TG_ERR_UNSUPPORTED,
                "cuTensorMapEncodeTiled failed (L2 prefetch tile of the dense operand)");
-    const size_t smem = std::max(hub_smem(a.T, a.cap_hub), doc_smem(a.Kh, a.cap_doc, nq, a.n_stages)) + 128;
-    const unsigned grid = (unsigned)(a.hub_lanes * a.groups * slices + a.doc_lanes * dslices);
-    int rc = TG_ERR_UNSUPPORTED;
-    if (nq == 4) rc = launch_wide<4>(a, epi, tmap, tmap_job, smem, grid, st);
-    else if (nq == 2) rc = launch_wide<2>(a, epi, tmap, tmap_job, smem, grid, st);
-    else if (nq == 1) rc = launch_wide<1>(a, epi, tmap, tmap_job, smem, grid, st);
+    const size_t smem = std::max(hub_smem(a.T, a.cap_hub, gs), doc_smem(a.Kh, a.cap_doc, nq, a.n_stages)) + 128;
+    const unsigned grid = (unsigned)(a.hub_lanes * a.groups * hslices + a.doc_lanes * dslices);
+    const int rc = launch_wide(gs, nq, a, epi, tmap, tmap_job, smem, grid, st);
     if (rc != TG_OK) return rc;
     FinishArgs f{a.partials, a.ldp, a.hub_lanes, a.Kh, a.Kv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
     return finish_run(f, epi, st);
@@ -1566,6 +1685,7 @@ static void narrow_smem(const tg_plan* pl, int n_feat, size_t* hub_s, size_t* do
 
 bool roles2_narrow_applicable(const tg_plan* pl, const StreamCall& c) {
     if (!pl || !pl->r2_ok || pl->r2_rect != 0 || !pl->r2_narrow_ok) return false;
+    if (pl->r2_gs != 32) return false;  // (the narrow hub role is written for the warp-per-slot layout: <= 256 hub rows per group)
     if (c.n_feat < 4 || c.n_feat > 32 || c.n_feat % 4 != 0) return false;
     // a narrow operand of a small graph is L2 resident and the gather kernel is faster (20NG shape: 0.033 vs 0.052 ms)
     if (pl->n_rows < (int64_t)pl->r2_narrow_min_rows) return false;
@@ -1668,7 +1788,7 @@ int roles2_rect_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* co
     if (pl->r2_ok || env_int2("TG_ROLES2", 1) == 0 || env_int2("TG_ROLES2_RECT", 1) == 0) return TG_OK;
     if (!colidx || !vals || pl->nnz == 0 || pl->nnz >= (int64_t)0x7fffffff) return TG_OK;
     const int64_t min_rows = pl->r2_min_rows;
-    const int max_k = kMaxGroups * kKv;
+    const int max_k = 1280;  // resident table rows / hub rows of the transposed product
     if (pl->n_rows <= max_k && pl->n_hub == pl->n_rows && pl->n_cols >= min_rows && pl->n_cols > pl->n_rows) {
         // ---- all-hub mode: the hub side of the square plan, over the columns of this matrix ----
         std::vector<int32_t> hub_rows((size_t)pl->n_rows);
@@ -1743,7 +1863,6 @@ int roles2_rect_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi,
     R2Args a;
     fill_common(a, pl, c);
     a.only_role = 0;
-    const int slices = (c.n_feat + kFT - 1) / kFT;
     CUtensorMap tmap, tmap_job;
     memset(&tmap, 0, sizeof(tmap));
     memset(&tmap_job, 0, sizeof(tmap_job));
@@ -1751,7 +1870,7 @@ int roles2_rect_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi,
         // X * W: the rows of W (c.B, n_cols of them) are the resident table; all CTAs run the document role
         const int nq = pl->r2_nq;
         const int dslices = (c.n_feat + 32 * nq - 1) / (32 * nq);
-        a.hub_slices = slices;
+        a.hub_slices = 1;
         a.doc_slices = dslices;
         a.hub_rows = pl->r2_ident; a.Kh = (int32_t)pl->n_cols;
         a.groups = 1; a.Kv = kKv;
@@ -1762,25 +1881,24 @@ int roles2_rect_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi,
         if (doc_lanes > n_sj) doc_lanes = n_sj;
         a.doc_lanes = doc_lanes;
         const size_t smem = doc_smem(a.Kh, a.cap_doc, nq, a.n_stages) + 128;
-        const unsigned grid = (unsigned)(doc_lanes * dslices);
-        if (nq == 4) return launch_table<4>(a, epi, tmap, tmap_job, smem, grid, st);
-        if (nq == 2) return launch_table<2>(a, epi, tmap, tmap_job, smem, grid, st);
-        return launch_table<1>(a, epi, tmap, tmap_job, smem, grid, st);
+        return launch_table(nq, a, epi, tmap, tmap_job, smem, (unsigned)(doc_lanes * dslices), st);
     }
     // X^T * dS: every row of this matrix is a hub row; all CTAs run the hub role over the rows of c.B, then the finish
-    a.hub_slices = a.doc_slices = slices;
+    const int gs = pl->r2_gs;
+    const int hslices = (c.n_feat + 4 * gs - 1) / (4 * gs);
+    a.hub_slices = a.doc_slices = hslices;
     a.doc_lanes = 0;
-    int hub_lanes = kNumSM / (slices * a.groups);
+    int hub_lanes = kNumSM / (hslices * a.groups);
     if (hub_lanes < 1) hub_lanes = 1;
     if (hub_lanes > a.n_chunks) hub_lanes = a.n_chunks;
     a.hub_lanes = hub_lanes;
     const size_t need = (size_t)hub_lanes * a.Kv * a.ldp * sizeof(float);
     TG_REQUIRE(c.workspace && c.workspace_bytes >= need + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B",
                c.workspace_bytes, need + 16);
-    TG_REQUIRE(make_tensor_map(&tmap, a.B, pl->n_cols, c.n_feat, a.ldb, a.T, kFT), TG_ERR_UNSUPPORTED,
+    TG_REQUIRE(make_tensor_map(&tmap, a.B, pl->n_cols, c.n_feat, a.ldb, std::min(a.T, 256), 4 * gs), TG_ERR_UNSUPPORTED,
                "cuTensorMapEncodeTiled failed (TMA tile of the dense operand)");
-    const size_t smem = hub_smem(a.T, a.cap_hub) + 128;
-    const int rc = launch_wide<4>(a, epi, tmap, tmap_job, smem, (unsigned)(hub_lanes * a.groups * slices), st);
+    const size_t smem = hub_smem(a.T, a.cap_hub, gs) + 128;
+    const int rc = launch_wide(gs, 4, a, epi, tmap, tmap_job, smem, (unsigned)(hub_lanes * a.groups * hslices), st);
     if (rc != TG_OK) return rc;
     FinishArgs f{a.partials, a.ldp, hub_lanes, a.Kh, a.Kv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
     return finish_run(f, epi, st);

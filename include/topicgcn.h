@@ -90,7 +90,8 @@ void tg_plan_destroy(tg_plan* plan);
 /* info: [0]=n_hub_rows [1]=n_segments [2]=hub_nnz [3]=max_row_nnz [4]=hub_threshold [5]=segment_nnz
  *       [6]=bits 0-1: role-specialised streaming kernels available (square graph, hub rows <= 1280),
  *           bits 2-3: rectangular sub-plan (1 = resident-table product X*W, 2 = all-hub product X^T*dS)
- *       [7]=nodes per hub chunk | hub slot groups << 16 | float4 chunks per lane of the document role << 24 */
+ *       [7]=nodes per hub chunk | hub slot groups << 16 | float4 chunks per lane of the document role << 24
+ *           | lanes per hub slot sub-group << 32 */
 int tg_plan_info(const tg_plan* plan, int64_t info_host[8]);
 /* bytes of scratch a tg_spmm* / tg_gc* call with `n_feat` columns needs (partials of split hub rows) */
 size_t tg_plan_workspace_bytes(const tg_plan* plan, int32_t n_feat);

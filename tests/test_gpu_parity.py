@@ -553,8 +553,8 @@ def test_roles2_narrow_kernel_parity(tg, monkeypatch, n_docs, n_topics, thr, C):
     assert torch.equal(y, tg.spmm(csr, S2d))
     csr_g = tg.DeviceCSR(csr.rowptr, csr.colidx, csr.vals, g.n, g.n, hub_threshold=thr, segment_nnz=max(8, thr // 2), streaming=False)
     y_g = tg.spmm(csr_g, S2d)
-    # (1 024 resident hub rows of 32 columns + the 8-deep ring do not fit shared memory: that one case takes the gather kernel)
-    assert csr.spmm_launches(S2d, C) == (1 if (n_topics == 1024 and C == 32) else 2) and csr_g.spmm_launches(S2d, C) == 1
+    # (the narrow role kernels are written for the warp-per-slot layout, <= 256 hub rows: more topics take the gather kernel)
+    assert csr.spmm_launches(S2d, C) == (2 if n_topics <= 256 else 1) and csr_g.spmm_launches(S2d, C) == 1
     assert float((y_g - y).abs().max() / y.abs().max()) <= SPMM_RTOL
     target = rng.integers(0, C, size=n_docs)
     index = np.sort(rng.choice(n_docs, size=n_docs * 2 // 3, replace=False))
@@ -754,7 +754,7 @@ def c4_small(tg):
 def test_c4_shape_plan(tg, c4_small):
     g, csr, _ = c4_small
     assert csr.n_hub_rows == 1024 and csr.streaming and csr.roles2
-    assert csr.hub_groups in (4, 5) and csr.doc_nq == 1
+    assert csr.hub_gs == 8 and csr.hub_groups in (1, 2) and csr.doc_nq == 1   # four slots per warp step, 32-column slices
     assert csr.is_symmetric
 
 
@@ -849,7 +849,7 @@ def test_empty_rows_on_the_role_kernels(tg, monkeypatch, n_docs, n_topics):
     for F in (128, 20):
         B = torch.randn(g.n, F, device=dev(), generator=gen)
         bias = torch.randn(F, device=dev(), generator=gen)
-        assert csr.spmm_launches(B, F) == 2
+        assert csr.spmm_launches(B, F) == (2 if (F > 32 or n_topics <= 256) else 1)   # (narrow role kernels: <= 256 hub rows)
         ref = O.spmm(coo, B.cpu().numpy())
         out = torch.full((g.n, F), float("nan"), device=dev())    # poisoned output buffer
         y = tg.spmm(csr, B, bias, out=out).cpu().numpy()

@@ -30,7 +30,7 @@ def main():
     g, hidden, n_class = graphgen.make_config(WORKLOADS[args.workload], device=dev, scale=args.scale)
     peak, _ = measured_peaks()
     base = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n)
-    print("plan:", dict(hub_rows=base.n_hub_rows, groups=base.hub_groups, nq=base.doc_nq, T=base.chunk_rows), flush=True)
+    print("plan:", dict(hub_rows=base.n_hub_rows, gs=base.hub_gs, groups=base.hub_groups, nq=base.doc_nq, T=base.chunk_rows), flush=True)
     out = {}
     for cfg in args.configs.split(";"):
         env = dict(kv.split("=") for kv in cfg.split(",") if "=" in kv)
