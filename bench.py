@@ -8,10 +8,14 @@ all four parameter gradients (reference trainer.py:354-361 without the optimizer
 it).  Workload at N=1: BASELINE.json configs[2], the 1M-document x 256-topic synthetic graph (featureless X = I,
 hidden 256, 20 classes) — the largest single-GPU configuration and the one whose operands exceed the 126 MB L2.
 At N>1 every rank holds a shard of that shape (documents row-sharded, topics replicated, see shard.py): weak scaling;
-`value` is epochs/s multiplied by the number of 1M-document shards, i.e. whole-job throughput in C3-equivalents.
+`value` is epochs/s multiplied by the number of 1M-document shards, i.e. whole-job throughput in C3-equivalents.  The
+N>1 line also carries a `c4` block: the same step on BASELINE.json configs[3] (6.25 M documents x 1 024 topics per
+GPU — 50 M documents at 8 GPUs) with its own per-kernel table, and a `consistency` block (replicated gradients bit-identical
+on all ranks; sharded loss against a single-GPU run of the same global graph at a small size).
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the reference path (all host
-threads) on a bounded slice of the same workload.
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference path on a bounded slice of
+the same workload: the OpenMP port (all host threads; the value) and, beside it, the ATen operators the reference
+itself runs on (oracle/torch_ref.py: th.spmm on a COO tensor + autograd), which anchors the port.
 """
 from __future__ import annotations
 
@@ -169,54 +173,126 @@ def cpu_epoch_rate(workload: str, sample_docs: int, steps: int, warmup: int):
     return rate_full, desc, threads, per_step * 1e3
 
 
+def aten_cpu_step_ms(workload: str, sample_docs: int, steps: int = 1, warmup: int = 1):
+    """ms per fwd+bwd step of oracle/torch_ref.py on the CPU — the ATen operators the reference runs on (th.spmm on COO
+    tensors, serial in ATen; dense products and elementwise ops on all torch threads) — on the same document slice."""
+    import torch
+    from oracle import torch_ref as TR
+    from topicgcn_b200 import graphgen
+
+    name = WORKLOADS[workload]
+    full_docs = graphgen.CONFIGS[name][1].get("n_docs", 7674)
+    g, hidden, n_class = graphgen.make_config(name, device="cpu", scale=min(sample_docs, full_docs) / full_docs)
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = TR.GCNRef(g.n, hidden, n_class, 0.5)
+    model.train()
+    x, adj = TR.sparse_identity(g.n, "cpu"), g.adj()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        TR.train_step(model, x, adj, g.labels, g.train_idx)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return statistics.median(times) * 1e3, g.n_docs, torch.get_num_threads()
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rate, desc, threads, ms = cpu_epoch_rate(args.workload, args.cpu_sample_docs, max(1, min(args.steps, 5)),
-                                             max(1, min(args.warmup, 2)))
+    # --steps / --warmup are honoured as given: every step is one fwd+bwd epoch of the OpenMP port on the bounded document
+    # slice (about 0.5 s per step at the default 200 K documents of C3)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    rate, desc, threads, ms = cpu_epoch_rate(args.workload, args.cpu_sample_docs, steps, warmup)
+    aten = None
+    try:
+        aten_ms, aten_docs, aten_threads = aten_cpu_step_ms(args.workload, args.cpu_sample_docs)
+        aten = {"ms_per_step_on_sample": aten_ms, "sample_docs": aten_docs, "torch_threads": aten_threads,
+                "what": "oracle/torch_ref.py: the reference's own operators (th.spmm on COO tensors — serial in ATen — "
+                        "relu, dropout, cross_entropy, autograd), 1 step after 1 warm-up on the same slice",
+                "port_speedup_over_aten": aten_ms / ms}
+    except Exception as exc:  # pragma: no cover
+        aten = {"error": str(exc)[:200]}
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "epochs/s", "n_gpus": args.gpus,
-        "steps": max(1, min(args.steps, 5)), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 / rate,
+        "steps": steps, "warmup": warmup,
+        # the time of ONE timed step as it ran (the slice), so that steps x ms_per_step is this run's own duration;
+        # `value` is that rate scaled to the full workload (epochs/s x slice fraction), as `cpu_baseline.sample` says
+        "ms_per_step": ms, "ms_per_step_full_workload_extrapolated": 1e3 / rate,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "featureless": True, "optimizer_in_step": False},
+        "config": {"workload": WORKLOADS[args.workload], "featureless": True, "optimizer_in_step": False,
+                   "sample_docs": args.cpu_sample_docs},
         "cpu_baseline": {"value": rate, "unit": "epochs/s", "cores": threads, "kind": "port", "sample": desc,
-                         "ms_per_step_on_sample": ms},
+                         "ms_per_step_on_sample": ms, "aten_path": aten},
         "e2e": {"value": rate, "unit": "epochs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def gpu_library_baseline(g, hidden: int, n_class: int, dev, steps: int = 5, warmup: int = 2):
+    """The unmodified library path on the same GPU and the same inputs (SURVEY §2.1's bar): oracle/torch_ref.py on `cuda`
+    — torch's COO tensors, per-call coalesce() + cuSPARSE SpMM, unfused elementwise kernels, autograd — timed with CUDA
+    events; plus the lone F = hidden product th.spmm(adj, B)."""
+    import torch
+    from oracle import torch_ref as TR
+
+    torch.manual_seed(0)
+    model = TR.GCNRef(g.n, hidden, n_class, 0.5).to(dev)
+    model.train()
+    x, adj = TR.sparse_identity(g.n, dev), g.adj()
+
+    def timed(fn, k, w):
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    ms_step = timed(lambda: TR.train_step(model, x, adj, g.labels, g.train_idx), steps, warmup)
+    B = torch.randn(g.n, hidden, device=dev)
+    ms_spmm = timed(lambda: torch.spmm(adj, B), steps, warmup)
+    adj_c = adj.coalesce()
+    ms_spmm_c = timed(lambda: torch.spmm(adj_c, B), steps, warmup)
+    del model, x, B, adj_c
+    torch.cuda.empty_cache()
+    return {"what": "oracle/torch_ref.py on cuda: the reference module's operators as torch 2.11 runs them (COO tensors, "
+                    "coalesce + cuSPARSE SpMM per call, unfused elementwise kernels, autograd); same graph, same shapes",
+            "ms_per_step": ms_step, "value": 1e3 / ms_step, "unit": "epochs/s",
+            "spmm_F%d_ms" % hidden: ms_spmm, "spmm_F%d_ms_coalesced_input" % hidden: ms_spmm_c, "steps": steps, "warmup": warmup}
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
-def run_ours(args):
+def kernel_name(csr, hidden: int, B=None) -> str:
+    """The kernel the F = hidden product runs on this plan (asked of the library: tg_plan_spmm_launches)."""
+    import torch
+    probe = B if B is not None else torch.empty((2, hidden), dtype=torch.float32, device=csr.device)
+    if csr.spmm_launches(probe, hidden) >= 2:
+        return (f"roles2_kernel<GS={csr.hub_gs},NQ={csr.doc_nq}> + stream_finish_kernel (role-specialised column-chunk streaming SpMM: "
+                f"TMA-staged {csr.chunk_rows}-node tiles, {csr.hub_groups} hub slot group(s), bulk-copy entry ring, FFMA2; F={hidden})")
+    return f"spmm_kernel<4,32,{(hidden // 4 + 31) // 32},EpiStore> (gather SpMM, F={hidden})"
+
+
+def measure_workload(name: str, args, world: int, rank: int, dev, hook, steps: int, warmup: int, extras: bool):
+    """Builds one workload (single graph at world = 1, one shard per rank otherwise), times `steps` train steps after
+    `warmup` with device-resident inputs and again end to end with host labels, and returns the measurements (every rank
+    runs this; the timing is the max over ranks).  `extras`: also time the step with Adam and replayed from a CUDA graph."""
     import torch
     import torch.distributed as dist
 
     import topicgcn_b200 as tg
     from topicgcn_b200 import graphgen, ops
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the single JSON line of the contract: NCCL's version/debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
-    tg._native.lib()
-
-    name = WORKLOADS[args.workload]
     hidden, n_class = graphgen.CONFIGS[name][2], graphgen.CONFIGS[name][3]
-    hook = EventHook({"spmm", "gc1_fwd", "gc2_loss_fwd", "stream_spmm"})
-    ops.set_kernel_hook(hook)
-
+    g = None
     if world == 1:
         g, hidden, n_class = graphgen.make_config(name, device=dev, seed=0)
         adj = g.adj()
@@ -248,8 +324,6 @@ def run_ours(args):
             loss.backward()
             return float(loss.item())
 
-        h2d = labels_host.numel() * 8 + index_host.numel() * 8
-        params = list(model.parameters())
         shard_desc = "single GPU, no collective"
     else:
         from topicgcn_b200 import shard
@@ -278,27 +352,28 @@ def run_ours(args):
             loss.backward()
             return float(loss.item())
 
-        h2d = labels_host.numel() * 8 + index_host.numel() * 8
-        params = list(model.parameters())
-        shard_desc = f"documents row-sharded over {world} ranks, topic rows replicated, NCCL all-reduce of K x F partials"
+        shard_desc = (f"documents row-sharded over {world} ranks, topic rows replicated; per step 3 NCCL all-reduces "
+                      f"(K x H, K x C, packed [K x H | dW2 | db1 | db2 | loss]), two of them on a side stream")
+    h2d = labels_host.numel() * 8 + index_host.numel() * 8
+    params = list(model.parameters())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, use_hook=False):
-        for _ in range(warmup):
+    def timed(fn, k, w, use_hook=False):
+        for _ in range(w):
             fn()
         barrier()
         ops.Stats.launches = 0
         hook.enabled = use_hook
-        sampler = ClockSampler(local_rank) if rank == 0 else None
+        sampler = ClockSampler(dev.index or 0) if rank == 0 else None
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(k):
             fn()
         e1.record()
         barrier()
@@ -311,38 +386,13 @@ def run_ours(args):
             ms = float(t.item())
         return ms, ops.Stats.launches, clocks
 
+    hook.records.clear()
     # ---- device-resident timing (value) + live per-kernel events ------------------------------------------------------
-    ms_total, launches, clocks = timed(step_device, args.steps, args.warmup, use_hook=True)
-    ms_step = ms_total / args.steps
-    # ---- with Adam (reported, not the headline) -----------------------------------------------------------------------
-    opt = tg.optim.Adam(params, lr=0.02)  # one tg_adam_f32 pass per parameter (torch.optim.Adam semantics, trainer.py:307)
-
-    def step_adam():
-        step_device()
-        opt.step()
-
-    ms_adam, _, _ = timed(step_adam, max(3, args.steps // 2), 3)
-    ms_adam /= max(3, args.steps // 2)
-    del opt
-    # ---- the same step replayed from a CUDA graph (launch-bound small graphs; reported, not the headline) -----------
-    graph_info = None
-    if world == 1:
-        try:
-            cap = tg.CapturedTrainStep(model, x, adj, g.labels, g.train_idx)
-            ms_g, _, _ = timed(cap.step, args.steps, args.warmup)
-            graph_info = {"ms_per_step": ms_g / args.steps, "value": 1e3 * args.steps / ms_g}
-            del cap
-            model._offset_dev = None
-        except Exception as exc:  # pragma: no cover
-            graph_info = {"error": str(exc)[:200]}
-    # ---- end to end through the public API with host inputs -----------------------------------------------------------
-    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
-    ms_e2e /= args.steps
-
-    shards = world  # one C3-shaped shard per rank
-    value = shards * 1e3 / ms_step
-    e2e_value = shards * 1e3 / ms_e2e
-
+    ms_total, launches, clocks = timed(step_device, steps, warmup, use_hook=True)
+    ms_step = ms_total / steps
+    out = {"name": name, "hidden": hidden, "classes": n_class, "ms_per_step": ms_step, "launches": launches, "clocks": clocks,
+           "h2d": h2d, "n_docs_total": n_docs_total, "nnz_total": nnz_total, "shard_desc": shard_desc,
+           "w1_gb": csr.n_cols * hidden * 4 / 1e9, "graph": g}
     # ---- roofline of the dominant kernel: the F = hidden SpMM (layer-1 forward and the dW1 backward) ----------------
     hbm_peak, peak_src = measured_peaks()
     kern = {}
@@ -350,7 +400,6 @@ def run_ours(args):
         if f is None or kcsr is None or kcsr.n_rows != csr.n_rows:
             continue  # (the sharded mode also runs the epilogue on the K replicated topic rows: not the SpMM)
         kern.setdefault((tag, f), []).append((kcsr, ts))
-    roof = None
     detail = {}
     for (tag, f), lst in kern.items():
         ts = [t for _, tl in lst for t in tl]
@@ -359,31 +408,188 @@ def run_ours(args):
         avg_ms = sum(ts) / len(ts)
         detail[f"{tag}_F{f}"] = {"launches": len(ts), "avg_ms": avg_ms, "algorithmic_GB": nbytes / 1e9,
                                  "GBps": nbytes / 1e6 / avg_ms, "frac_of_peak": nbytes / 1e6 / avg_ms / hbm_peak}
+    out["kernels"] = detail
+    roof = None
     dom = [(k, v) for k, v in detail.items() if k.endswith(f"_F{hidden}")]
     if dom:
         tot_ms = sum(v["avg_ms"] * v["launches"] for _, v in dom)
         tot_bytes = sum(v["algorithmic_GB"] * v["launches"] for _, v in dom)
         n_l = sum(v["launches"] for _, v in dom)
         achieved = tot_bytes * 1e3 / tot_ms
-        if ops.roles2_path(csr, hidden) == "wide":
-            kname = (f"roles2_kernel + stream_finish_kernel (warp-per-slot role-specialised column-chunk streaming SpMM: "
-                     f"TMA-staged chunks, bulk-copy entry ring, FFMA2; F={hidden})")
-        elif csr.streaming:
-            kname = (f"stream_roles_kernel<512,4,KPG,EpiStore> + stream_finish_kernel (role-specialised column-chunk "
-                     f"streaming SpMM with TMA-staged chunks, F={hidden})")
-        else:
-            kname = f"spmm_kernel<4,32,{(hidden // 4 + 31) // 32},EpiStore> (gather SpMM, F={hidden})"
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if csr.streaming and world == 1 and os.path.exists(tpath):
+        if world == 1 and os.path.exists(tpath):
             with open(tpath) as fh:
-                traffic = json.load(fh).get(name)  # dram bytes per launch from the committed ncu --set full capture
+                tj = json.load(fh)
+            traffic = tj.get(name)  # dram bytes per launch from the committed ncu --set full capture of this kernel
+            traffic_src = "static: profiles/roofline_traffic.json (dram__bytes of a committed ncu --set full capture, not measured in this run)"
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "kernel": kname,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name(csr, hidden),
                 "launches_timed": n_l, "avg_launch_ms": tot_ms / n_l, "algorithmic_bytes_per_launch": tot_bytes * 1e9 / n_l,
-                "share_of_step": tot_ms / (ms_step * args.steps), "peak_source": peak_src,
+                "share_of_step": tot_ms / (ms_step * steps), "peak_source": peak_src,
                 "frac_of_nominal_8TBps": achieved / 8000.0,
                 "bytes_formula": "nnz*8 + (n_rows+1)*4 + n_cols*F*4 + n_rows*F*4 (SURVEY 8d)"}
+    out["roofline"] = roof
+    if extras:
+        # ---- with Adam (reported, not the headline) -------------------------------------------------------------------
+        opt = tg.optim.Adam(params, lr=0.02)  # one tg_adam_f32 pass per parameter (torch.optim.Adam semantics, trainer.py:307)
+
+        def step_adam():
+            step_device()
+            opt.step()
+
+        k_adam = max(3, steps // 2)
+        ms_adam, _, _ = timed(step_adam, k_adam, 3)
+        out["ms_adam"] = ms_adam / k_adam
+        del opt
+        # ---- the same step replayed from a CUDA graph (launch-bound small graphs; reported, not the headline) -------
+        graph_info = None
+        if world == 1:
+            try:
+                cap = tg.CapturedTrainStep(model, x, adj, g.labels, g.train_idx)
+                ms_g, _, _ = timed(cap.step, steps, warmup)
+                graph_info = {"ms_per_step": ms_g / steps, "value": 1e3 * steps / ms_g}
+                del cap
+                model._offset_dev = None
+            except Exception as exc:  # pragma: no cover
+                graph_info = {"error": str(exc)[:200]}
+        out["cuda_graph_step"] = graph_info
+    # ---- end to end through the public API with host inputs -----------------------------------------------------------
+    ms_e2e, _, _ = timed(step_e2e, steps, warmup)
+    out["ms_e2e"] = ms_e2e / steps
+    # ---- N > 1: the replicated gradients must be bit-identical on every rank --------------------------------------------
+    if world > 1:
+        step_device()
+        D = model.lg.n_docs_local
+        rep = torch.cat([model.gc1.weight.grad[D:].reshape(-1), model.gc1.bias.grad, model.gc2.weight.grad.reshape(-1),
+                         model.gc2.bias.grad]).contiguous().view(torch.int32)
+        hi, lo = rep.clone(), rep.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        out["replicated_grads_bit_identical"] = bool(torch.equal(hi, lo))
+    del model, params
+    torch.cuda.empty_cache()
+    return out
+
+
+def sharded_vs_single_gpu_check(world: int, rank: int, dev):
+    """Cross-rank correctness inside the benchmark run (real NCCL ranks): one train step, dropout off, on a small GLOBAL
+    graph (20 K documents x 64 topics) cut into `world` document shards against the same step on one GPU (rank 0 runs the
+    un-sharded module).  Returns the relative differences of the loss and of the replicated gradients."""
+    import torch
+    import torch.distributed as dist
+
+    import topicgcn_b200 as tg
+    from topicgcn_b200 import graphgen, ops, shard
+
+    Dg, K, H, C = 20_000, 64, 64, 8
+    gen = torch.Generator(device=dev).manual_seed(5)
+    d, t, w = graphgen.doc_topic_edges(Dg, K, 2, 9, gen, dev)
+    ti, tj, ts = graphgen.topic_topic_edges(K, gen, dev, dense=True)
+    cg = torch.Generator(device="cpu").manual_seed(9)
+    labels = torch.randint(0, C, (Dg,), generator=cg).to(dev)
+    train_idx = torch.sort(torch.randperm(Dg, generator=cg)[: int(0.6 * Dg)]).values.to(dev)
+    torch.manual_seed(3)
+    full = tg.GCN(Dg + K, H, C, 0.0)
+    params = {k: v.to(dev) for k, v in full.state_dict().items()}
+    comm = shard.TorchDistComm()
+    lo, hi = shard.shard_edges(Dg, world)[rank]
+    mine = (d >= lo) & (d < hi)
+    lg = shard.build_local_graph(d[mine] - lo, t[mine], w[mine], ti, tj, ts, hi - lo, K, comm)
+    lg.n_train_global = int(train_idx.numel())
+    model = shard.ShardedGCN(lg, H, C, 0.0, comm=comm).to(dev)
+    with torch.no_grad():
+        model.gc1.weight.copy_(torch.cat([params["gc1.weight"][lo:hi], params["gc1.weight"][Dg:]]))
+        model.gc1.bias.copy_(params["gc1.bias"]); model.gc2.weight.copy_(params["gc2.weight"]); model.gc2.bias.copy_(params["gc2.bias"])
+    model.train()
+    tr_local = train_idx[(train_idx >= lo) & (train_idx < hi)] - lo
+    loss = model.loss(row_label=ops.make_row_label(lg.n_local, labels[lo:hi], tr_local))
+    loss.backward()
+    res = None
+    if rank == 0:
+        u = torch.cat([d, ti + Dg]); v = torch.cat([t + Dg, tj + Dg]); ww = torch.cat([w, ts])
+        r, c, vals = graphgen.normalize_undirected(u, v, ww, Dg + K)
+        adj = torch.sparse_coo_tensor(torch.stack([r, c]), vals, (Dg + K, Dg + K), check_invariants=False)
+        ref = full.to(dev)
+        ref.train()
+        ref_loss = ref.loss(tg.Featureless(Dg + K), adj, labels, train_idx)
+        ref_loss.backward()
+
+        def rel(a, b):
+            return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+        res = {"graph": f"{Dg} documents x {K} topics over {world} NCCL ranks vs one GPU, dropout off",
+               "loss_rel_err": abs(float(loss) - float(ref_loss)) / max(abs(float(ref_loss)), 1e-30),
+               "grad_rel_err": {"gc1.weight[topic rows]": rel(model.gc1.weight.grad[hi - lo:], ref.gc1.weight.grad[Dg:]),
+                                "gc1.weight[rank-0 document rows]": rel(model.gc1.weight.grad[:hi - lo], ref.gc1.weight.grad[lo:hi]),
+                                "gc1.bias": rel(model.gc1.bias.grad, ref.gc1.bias.grad),
+                                "gc2.weight": rel(model.gc2.weight.grad, ref.gc2.weight.grad),
+                                "gc2.bias": rel(model.gc2.bias.grad, ref.gc2.bias.grad)}}
+        res["ok"] = bool(res["loss_rel_err"] <= 1e-5 and max(res["grad_rel_err"].values()) <= 2e-5)
+    dist.barrier()
+    return res
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import topicgcn_b200 as tg
+    from topicgcn_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the single JSON line of the contract: NCCL's version/debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    tg._native.lib()
+    hook = EventHook({"spmm", "gc1_fwd", "gc2_loss_fwd"})
+    ops.set_kernel_hook(hook)
+
+    name = WORKLOADS[args.workload]
+    m = measure_workload(name, args, world, rank, dev, hook, args.steps, args.warmup, extras=True)
+    shards = world  # one shard of the workload per rank
+    value = shards * 1e3 / m["ms_per_step"]
+
+    lib_base = None
+    if world == 1 and rank == 0 and not args.no_library_baseline and m["graph"] is not None:
+        try:
+            lib_base = gpu_library_baseline(m["graph"], m["hidden"], m["classes"], dev)
+            lib_base["ours_over_library"] = lib_base["ms_per_step"] / m["ms_per_step"]
+        except Exception as exc:  # pragma: no cover
+            lib_base = {"error": str(exc)[:300]}
+    m["graph"] = None
+
+    # ---- N > 1: the north-star configuration (BASELINE.json configs[3]) and the cross-rank checks ------------------------
+    c4, consistency = None, None
+    if world > 1:
+        consistency = {"replicated_grads_bit_identical": m.get("replicated_grads_bit_identical")}
+        try:
+            chk = sharded_vs_single_gpu_check(world, rank, dev)
+            if chk is not None:
+                consistency["sharded_vs_single_gpu"] = chk
+        except Exception as exc:  # pragma: no cover
+            consistency["sharded_vs_single_gpu"] = {"error": str(exc)[:300]}
+        if not args.no_c4 and args.workload != "c4":
+            try:
+                c = measure_workload(WORKLOADS["c4"], args, world, rank, dev, hook, args.c4_steps, 3, extras=False)
+                c4 = {"workload": c["name"], "docs_per_gpu": c["n_docs_total"] // world, "docs_total": c["n_docs_total"],
+                      "nnz_total": c["nnz_total"], "steps": args.c4_steps, "warmup": 3, "ms_per_step": c["ms_per_step"],
+                      "epochs_per_sec_whole_graph": 1e3 / c["ms_per_step"],
+                      "shard_epochs_per_sec_x_shards": world * 1e3 / c["ms_per_step"],
+                      "e2e_ms_per_step": c["ms_e2e"], "gpu_launches": c["launches"], "roofline": c["roofline"],
+                      "kernels": c["kernels"], "replicated_grads_bit_identical": c.get("replicated_grads_bit_identical"),
+                      "scaling_note": "weak: 6.25 M documents per GPU at every N (50 M documents at N = 8); compare "
+                                      "shard_epochs_per_sec_x_shards across N, or ms_per_step against the N = 1 run of --workload c4"}
+            except Exception as exc:  # pragma: no cover
+                c4 = {"error": str(exc)[:300]}
 
     line = None
     if rank == 0:
@@ -394,17 +600,20 @@ def run_ours(args):
                    "ms_per_step_on_sample": ms}
         line = {
             "metric": METRIC, "value": value, "unit": "epochs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "docs_total": n_docs_total, "nnz_total": nnz_total, "hidden": hidden,
-                       "classes": n_class, "featureless": True, "optimizer_in_step": False,
-                       "l2_policy": "inputs larger than L2 (W1 alone is %.2f GB per GPU)" % (csr.n_cols * hidden * 4 / 1e9),
-                       "parallelism": shard_desc, "value_definition": "epochs/s x number of per-GPU shards"},
-            "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": e2e_value, "unit": "epochs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e},
-            "roofline": roof, "kernels": detail, "cuda_graph_step": graph_info, "with_adam": {"ms_per_step": ms_adam, "value": shards * 1e3 / ms_adam},
-            "cpu_baseline": cpu,
+            "config": {"workload": name, "docs_total": m["n_docs_total"], "nnz_total": m["nnz_total"], "hidden": m["hidden"],
+                       "classes": m["classes"], "featureless": True, "optimizer_in_step": False,
+                       "l2_policy": "inputs larger than L2 (W1 alone is %.2f GB per GPU)" % m["w1_gb"],
+                       "parallelism": m["shard_desc"],
+                       "value_definition": "epochs/s of one shard x number of per-GPU shards (weak scaling: every GPU holds one "
+                                           "graph of the workload's size; N = 1: plain epochs/s)"},
+            "clocks": m["clocks"], "gpu_launches": m["launches"],
+            "e2e": {"value": shards * 1e3 / m["ms_e2e"], "unit": "epochs/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4,
+                    "ms_per_step": m["ms_e2e"]},
+            "roofline": m["roofline"], "kernels": m["kernels"], "cuda_graph_step": m.get("cuda_graph_step"),
+            "with_adam": {"ms_per_step": m["ms_adam"], "value": shards * 1e3 / m["ms_adam"]},
+            "cpu_baseline": cpu, "gpu_library_baseline": lib_base, "c4": c4, "consistency": consistency,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -422,6 +631,9 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample-docs", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the torch.spmm-on-cuda (cuSPARSE) arm at N = 1")
+    ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the block on the 6.25 M x 1 024 per-GPU shard")
+    ap.add_argument("--c4-steps", type=int, default=5)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

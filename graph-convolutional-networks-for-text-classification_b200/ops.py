@@ -247,14 +247,17 @@ def class_counts(logits: torch.Tensor, row_label: torch.Tensor) -> torch.Tensor:
     return counts
 
 
-def dense_nn(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
-    """A[n x h] @ W[h x c] for skinny c: tg_dense_nn_f32."""
+def dense_nn(A: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A[n x h] @ W[h x c] for skinny c: tg_dense_nn_f32.  `out`: optional [n x c] destination (contiguous rows)."""
     A = _dense2d(A, "A")
     W = _dense2d(W, "W")
     n, h, c = int(A.shape[0]), int(A.shape[1]), int(W.shape[1])
     if W.shape[0] != h:
         raise N.TopicGCNError("inner dimensions differ")
-    out = torch.empty((n, c), dtype=torch.float32, device=A.device)
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.float32, device=A.device)
+    elif tuple(out.shape) != (n, c) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise N.TopicGCNError("out must be a contiguous float32 [n x c] tensor")
     with torch.cuda.device(A.device), _call("dense_nn", (c + 31) // 32, n=n, h=h, c=c):
         N.check(N.lib().tg_dense_nn_f32(N.ptr(A), _ld(A), N.ptr(W), _ld(W), N.ptr(out), c, n, h, c, _stream()),
                 "tg_dense_nn_f32")

@@ -12,6 +12,8 @@ so  Y = Â B  on rank g is the local SpMM followed by ONE all-reduce (sum) of th
 collective of a layer.  Â is symmetric, hence the backward products Â^T dZ are the same operation.  Replicated
 parameters (W2, b1, b2) get one packed all-reduce of their gradients (+ the loss) per step; W1 is row-sharded with
 the documents and its K topic rows stay bit-identical on all ranks because they only ever see all-reduced values.
+Per train step: three all-reduces (K x H forward, K x C backward, one packed [K x H | dW2 | db1 | db2 | loss] at the
+end), the first two issued on a side stream behind document-row kernels that do not depend on them.
 
 The local SpMM runs the fused kernels of the single-GPU path; rows >= D_g (the topic rows) are stored raw
 (`raw_row_begin`), all-reduced, and then given their epilogue.  The reference has nothing comparable (single process,
@@ -39,6 +41,8 @@ from . import graphgen
 # ---------------------------------------------------------------------------------------------------------------
 class TorchDistComm:
     """torch.distributed process group (NCCL or gloo)."""
+
+    overlap = True  # collectives may be issued on a side stream (they order themselves against the stream they are called on)
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -242,7 +246,9 @@ class ShardedGCN(torch.nn.Module):
         self.gc1 = GraphConvolution(lg.n_local, nhid)
         self.gc2 = GraphConvolution(nhid, nclass)
         self.dropout = float(dropout)
-        self._seed, self._calls = 0x5EED, 0
+        self._seed: Optional[int] = None
+        self._calls = 0
+        self._side: Optional[torch.cuda.Stream] = None
 
     def sync_replicated(self) -> None:
         """Make the replicated tensors identical on all ranks (call after moving the module to its device)."""
@@ -254,9 +260,40 @@ class ShardedGCN(torch.nn.Module):
             for p in (self.gc1.bias, self.gc2.weight, self.gc2.bias):
                 self.comm.broadcast(p.data)
 
+    def set_dropout_seed(self, seed: int) -> None:
+        """The shared dropout seed (must be the same on every rank)."""
+        self._seed, self._calls = int(seed), 0
+
+    def dropout_seeds(self):
+        """(document-row seed of this rank, topic-row seed shared by all ranks).  The shared seed is drawn from torch's
+        global generator on rank 0 (so `th.manual_seed` makes runs reproducible, like GCN._dropout_state) and broadcast;
+        the Philox counter is keyed on the LOCAL row index, so each rank mixes its rank into the seed of its document
+        rows — otherwise document i of every shard would draw the same mask.  The replicated topic rows keep the shared
+        seed: their masks must agree on all ranks."""
+        if self._seed is None:
+            t = torch.randint(0, 2**62, (1,), dtype=torch.int64).to(self.gc1.weight.device)
+            self.comm.broadcast(t)
+            self._seed = int(t.item())
+        rank = int(getattr(self.comm, "rank", 0))
+        return (self._seed ^ ((rank + 1) * 0x9E3779B97F4A7C15)) & (2**63 - 1), self._seed ^ 0x7091C
+
+    def side_stream(self) -> Optional[torch.cuda.Stream]:
+        """Stream for the collectives and the topic-row work that overlap the document-row kernels; None when the
+        communicator emulates ranks on one stream (ThreadComm) or there is nothing to overlap (one rank)."""
+        if not getattr(self.comm, "overlap", False):
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.gc1.weight.device)
+        return self._side
+
     def loss(self, labels: Optional[torch.Tensor] = None, index: Optional[torch.Tensor] = None,
              row_label: Optional[torch.Tensor] = None, keep_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Global mean cross-entropy over all ranks' training documents (reference trainer.py:357-359 semantics)."""
+        """Global mean cross-entropy over all ranks' training documents (reference trainer.py:357-359 semantics).
+
+        In training mode with gradients enabled the sum over ranks of the loss travels in the LAST all-reduce of the
+        backward pass (one collective fewer per step): the returned tensor holds this rank's partial sum until
+        `backward()` has run, and the global value from then on — the order the reference trainer uses it in
+        (`loss.backward(); ...; loss.item()`, trainer.py:360-367).  Without gradients the loss is reduced at once."""
         from . import ops
         lg = self.lg
         if row_label is None:
@@ -271,66 +308,117 @@ class ShardedGCN(torch.nn.Module):
                                   keep_mask)
 
 
-def sharded_forward(model: ShardedGCN, W1, b1, W2, b2, row_label, keep_mask):
-    """Train-mode forward on one rank.  Returns (global loss, saved tensors for the backward)."""
+class _Fork:
+    """`with _Fork(side):` runs its body on the side stream after everything queued on the current stream so far; the
+    caller joins with `.join()` (current stream waits for the side stream).  side = None: the body runs in line."""
+
+    def __init__(self, side: Optional[torch.cuda.Stream]):
+        self.side, self.ctx = side, None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+
+
+def sharded_forward(model: ShardedGCN, W1, b1, W2, b2, row_label, keep_mask, defer_loss: bool = False):
+    """Train-mode forward on one rank.  Returns (loss, saved tensors for the backward); the loss is the global mean
+    unless `defer_loss` (then this rank's partial sum: sharded_backward adds the ranks up in its last collective).
+
+    Collectives: ONE all-reduce of the K x H topic rows, issued on the side stream together with the topic-row epilogue and
+    the topic rows of S2 = H1 W2, while the main stream computes the document rows of S2 (0.25 ms at 1 M documents: the
+    latency-bound all-reduce disappears behind it)."""
     from . import ops
     lg, comm = model.lg, model.comm
     csr, D, K = _csr(lg), lg.n_docs_local, lg.n_topics
     p, training = model.dropout, model.training
     inv = 1.0 / max(lg.n_train_global, 1)
+    seed_doc, seed_top = model.dropout_seeds() if (training and p > 0 and keep_mask is None) else (0, 0)
     # layer 1: document rows get the fused epilogue, topic rows are stored raw, summed over ranks, then finished
-    H1 = ops.gc1_forward(csr, W1, b1, p, training, keep_mask, model._seed, model._calls, raw_row_begin=D)
+    H1 = ops.gc1_forward(csr, W1, b1, p, training, keep_mask, seed_doc, model._calls, raw_row_begin=D)
+    S2 = torch.empty((lg.n_local, int(W2.shape[1])), dtype=torch.float32, device=H1.device)
     top = H1[D:]
-    comm.all_reduce(top)
-    ops.gc1_forward(ops.identity_csr(K, H1.device), top, b1, p, training,
-                    None if keep_mask is None else keep_mask[D:].contiguous(), model._seed ^ 0x7091C, model._calls, out=top)
+    with _Fork(model.side_stream()) as side:
+        comm.all_reduce(top)
+        ops.gc1_forward(ops.identity_csr(K, H1.device), top, b1, p, training,
+                        None if keep_mask is None else keep_mask[D:].contiguous(), seed_top, model._calls, out=top)
+        ops.dense_nn(top, W2, out=S2[D:])
+    ops.dense_nn(H1[:D], W2, out=S2[:D])
+    side.join()
     # layer 2 + loss: only document rows carry labels, so their logits need no collective in the forward
-    S2 = ops.dense_nn(H1, W2)
-    loss_local, _, dZ2 = ops.gc2_loss_forward(csr, S2, b2, row_label, inv, want_logits=False, want_grad=True)
-    loss = loss_local.clone()
-    comm.all_reduce(loss)
+    loss, _, dZ2 = ops.gc2_loss_forward(csr, S2, b2, row_label, inv, want_logits=False, want_grad=True)
+    if not defer_loss:
+        loss = loss.clone()
+        comm.all_reduce(loss)
     return loss, (H1, dZ2)
 
 
-def sharded_backward(model: ShardedGCN, W2, saved, dloss=None):
-    """Backward on one rank: returns (dW1, db1, dW2, db2), replicated gradients already summed over ranks."""
+def sharded_backward(model: ShardedGCN, W2, saved, dloss=None, loss_partial: Optional[torch.Tensor] = None):
+    """Backward on one rank: returns (dW1, db1, dW2, db2), replicated gradients already summed over ranks.
+
+    Collectives: the K x C topic rows of dS2 (side stream, behind the document rows of the hidden-layer backward) and ONE
+    packed all-reduce at the end: the K x H topic rows of dW1, dW2, db1, db2 and — when `loss_partial` is given — the
+    deferred loss sum, which is written back into `loss_partial` in place.  `dloss` (the upstream gradient of the
+    scalar loss, a device scalar) is folded into dS2 by the SpMM epilogue and into db2 on C elements: no pass over dZ2."""
     from . import ops
     lg, comm = model.lg, model.comm
     csr, D, K = _csr(lg), lg.n_docs_local, lg.n_topics
     H1, dZ2 = saved
-    if dloss is not None:
-        dZ2 = dZ2 * dloss
+    g = None if dloss is None else dloss.reshape(()).to(torch.float32).contiguous()
     scale = 1.0 / (1.0 - model.dropout) if (model.training and model.dropout > 0) else 1.0
     db2 = ops.colsum(dZ2)  # topic rows of dZ2 are zero: every rank contributes its documents only
-    dS2 = ops.spmm(csr, dZ2)
-    comm.all_reduce(dS2[D:])
+    if g is not None:
+        db2 = db2 * g
+    dS2 = ops.spmm(csr, dZ2, out_scale=g)
     dZ1 = torch.empty_like(H1)
+    with _Fork(model.side_stream()) as side:
+        comm.all_reduce(dS2[D:])
+        _, dW2_t, db1_t = ops.hidden_backward(H1[D:], dS2[D:], W2, scale, out_dZ1=dZ1[D:])
     _, dW2, db1 = ops.hidden_backward(H1[:D], dS2[:D], W2, scale, out_dZ1=dZ1[:D])
-    _, dW2_t, db1_t = ops.hidden_backward(H1[D:], dS2[D:], W2, scale, out_dZ1=dZ1[D:])
+    side.join()
     if comm.rank == 0:  # the replicated topic rows count once
         dW2 = dW2 + dW2_t
         db1 = db1 + db1_t
-    packed = torch.cat([dW2.reshape(-1), db1, db2])
-    comm.all_reduce(packed)
-    h, c = dW2.shape
-    dW2, db1, db2 = packed[:h * c].view(h, c), packed[h * c:h * c + h], packed[h * c + h:]
     dW1 = ops.spmm(csr, dZ1)
-    comm.all_reduce(dW1[D:])
+    h, c = dW2.shape
+    parts = [dW1[D:].reshape(-1), dW2.reshape(-1), db1, db2]
+    if loss_partial is not None:
+        parts.append(loss_partial.reshape(1))
+    packed = torch.cat(parts)
+    comm.all_reduce(packed)
+    o = K * h
+    dW1[D:] = packed[:o].view(K, h)
+    dW2, db1, db2 = packed[o:o + h * c].view(h, c), packed[o + h * c:o + h * c + h], packed[o + h * c + h:o + h * c + h + c]
+    if loss_partial is not None:
+        loss_partial.copy_(packed[-1])
     return dW1, db1, dW2, db2
 
 
 class _ShardedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, W1, b1, W2, b2, model, row_label, keep_mask):
-        loss, saved = sharded_forward(model, W1, b1, W2, b2, row_label, keep_mask)
+        defer = bool(model.training and torch.is_grad_enabled() and model.comm.world > 1)
+        loss, saved = sharded_forward(model, W1, b1, W2, b2, row_label, keep_mask, defer_loss=defer)
         ctx.model = model
+        ctx.loss_partial = loss.detach() if defer else None  # (an alias of the output's storage, without its autograd node)
         ctx.save_for_backward(W2, *saved)
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
         W2, H1, dZ2 = ctx.saved_tensors
-        dW1, db1, dW2, db2 = sharded_backward(ctx.model, W2, (H1, dZ2), dloss)
+        dW1, db1, dW2, db2 = sharded_backward(ctx.model, W2, (H1, dZ2), dloss, loss_partial=ctx.loss_partial)
         return dW1, db1, dW2, db2, None, None, None
 
 

@@ -132,3 +132,34 @@ def test_metrics_match_reference_golden():
         m = O.metrics_from_counts(counts, index.size)
         got = np.array([m["acc"], m["macro_f1"], m["precision"], m["recall"]])
         assert np.allclose(got, ref, rtol=0, atol=1e-12), (i, got, ref)
+
+
+@pytest.mark.parametrize("prefix", ["fl", "sf"])
+def test_torch_ref_matches_reference_golden(small_golden, prefix):
+    """oracle/torch_ref.py (the reference's module restated on the same ATen operators: the ATen CPU baseline and the
+    cuSPARSE GPU baseline of bench.py) against vectors the REAL reference modules produced: eval logits and loss, and in
+    train mode with dropout off (p = 0 draws no mask) the gradients of the oracle's own backward."""
+    import torch
+    from oracle import torch_ref as TR
+    g = small_golden
+    n = int(g["n_docs"] + g["n_topics"])
+    adj = torch.sparse_coo_tensor(torch.tensor(np.stack([g["adj_rows"], g["adj_cols"]])), torch.tensor(g["adj_vals"]), (n, n))
+    if prefix == "fl":
+        x, nfeat = TR.sparse_identity(n, "cpu"), n
+    else:
+        x = torch.sparse_coo_tensor(torch.tensor(np.stack([g["sf_x_rows"], g["sf_x_cols"]])), torch.tensor(g["sf_x_vals"]), (n, 24))
+        nfeat = 24
+    model = TR.GCNRef(nfeat, int(g["nhid"]), int(g["nclass"]), 0.0)
+    model.load_state_dict({k: torch.tensor(g[f"{prefix}_{k}"]) for k in ("gc1.weight", "gc1.bias", "gc2.weight", "gc2.bias")})
+    model.eval()
+    with torch.no_grad():
+        _close(model(x, adj).numpy(), g[f"{prefix}_eval_logits"])
+    model.train()
+    target, index = torch.tensor(g["target"]), torch.tensor(g["index"])
+    loss = TR.train_step(model, x, adj, target, index)
+    params = _params(g, prefix)
+    xo = None if prefix == "fl" else O.Coo(g["sf_x_rows"], g["sf_x_cols"], g["sf_x_vals"], (n, 24))
+    ref_loss, _, ref_grads = O.gcn_loss_and_grads(xo, _adj(g), params, g["target"], g["index"], p=0.0, training=True, keep_mask=None)
+    assert abs(float(loss) - float(ref_loss)) <= 2e-6 * max(1.0, abs(float(ref_loss)))
+    for k, p in model.named_parameters():
+        _close(p.grad.numpy(), ref_grads[k], rtol=5e-6)
