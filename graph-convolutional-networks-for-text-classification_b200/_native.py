@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "tg_reduce_scratch_floats", "tg_reduce_sum_f32",
     "tg_dense_nn_f32", "tg_hidden_bwd_scratch_floats", "tg_hidden_bwd_f32",
     "tg_colsum_scratch_floats", "tg_colsum_f32", "tg_relu_dropout_bwd_f32", "tg_adam_f32", "tg_class_counts_i32",
+    "tg_gemm_scratch_floats", "tg_gemm_f32",
 ]
 
 
@@ -71,6 +72,8 @@ def _declare(lib) -> None:
     sig("tg_colsum_f32", C.c_int, _p, _i64, _i64, _i32, _p, _p, _p)
     sig("tg_relu_dropout_bwd_f32", C.c_int, _p, _i64, _p, _i64, _f32, _p, _i64, _i64, _i32, _p)
     sig("tg_class_counts_i32", C.c_int, _p, _i64, _p, _i64, _i32, _p, _p)
+    sig("tg_gemm_scratch_floats", _i64, _i32, _i64, _i64, _i64)
+    sig("tg_gemm_f32", C.c_int, _i32, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _p, _p)
     sig("tg_adam_f32", C.c_int, _p, _p, _p, _p, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _p)
 
 

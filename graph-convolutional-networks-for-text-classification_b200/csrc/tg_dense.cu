@@ -463,7 +463,10 @@ __global__ void __launch_bounds__(256, 2) hidden_bwd_dense_kernel(const float* _
                                                                   const float* __restrict__ W2, int64_t ldw, float scale,
                                                                   float* __restrict__ dZ1, int64_t ldz,
                                                                   float* __restrict__ partials, int64_t n, int h, int c,
-                                                                  int64_t rows_per_block) {
+                                                                  int64_t rows_per_block, int acc_in, int final_pass) {
+    // Class counts above 32 run this kernel once per block of <= 32 classes: a pass that is not the last one stores the raw
+    // sum dS2[:, block] * W2[:, block]^T (added to the previous passes' sum when acc_in is set) in dZ1; the last pass adds
+    // its own block, then applies the ReLU / dropout mask and the scale.  acc_in = 0, final_pass = 1: the single-pass case.
     constexpr int CP = NC4 * 4;
     __shared__ __align__(16) float Ds[2][kHdTile][CP];
     const int j = threadIdx.x;
@@ -543,13 +546,12 @@ __global__ void __launch_bounds__(256, 2) hidden_bwd_dense_kernel(const float* _
                     gw2[2 * q4] = __ffma2_rn(aa, make_float2(d.x, d.y), gw2[2 * q4]);
                     gw2[2 * q4 + 1] = __ffma2_rn(aa, make_float2(d.z, d.w), gw2[2 * q4 + 1]);
                 }
-                const float dz = (a > 0.f) ? ((dh01.x + dh01.y) + (dh23.x + dh23.y)) * scale : 0.f;
+                const bool in_range = live && (full || r0 + b + u < r_end);
+                float dh = (dh01.x + dh01.y) + (dh23.x + dh23.y);
+                if (acc_in && in_range) dh += *zp;  // (the same thread wrote it in the previous pass)
+                const float dz = final_pass ? ((a > 0.f) ? dh * scale : 0.f) : dh;
                 gb += dz;
-                if (full) {
-                    if (live) *zp = dz;
-                } else if (live && r0 + b + u < r_end) {
-                    *zp = dz;
-                }
+                if (in_range) *zp = dz;
                 zp += ldz;
             }
 #pragma unroll
@@ -573,7 +575,9 @@ __global__ void __launch_bounds__(256, 2) hidden_bwd_dense_kernel(const float* _
 // ascending order, four loads in flight) and their eight sums meet in a fixed shuffle tree: deterministic, and the
 // latency of a serial walk over hundreds of L2-resident rows no longer sits on the step's critical path.
 __global__ void sum_partials_kernel(const float* __restrict__ partials, int64_t n_blocks, int64_t n_elem,
-                                    float* __restrict__ out_a, int64_t split, float* __restrict__ out_b) {
+                                    float* __restrict__ out_a, int64_t split, float* __restrict__ out_b, int a_cols, int64_t a_ld) {
+    // elements [0, split) form a matrix with a_cols columns that is written with leading dimension a_ld (a column block of
+    // dW2); elements [split, n_elem) go to out_b (db1) unless it is null
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = t >> 3;
     const int l = (int)(t & 7);
@@ -590,8 +594,8 @@ __global__ void sum_partials_kernel(const float* __restrict__ partials, int64_t 
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (e >= n_elem || l != 0) return;
-    if (e < split) out_a[e] = s;
-    else out_b[e - split] = s;
+    if (e < split) out_a[(e / a_cols) * a_ld + (e % a_cols)] = s;
+    else if (out_b) out_b[e - split] = s;
 }
 
 static bool dense_hidden_enabled() {
@@ -610,10 +614,10 @@ static int launch_hidden_bwd(const float* H1, int64_t ldh, const float* dS2, int
         rpb = ceil_div64(rpb, kHdTile) * kHdTile;
         grid = ceil_div64(n > 0 ? n : 1, rpb);
         const int threads = ((h + 31) / 32) * 32;
-        hidden_bwd_dense_kernel<NC4><<<(unsigned)grid, threads, 0, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb);
+        hidden_bwd_dense_kernel<NC4><<<(unsigned)grid, threads, 0, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, 0, 1);
         TG_LAUNCH_CHECK();
         const int64_t n_elem = (int64_t)h * (c + 1);
-        sum_partials_kernel<<<(unsigned)ceil_div64(n_elem * 8, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1);
+        sum_partials_kernel<<<(unsigned)ceil_div64(n_elem * 8, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1, c, c);
         TG_LAUNCH_CHECK();
         return TG_OK;
     }
@@ -644,9 +648,119 @@ static int launch_hidden_bwd(const float* H1, int64_t ldh, const float* dS2, int
     }
     TG_LAUNCH_CHECK();
     const int64_t n_elem = (int64_t)h * (c + 1);
-    sum_partials_kernel<<<(unsigned)ceil_div64(n_elem * 8, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1);
+    sum_partials_kernel<<<(unsigned)ceil_div64(n_elem * 8, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1, c, c);
     TG_LAUNCH_CHECK();
     return TG_OK;
+}
+
+// Any class count / hidden width: blocks of <= 256 hidden units x blocks of <= 32 classes on the dense kernel.  Within a
+// hidden block the class blocks run in order with the running pre-activation sum kept in dZ1 (see the kernel); dW2 is
+// produced block by block, db1 by the last class block.  (R52: 52 classes -> two passes; reference data/text_dataset/R52.txt.)
+template <int NC4>
+static int launch_hidden_block(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw,
+                               float scale, float* dZ1, int64_t ldz, float* dW2, int64_t ldg, float* db1, float* partials,
+                               int64_t n, int hb, int cb, int acc_in, int final_pass, cudaStream_t st) {
+    int64_t grid = 2 * kNumSM;
+    int64_t rpb = ceil_div64(n > 0 ? n : 1, grid);
+    rpb = ceil_div64(rpb, kHdTile) * kHdTile;
+    grid = ceil_div64(n > 0 ? n : 1, rpb);
+    const int threads = ((hb + 31) / 32) * 32;
+    hidden_bwd_dense_kernel<NC4><<<(unsigned)grid, threads, 0, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, hb, cb, rpb,
+                                                                     acc_in, final_pass);
+    TG_LAUNCH_CHECK();
+    const int64_t n_elem = (int64_t)hb * (cb + 1);
+    sum_partials_kernel<<<(unsigned)ceil_div64(n_elem * 8, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)hb * cb,
+                                                                               final_pass ? db1 : nullptr, cb, ldg);
+    TG_LAUNCH_CHECK();
+    return TG_OK;
+}
+
+static int hidden_bwd_blocked(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw, float scale,
+                              float* dZ1, int64_t ldz, float* dW2, float* db1, float* partials, int64_t n, int h, int c,
+                              cudaStream_t st) {
+    for (int j0 = 0; j0 < h; j0 += 256) {
+        const int hb = (h - j0 < 256) ? (h - j0) : 256;
+        for (int c0 = 0; c0 < c; c0 += 32) {
+            const int cb = (c - c0 < 32) ? (c - c0) : 32;
+            const int acc_in = c0 > 0, final_pass = (c0 + 32 >= c);
+            const float *h1 = H1 + j0, *ds = dS2 + c0, *w2 = W2 + (int64_t)j0 * ldw + c0;
+            float *dz = dZ1 + j0, *dw = dW2 + (int64_t)j0 * c + c0, *db = db1 + j0;
+            int rc;
+            switch ((cb + 3) / 4) {
+                case 1: rc = launch_hidden_block<1>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
+                case 2: rc = launch_hidden_block<2>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
+                case 3: rc = launch_hidden_block<3>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
+                case 4: rc = launch_hidden_block<4>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
+                case 5: rc = launch_hidden_block<5>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
+                case 6: rc = launch_hidden_block<6>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
+                case 7: rc = launch_hidden_block<7>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
+                default: rc = launch_hidden_block<8>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
+            }
+            if (rc != TG_OK) return rc;
+        }
+    }
+    return TG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// plain fp32 GEMM for a DENSE layer-1 feature matrix (reference layer.py:102 when infeatn is dense; its autograd
+// transpose product).  Not the reference's mode (its features are sparse) and not on the benchmark path: a
+// straightforward shared-memory tiled kernel (64 x 64 tile, 4 x 4 per thread, fp32 FMA), deterministic.
+//   NN: C[M x N] = A[M x K] * B[K x N]
+//   TN: C[M x N] = A[K x M]^T * B[K x N], K split into `splits` ranges whose partial products are summed in range order
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kGT = 64, kGK = 16;
+template <bool TA>
+__global__ void __launch_bounds__(256) gemm_tile_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                        int64_t ldb, float* __restrict__ C, int64_t ldc, int64_t M, int64_t N,
+                                                        int64_t K, int64_t k_per_split, int64_t c_split_stride) {
+    __shared__ float As[kGK][kGT + 1], Bs[kGK][kGT + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t m0 = (int64_t)blockIdx.y * kGT, n0 = (int64_t)blockIdx.x * kGT;
+    const int64_t kb = (int64_t)blockIdx.z * k_per_split, ke = min(K, kb + k_per_split);
+    float acc[4][4] = {};
+    for (int64_t k0 = kb; k0 < ke; k0 += kGK) {
+        for (int idx = threadIdx.x; idx < kGK * kGT; idx += 256) {
+            int kk, mm;
+            if (TA) { mm = idx % kGT; kk = idx / kGT; } else { kk = idx % kGK; mm = idx / kGK; }   // coalesced along the contiguous axis
+            const int64_t k = k0 + kk, m = m0 + mm;
+            As[kk][mm] = (k < ke && m < M) ? (TA ? A[k * lda + m] : A[m * lda + k]) : 0.f;
+        }
+        for (int idx = threadIdx.x; idx < kGK * kGT; idx += 256) {
+            const int nn = idx % kGT, kk = idx / kGT;
+            const int64_t k = k0 + kk, nn_g = n0 + nn;
+            Bs[kk][nn] = (k < ke && nn_g < N) ? B[k * ldb + nn_g] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kGK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) acc[i][jn] = fmaf(a[i], b[jn], acc[i][jn]);
+        }
+        __syncthreads();
+    }
+    float* Cz = C + (int64_t)blockIdx.z * c_split_stride;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+            const int64_t m = m0 + ty * 4 + i, nn = n0 + tx * 4 + jn;
+            if (m < M && nn < N) Cz[m * ldc + nn] = acc[i][jn];
+        }
+}
+
+// C[e] = sum over splits (in order) of partials[s][e]
+__global__ void gemm_sum_splits_kernel(const float* __restrict__ partials, int splits, int64_t M, int64_t N, float* __restrict__ C, int64_t ldc) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M * N) return;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partials[(int64_t)z * M * N + e];
+    C[(e / N) * ldc + (e % N)] = s;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -759,9 +873,8 @@ int tg_hidden_bwd_f32(const float* H1, int64_t ldh, const float* dS2, int64_t ld
     using namespace tg;
     TG_REQUIRE(H1 && dS2 && W2 && dZ1 && dW2 && db1 && partials, TG_ERR_INVALID_ARG, "null pointer");
     TG_REQUIRE(n >= 0 && h > 0 && c > 0 && ldh >= h && ldd >= c && ldw >= c && ldz >= h, TG_ERR_INVALID_ARG, "bad shape");
-    TG_REQUIRE(h <= 1024, TG_ERR_UNSUPPORTED, "hidden width %d > 1024 not supported by the fused backward", h);
-    TG_REQUIRE(c <= 32, TG_ERR_UNSUPPORTED, "n_class %d > 32 not supported by the fused backward", c);
     cudaStream_t st = as_stream(stream);
+    if (c > 32 || h > 1024) return hidden_bwd_blocked(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
     const int nc4 = (c + 3) / 4;
     switch (nc4) {
         case 1: return launch_hidden_bwd<1>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
@@ -773,6 +886,45 @@ int tg_hidden_bwd_f32(const float* H1, int64_t ldh, const float* dS2, int64_t ld
         case 7: return launch_hidden_bwd<7>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
         default: return launch_hidden_bwd<8>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
     }
+}
+
+int64_t tg_gemm_scratch_floats(int32_t trans_a, int64_t m, int64_t n, int64_t k) {
+    if (!trans_a) return 0;
+    int64_t splits = tg::ceil_div64(k, 8192);
+    if (splits > 512) splits = 512;
+    return splits > 1 ? splits * m * n : 0;
+}
+
+int tg_gemm_f32(int32_t trans_a, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m,
+                int64_t n, int64_t k, float* scratch, void* stream) {
+    using namespace tg;
+    TG_REQUIRE(A && B && C, TG_ERR_INVALID_ARG, "null pointer");
+    TG_REQUIRE(m >= 0 && n >= 0 && k >= 0 && ldb >= n && ldc >= n && lda >= (trans_a ? m : k), TG_ERR_INVALID_ARG, "bad shape");
+    if (m == 0 || n == 0) return TG_OK;
+    cudaStream_t st = as_stream(stream);
+    const dim3 tiles((unsigned)ceil_div64(n, kGT), (unsigned)ceil_div64(m, kGT), 1);
+    TG_REQUIRE(tiles.y <= 65535, TG_ERR_UNSUPPORTED, "too many row tiles for one launch (m = %lld)", (long long)m);
+    if (!trans_a) {
+        gemm_tile_kernel<false><<<tiles, 256, 0, st>>>(A, lda, B, ldb, C, ldc, m, n, k, k > 0 ? k : 1, 0);
+        TG_LAUNCH_CHECK();
+        return TG_OK;
+    }
+    // the reduction runs over the long axis (the nodes): split it, one partial product per range, summed in range order
+    int64_t splits = ceil_div64(k, 8192);
+    if (splits > 512) splits = 512;
+    if (splits <= 1) {
+        gemm_tile_kernel<true><<<tiles, 256, 0, st>>>(A, lda, B, ldb, C, ldc, m, n, k, k > 0 ? k : 1, 0);
+        TG_LAUNCH_CHECK();
+        return TG_OK;
+    }
+    TG_REQUIRE(scratch, TG_ERR_WORKSPACE, "tg_gemm_f32 (transposed) needs tg_gemm_scratch_floats() floats of scratch");
+    const int64_t kps = ceil_div64(ceil_div64(k, splits), kGK) * kGK;
+    const dim3 grid(tiles.x, tiles.y, (unsigned)ceil_div64(k, kps));
+    gemm_tile_kernel<true><<<grid, 256, 0, st>>>(A, lda, B, ldb, scratch, n, m, n, k, kps, m * n);
+    TG_LAUNCH_CHECK();
+    gemm_sum_splits_kernel<<<(unsigned)ceil_div64(m * n, 256), 256, 0, st>>>(scratch, (int)grid.z, m, n, C, ldc);
+    TG_LAUNCH_CHECK();
+    return TG_OK;
 }
 
 int64_t tg_colsum_scratch_floats(int64_t n, int32_t c) {
@@ -791,7 +943,7 @@ int tg_colsum_f32(const float* X, int64_t ldx, int64_t n, int32_t c, float* scra
     const int grid = colsum_grid(n, &rpb);
     colsum_partial_kernel<<<grid, 256, 0, st>>>(X, ldx, n, c, cw, rpb, scratch);
     TG_LAUNCH_CHECK();
-    sum_partials_kernel<<<(unsigned)ceil_div64((int64_t)c * 8, 256), 256, 0, st>>>(scratch, grid, c, out, c, nullptr);
+    sum_partials_kernel<<<(unsigned)ceil_div64((int64_t)c * 8, 256), 256, 0, st>>>(scratch, grid, c, out, c, nullptr, c, c);
     TG_LAUNCH_CHECK();
     return TG_OK;
 }
@@ -810,7 +962,7 @@ int tg_reduce_sum_f32(const float* x, int64_t n, float* scratch, float* out, voi
     const int grid = colsum_grid(n, &rpb);
     colsum_partial_kernel<<<grid, 256, 0, st>>>(x, 1, n, 1, 1, rpb, scratch);
     TG_LAUNCH_CHECK();
-    sum_partials_kernel<<<1, 256, 0, st>>>(scratch, grid, 1, out, 1, nullptr);
+    sum_partials_kernel<<<1, 256, 0, st>>>(scratch, grid, 1, out, 1, nullptr, 1, 1);
     TG_LAUNCH_CHECK();
     return TG_OK;
 }

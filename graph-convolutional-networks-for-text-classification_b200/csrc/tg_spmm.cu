@@ -367,7 +367,7 @@ int tg_gc1_fwd_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* co
     using namespace tg;
     TG_REQUIRE(H1, TG_ERR_INVALID_ARG, "null output");
     TG_REQUIRE(ldh >= n_feat, TG_ERR_INVALID_ARG, "ldh < n_feat");
-    TG_REQUIRE(p >= 0.f && p < 1.f, TG_ERR_INVALID_ARG, "dropout p must be in [0,1)");
+    TG_REQUIRE(p >= 0.f && p <= 1.f, TG_ERR_INVALID_ARG, "dropout p must be in [0,1]");  // (p = 1 drops everything, like torch.dropout)
     EpiStore epi{};
     epi.Y = H1; epi.ldy = ldh; epi.bias = bias; epi.relu = 1; epi.n_feat = n_feat;
     epi.seed = seed; epi.offset = offset; epi.keep_mask = keep_mask;
@@ -377,7 +377,7 @@ int tg_gc1_fwd_f32(const tg_plan* plan, const int32_t* rowptr, const int32_t* co
     const bool drop = training && p > 0.f;
     epi.drop_mode = !drop ? 0 : (keep_mask ? 2 : 1);
     epi.keep_thr = dropout_keep_threshold(p);
-    epi.scale = drop ? 1.f / (1.f - p) : 1.f;
+    epi.scale = drop ? (p < 1.f ? 1.f / (1.f - p) : 0.f) : 1.f;
     const bool ok4 = (ldh % 4 == 0) && aligned16(H1) && (!bias || aligned16(bias)) &&
                      (epi.drop_mode != 2 || (reinterpret_cast<uintptr_t>(keep_mask) & 3u) == 0);
     return run_spmm(plan, rowptr, colidx, vals, S, lds, n_feat, ok4, epi, workspace, workspace_bytes,

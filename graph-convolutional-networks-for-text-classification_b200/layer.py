@@ -102,10 +102,10 @@ def _support(x, weight: torch.Tensor) -> torch.Tensor:
         return ops.SpMMFunction.apply(weight, None, x)
     if x.layout in (torch.sparse_coo, torch.sparse_csr):
         return ops.SpMMFunction.apply(weight, None, cached_csr(x))
-    # dense features: a plain library GEMM (cuBLAS through torch.mm)
+    # dense features (not the reference's mode: its features are sparse): tg_gemm_f32, dW1 = X^T dS1 in the backward
     if not x.is_cuda:
         raise N.TopicGCNError("x must be on a CUDA device; topicgcn_b200 has no CPU fallback")
-    return torch.mm(x, weight)
+    return ops.DenseFeatureTransform.apply(x, weight)
 
 
 class GraphConvolution(Module):

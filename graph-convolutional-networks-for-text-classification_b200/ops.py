@@ -287,38 +287,45 @@ def relu_dropout_backward(H: torch.Tensor, dH: torch.Tensor, scale: float) -> to
     return dZ
 
 
-FUSED_BWD_MAX_CLASSES = 32
-FUSED_BWD_MAX_HIDDEN = 1024
-
-
 def hidden_backward(H1: torch.Tensor, dS2: torch.Tensor, W2: torch.Tensor, scale: float,
                     out_dZ1: Optional[torch.Tensor] = None):
-    """(dZ1, dW2, db1) — fused backward of S2 = H1 @ W2, dropout, relu, +b1: tg_hidden_bwd_f32.
-    Class counts above 32 (or hidden widths above 1024) are plain library GEMMs (cuBLAS via torch.mm) followed by the
-    elementwise/colsum kernels."""
+    """(dZ1, dW2, db1) — fused backward of S2 = H1 @ W2, dropout, relu, +b1: tg_hidden_bwd_f32.  Any class count and hidden
+    width: up to 32 classes (and 1024 hidden units) in one pass over H1, more in blocks of 32 classes / 256 units."""
     H1 = _dense2d(H1, "H1")
     dS2 = _dense2d(dS2, "dS2")
     W2 = _dense2d(W2, "W2")
     n, h, c = int(H1.shape[0]), int(H1.shape[1]), int(W2.shape[1])
-    if c > FUSED_BWD_MAX_CLASSES or h > FUSED_BWD_MAX_HIDDEN:
-        dH1 = torch.mm(dS2, W2.t())
-        dW2 = torch.mm(H1.t(), dS2)
-        dZ1 = relu_dropout_backward(H1, dH1, scale)
-        if out_dZ1 is not None:
-            out_dZ1.copy_(dZ1)
-            dZ1 = out_dZ1
-        return dZ1, dW2, colsum(dZ1)
     dev = H1.device
     dZ1 = out_dZ1 if out_dZ1 is not None else torch.empty((n, h), dtype=torch.float32, device=dev)
     dW2 = torch.empty((h, c), dtype=torch.float32, device=dev)
     db1 = torch.empty(h, dtype=torch.float32, device=dev)
     scratch = torch.empty(int(N.lib().tg_hidden_bwd_scratch_floats(n, h, c)), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev), _call("hidden_bwd", 2, n=n, h=h, c=c):
+    blocks = 1 if (c <= 32 and h <= 1024) else ((c + 31) // 32) * ((h + 255) // 256)
+    with torch.cuda.device(dev), _call("hidden_bwd", 2 * blocks, n=n, h=h, c=c):
         N.check(N.lib().tg_hidden_bwd_f32(N.ptr(H1), _ld(H1), N.ptr(dS2), _ld(dS2), N.ptr(W2), _ld(W2), float(scale),
                                           N.ptr(dZ1), _ld(dZ1), N.ptr(dW2), N.ptr(db1), N.ptr(scratch), n, h, c,
                                           _stream()),
                 "tg_hidden_bwd_f32")
     return dZ1, dW2, db1
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, trans_a: bool = False) -> torch.Tensor:
+    """A @ B (trans_a = False) or A^T @ B (trans_a = True) for dense fp32 operands: tg_gemm_f32 — the products of a DENSE
+    layer-1 feature matrix (reference layer.py:102 when `infeatn` is dense, and its autograd transpose product)."""
+    A = _dense2d(A, "A")
+    B = _dense2d(B, "B")
+    k = int(B.shape[0])
+    m = int(A.shape[1]) if trans_a else int(A.shape[0])
+    if (int(A.shape[0]) if trans_a else int(A.shape[1])) != k:
+        raise N.TopicGCNError("inner dimensions differ")
+    n = int(B.shape[1])
+    out = torch.empty((m, n), dtype=torch.float32, device=A.device)
+    ns = int(N.lib().tg_gemm_scratch_floats(int(trans_a), m, n, k))
+    scratch = torch.empty(ns, dtype=torch.float32, device=A.device) if ns else None
+    with torch.cuda.device(A.device), _call("gemm", 2 if ns else 1, m=m, n=n, k=k):
+        N.check(N.lib().tg_gemm_f32(int(trans_a), N.ptr(A), _ld(A), N.ptr(B), _ld(B), N.ptr(out), n, m, n, k, N.ptr(scratch),
+                                    _stream()), "tg_gemm_f32")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -340,8 +347,25 @@ class SpMMFunction(torch.autograd.Function):
         return dB, db, None
 
 
+class DenseFeatureTransform(torch.autograd.Function):
+    """support = X @ W for a dense, constant feature matrix X (reference layer.py:102 with dense `infeatn`); only W gets a
+    gradient (dW = X^T @ dS), like the reference, which never differentiates its features."""
+
+    @staticmethod
+    def forward(ctx, X, W):
+        ctx.save_for_backward(X)
+        return gemm(X, W)
+
+    @staticmethod
+    def backward(ctx, dS):
+        (X,) = ctx.saved_tensors
+        return None, gemm(X, dS.contiguous(), trans_a=True)
+
+
 def _dropout_scale(p: float, training: bool) -> float:
-    return 1.0 / (1.0 - p) if (training and p > 0.0) else 1.0
+    if not (training and p > 0.0):
+        return 1.0
+    return 1.0 / (1.0 - p) if p < 1.0 else 0.0  # p = 1 drops everything (torch.dropout accepts it): outputs and gradients are 0
 
 
 class GCNCoreFunction(torch.autograd.Function):

@@ -161,6 +161,17 @@ int64_t tg_reduce_scratch_floats(int64_t n);
 int tg_reduce_sum_f32(const float* x, int64_t n, float* scratch, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Plain fp32 product for a DENSE layer-1 feature matrix                replaces layer.py:102 when infeatn is dense
+ *   trans_a = 0:  C[m x n] = A[m x k]   * B[k x n]        (support = X W1)
+ *   trans_a = 1:  C[m x n] = A[k x m]^T * B[k x n]        (dW1 = X^T dS1; the long axis k is split and the partial
+ *                 products are summed in a fixed order: deterministic, no float atomics)
+ * scratch: tg_gemm_scratch_floats(trans_a, m, n, k) floats (0 for trans_a = 0).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t tg_gemm_scratch_floats(int32_t trans_a, int64_t m, int64_t n, int64_t k);
+int tg_gemm_f32(int32_t trans_a, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t m,
+                int64_t n, int64_t k, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Skinny dense products around the hidden layer                    replaces layer.py:102 (layer 2)
  *   tg_dense_nn_f32 :  C[n x c] = A[n x h] * W[h x c]                      (S2 = H1 * W2)
  *   tg_hidden_bwd_f32: fused backward of  S2 = H1*W2, dropout, relu, +b1   

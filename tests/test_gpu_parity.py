@@ -294,9 +294,13 @@ def test_dense_nn(tg, n, h, c):
     assert rel_err(got, ref) <= 1e-5
 
 
-@pytest.mark.parametrize("n,h,c", [(1, 8, 2), (700, 200, 8), (5000, 256, 20), (513, 200, 23), (300, 64, 52), (40000, 256, 20)])
+@pytest.mark.parametrize("n,h,c", [(1, 8, 2), (700, 200, 8), (5000, 256, 20), (513, 200, 23), (300, 64, 52), (40000, 256, 20),
+                                   (9100, 200, 52), (3000, 300, 52), (2000, 1100, 8), (1500, 520, 70)])
 def test_hidden_backward(tg, n, h, c):
+    """(9100, 200, 52) is the R52 shape of the reference (data/text_dataset/R52.txt: 52 classes); class counts above 32 and
+    hidden widths above 1024 run in blocks on the same kernel — no library GEMM anywhere on the path."""
     from topicgcn_b200 import ops
+    ops.Stats.launches = 0
     rng = np.random.default_rng(n + h + c)
     H1 = np.maximum(rng.normal(size=(n, h)), 0).astype(np.float32) * 2.0
     dS2 = rng.normal(size=(n, c)).astype(np.float32)
@@ -305,6 +309,7 @@ def test_hidden_backward(tg, n, h, c):
                                         torch.tensor(W2, device=dev()), 2.0)
     dH1 = dS2.astype(np.float64) @ W2.astype(np.float64).T
     dZ1_ref = np.where(H1 > 0, dH1 * 2.0, 0.0)
+    assert ops.Stats.launches == 2 * (1 if (c <= 32 and h <= 1024) else ((c + 31) // 32) * ((h + 255) // 256))   # our kernels only
     assert rel_err(dZ1.cpu().numpy(), dZ1_ref) <= 1e-5
     assert rel_err(dW2.cpu().numpy(), H1.astype(np.float64).T @ dS2.astype(np.float64)) <= 2e-5
     assert rel_err(db1.cpu().numpy(), dZ1_ref.sum(axis=0)) <= 2e-5
@@ -941,3 +946,60 @@ def test_c3_full_size_against_float64_on_a_row_sample(tg):
     safe = np.abs(z) > 1e-4
     assert np.abs(hg - want)[safe].max() <= 2e-5 * np.abs(want).max()
     assert np.array_equal((hg != 0)[safe], (want != 0)[safe])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dense layer-1 features and the R52 class count: every product on the path is one of our kernels
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(1000, 200, 300), (257, 64, 33), (5, 3, 70000), (300, 256, 40000)])
+def test_gemm_nn_and_tn(tg, m, n, k):
+    from topicgcn_b200 import ops
+    gen = torch.Generator(device="cuda:0").manual_seed(m + n + k)
+    A = torch.randn(m, k, device=dev(), generator=gen)
+    B = torch.randn(k, n, device=dev(), generator=gen)
+    C = ops.gemm(A, B).cpu().numpy()
+    assert rel_err(C, A.double().cpu().numpy() @ B.double().cpu().numpy()) <= 1e-5
+    At = A.t().contiguous()                                   # [k x m]: the transposed product reduces over the long axis
+    Ct = ops.gemm(At, B, trans_a=True)
+    assert rel_err(Ct.cpu().numpy(), A.double().cpu().numpy() @ B.double().cpu().numpy()) <= 1e-5
+    assert torch.equal(Ct, ops.gemm(At, B, trans_a=True))     # split sums in a fixed order: deterministic
+
+
+def test_gcn_with_dense_features_and_52_classes(tg, small_golden):
+    """The module with a DENSE feature matrix (tg_gemm_f32 forward and backward) and 52 classes (blocked fused backward)
+    against the torch restatement of the reference module on the same device (oracle/torch_ref.py); dropout off."""
+    from oracle import torch_ref as TR
+    from topicgcn_b200 import ops
+    g = small_golden
+    n = int(g["n_docs"] + g["n_topics"])
+    adj = _sparse(g["adj_rows"], g["adj_cols"], g["adj_vals"], (n, n))
+    gen = torch.Generator(device="cuda:0").manual_seed(0)
+    X = torch.randn(n, 37, device=dev(), generator=gen)
+    target = torch.randint(0, 52, (int(g["n_docs"]),), device=dev(), generator=gen)
+    index = torch.tensor(g["index"], device=dev())
+    torch.manual_seed(1)
+    model = tg.GCN(37, 48, 52, 0.0).to(dev())
+    ref = TR.GCNRef(37, 48, 52, 0.0).to(dev())
+    ref.load_state_dict(model.state_dict())
+    model.train(); ref.train()
+    ops.Stats.launches = 0
+    loss = model.loss(X, adj, target, index)
+    loss.backward()
+    assert ops.Stats.launches > 0
+    ref_loss = TR.train_step(ref, X, adj, target, index)
+    assert abs(float(loss) - float(ref_loss)) <= 1e-5 * max(1.0, abs(float(ref_loss)))
+    for (k, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        assert rel_err(p.grad.cpu().numpy(), q.grad.cpu().numpy()) <= 2e-5, k
+
+
+def test_dropout_p_one_drops_everything(tg, small_golden):
+    g = small_golden
+    n = int(g["n_docs"] + g["n_topics"])
+    adj = _sparse(g["adj_rows"], g["adj_cols"], g["adj_vals"], (n, n))
+    model = _load_params(tg.GCN(n, int(g["nhid"]), int(g["nclass"]), 1.0), g, "fl")
+    model.train()
+    logits = model(tg.Featureless(n), adj)
+    b2 = model.gc2.bias.detach()
+    assert torch.isfinite(logits).all() and torch.equal(logits.detach(), b2.expand_as(logits).contiguous())   # H1 = 0: logits = b2
+    logits.sum().backward()
+    assert float(model.gc1.weight.grad.abs().max()) == 0.0

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 python -c "
 import sys; sys.path.insert(0,'graph-convolutional-networks-for-text-classification_b200')
 import build; build.build()
-" 2>&1 | tail -1
+" 2>&1 | grep -v "ptxas info" | tail -4
 python - <<'PY'
 import re,subprocess
 txt=open('graph-convolutional-networks-for-text-classification_b200/build/tg_roles2.cu.ptxas.log').read()
