@@ -272,6 +272,14 @@ int tg_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* va
     TG_REQUIRE(rowptr && plan_out, TG_ERR_INVALID_ARG, "null pointer");
     TG_REQUIRE(n_rows >= 0 && n_rows < (int64_t)INT32_MAX && nnz < (int64_t)INT32_MAX, TG_ERR_OVERFLOW,
                "n_rows/nnz must fit int32");
+    if (segment_nnz <= 0 && hub_threshold <= 0 && n_rows > 0 && nnz <= (int64_t)32 << 20 && nnz / n_rows >= 24) {
+        // Graphs whose TYPICAL row is long (TextGCN-style word rows: median ~200 entries, reference build_graph.py PMI edges):
+        // with the 512-entry threshold almost every row would be a "short" row walked serially by one lane group (a 2-lane
+        // group for an 8-column operand).  A budget of 64 entries per segment turns them into warp-cooperative segments —
+        // the merge-path treatment of mid-degree rows; the partial rows stay small because such graphs are small.
+        segment_nnz = 64;
+        hub_threshold = 128;
+    }
     if (segment_nnz <= 0) segment_nnz = 256;
     if (hub_threshold <= 0) hub_threshold = 2 * segment_nnz;
     TG_REQUIRE(hub_threshold >= segment_nnz, TG_ERR_INVALID_ARG, "hub_threshold must be >= segment_nnz");

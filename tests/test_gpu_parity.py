@@ -169,14 +169,20 @@ def test_spmm_deterministic_and_split_rows(tg, streaming):
     assert rel_err(y[nd:], ref[nd:]) <= max(SPMM_RTOL, 2 * e_ref)
 
 
-def test_spmm_textgcn_skew(tg):
-    """C5: power-law word rows (median ~200, max ~1.5e4 entries) - every row class of the plan in one graph."""
+@pytest.mark.parametrize("F", [200, 8])
+def test_spmm_textgcn_skew(tg, F):
+    """C5: power-law word rows (median ~200, max ~1.5e4 entries) - every row class of the plan in one graph.  The default
+    plan of such a graph cuts rows longer than 128 entries into 64-entry warp-cooperative segments (merge-path treatment of
+    the mid-degree rows); deterministic."""
     from topicgcn_b200 import graphgen
     g, h, c = graphgen.make_config("c5_textgcn_r8_shape", device="cuda:0")
     csr = tg.DeviceCSR.from_coo(g.rows, g.cols, g.vals, g.n, g.n)
-    assert 0 < csr.n_hub_rows < g.n_hubs
-    B = torch.randn(g.n, 200, device=dev())
-    y = tg.spmm(csr, B).cpu().numpy()
+    assert csr.hub_threshold == 128 and csr.segment_nnz == 64
+    assert 0 < csr.n_hub_rows < g.n_hubs and csr.n_segments > 4 * csr.n_hub_rows
+    B = torch.randn(g.n, F, device=dev())
+    y = tg.spmm(csr, B)
+    assert torch.equal(y, tg.spmm(csr, B))
+    y = y.cpu().numpy()
     coo = O.Coo(g.rows.cpu().numpy(), g.cols.cpu().numpy(), g.vals.cpu().numpy(), (g.n, g.n))
     ref, ref64 = O.spmm(coo, B.cpu().numpy()), O.spmm_f64(coo, B.cpu().numpy())
     assert rel_err(y, ref64) <= rel_err(ref, ref64) + 2e-7
