@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "tg_plan_create", "tg_plan_destroy", "tg_plan_info", "tg_plan_workspace_bytes", "tg_plan_spmm_launches",
     "tg_spmm_f32", "tg_gc1_fwd_f32", "tg_dropout_keep_mask", "tg_gc2_loss_fwd_f32", "tg_masked_ce_f32",
     "tg_reduce_scratch_floats", "tg_reduce_sum_f32",
-    "tg_dense_nn_f32", "tg_hidden_bwd_scratch_floats", "tg_hidden_bwd_f32",
+    "tg_dense_nn_f32", "tg_hidden_bwd_scratch_floats", "tg_hidden_bwd_f32", "tg_hidden_bwd_rows_f32",
     "tg_colsum_scratch_floats", "tg_colsum_f32", "tg_relu_dropout_bwd_f32", "tg_adam_f32", "tg_class_counts_i32",
     "tg_gemm_scratch_floats", "tg_gemm_f32",
 ]
@@ -68,6 +68,8 @@ def _declare(lib) -> None:
     sig("tg_hidden_bwd_scratch_floats", _i64, _i64, _i32, _i32)
     sig("tg_hidden_bwd_f32", C.c_int, _p, _i64, _p, _i64, _p, _i64, _f32, _p, _i64, _p, _p, _p, _i64, _i32,
         _i32, _p)
+    sig("tg_hidden_bwd_rows_f32", C.c_int, _p, _i64, _p, _i64, _p, _i64, _f32, _p, _i64, _p, _p, _p, _i64, _i32,
+        _i32, _i64, _p)
     sig("tg_colsum_scratch_floats", _i64, _i64, _i32)
     sig("tg_colsum_f32", C.c_int, _p, _i64, _i64, _i32, _p, _p, _p)
     sig("tg_relu_dropout_bwd_f32", C.c_int, _p, _i64, _p, _i64, _f32, _p, _i64, _i64, _i32, _p)

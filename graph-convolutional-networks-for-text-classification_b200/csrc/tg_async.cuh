@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace tg {
 
@@ -96,8 +97,19 @@ static inline bool make_tensor_map(CUtensorMap* map, const float* B, int64_t row
     const cuuint64_t gstr[1] = {(cuuint64_t)ldb * 4};
     const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1u, 1u};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(B), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(B), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc == CUDA_ERROR_INVALID_CONTEXT) {
+        // a thread that has made no runtime call yet (an autograd worker whose first call is ours) has no driver context
+        // bound: a runtime call binds the device's primary context, then the driver-API encode works
+        (void)cudaFree(nullptr);
+        rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(B), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (rc != CUDA_SUCCESS)
+        fprintf(stderr, "[topicgcn] cuTensorMapEncodeTiled -> %d (B=%p rows=%lld cols=%lld ldb=%lld box=%dx%d)\n", (int)rc, (const void*)B,
+                (long long)rows, (long long)cols, (long long)ldb, box_rows, box_cols);
+    return rc == CUDA_SUCCESS;
 }
 
 }  // namespace tg

@@ -13,6 +13,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tg_common.cuh"
 
 namespace tg {
@@ -326,7 +328,8 @@ __global__ void __launch_bounds__(TB, (TB == 256 ? 2 : 1)) hidden_bwd_kernel(con
                                                           const float* __restrict__ W2, int64_t ldw, float scale,
                                                           float* __restrict__ dZ1, int64_t ldz,
                                                           float* __restrict__ partials, int64_t n, int h, int c,
-                                                          int64_t rows_per_block, int vec_ok, int out_vec) {
+                                                          int64_t rows_per_block, int vec_ok, int out_vec, int64_t n_count) {
+    // rows >= n_count get their dZ1 but do not count into dW2 / db1 (replicated rows of a document-sharded graph)
     constexpr int CP = NC4 * 4;
     extern __shared__ __align__(16) float hb_smem[];
     const int hp4 = (h + 3) & ~3;                     // row stride of the staged H1 tile (floats)
@@ -396,11 +399,13 @@ __global__ void __launch_bounds__(TB, (TB == 256 ? 2 : 1)) hidden_bwd_kernel(con
             const int u = act ? (__ffs(mask) - 1) : 0;
             mask &= mask - 1;  // (0 stays 0)
             const float a = act ? acol[u * hp4] : 0.f;
+            const bool counted = r0 + u < n_count;
             const float* dr = dsm + u * CP;  // lane-private row of the dS2 tile
             // packed fp32 FMAs (FFMA2): the products of two adjacent classes per instruction — half the issue slots of the
             // arithmetic that bounds this kernel; every lane of a pair is an IEEE fma, the sums keep their order
             float2 dh01 = make_float2(0.f, 0.f), dh23 = make_float2(0.f, 0.f);
-            const float2 aa = make_float2(a, a);
+            const float ac = counted ? a : 0.f;
+            const float2 aa = make_float2(ac, ac);
 #pragma unroll
             for (int q4 = 0; q4 < NC4; ++q4) {
                 const float4 d = *reinterpret_cast<const float4*>(dr + q4 * 4);
@@ -415,7 +420,7 @@ __global__ void __launch_bounds__(TB, (TB == 256 ? 2 : 1)) hidden_bwd_kernel(con
             if (act) {
                 const float dz = ((dh0 + dh1) + (dh2 + dh3)) * scale;
                 acol[u * hp4] = dz;  // in place: the tile turns into dZ1
-                gb += dz;
+                if (counted) gb += dz;
             }
         }
         __syncthreads();
@@ -457,13 +462,15 @@ __global__ void __launch_bounds__(TB, (TB == 256 ? 2 : 1)) hidden_bwd_kernel(con
 // one instruction carries two of them.  Same summation order per element as the sparse kernel (zeros add exactly 0).
 constexpr int kHdTile = 64;   // rows of dS2 per staged tile
 constexpr int kHdBatch = 16;  // rows whose H1 values a thread holds in flight
-template <int NC4>
+template <int NC4, bool MULTI>
 __global__ void __launch_bounds__(256, 2) hidden_bwd_dense_kernel(const float* __restrict__ H1, int64_t ldh,
                                                                   const float* __restrict__ dS2, int64_t ldd,
                                                                   const float* __restrict__ W2, int64_t ldw, float scale,
                                                                   float* __restrict__ dZ1, int64_t ldz,
                                                                   float* __restrict__ partials, int64_t n, int h, int c,
-                                                                  int64_t rows_per_block, int acc_in, int final_pass) {
+                                                                  int64_t rows_per_block, int acc_in_arg, int final_pass_arg, int64_t n_count) {
+    // MULTI = false is the single-pass kernel of the benchmark path: the two pass flags are compile-time constants there
+    const int acc_in = MULTI ? acc_in_arg : 0, final_pass = MULTI ? final_pass_arg : 1;
     // Class counts above 32 run this kernel once per block of <= 32 classes: a pass that is not the last one stores the raw
     // sum dS2[:, block] * W2[:, block]^T (added to the previous passes' sum when acc_in is set) in dZ1; the last pass adds
     // its own block, then applies the ReLU / dropout mask and the scale.  acc_in = 0, final_pass = 1: the single-pass case.
@@ -533,27 +540,38 @@ __global__ void __launch_bounds__(256, 2) hidden_bwd_dense_kernel(const float* _
                 }
             }
             const float4* dr = reinterpret_cast<const float4*>(&Ds[t & 1][b][0]);  // warp-uniform: broadcast reads
+            // rows past n_count give their dZ1 but stay out of dW2 / db1.  They are the last rows of the matrix: the test is made
+            // once per batch (block-uniform), and the batches that lie wholly below n_count — all but one or two of the whole
+            // launch — run the loop without any per-row test (a per-row test cost 11 % on this issue-bound kernel).
+            const int64_t cnt_rows = n_count - (r0 + b);
+            auto batch = [&](auto all_counted_tag) {
+                constexpr bool kAll = decltype(all_counted_tag)::value;
 #pragma unroll
-            for (int u = 0; u < kHdBatch; ++u) {
-                const float a = hv[u];
-                float2 dh01 = make_float2(0.f, 0.f), dh23 = make_float2(0.f, 0.f);
-                const float2 aa = make_float2(a, a);
+                for (int u = 0; u < kHdBatch; ++u) {
+                    const float a = hv[u];
+                    const bool counted = kAll || u < cnt_rows;
+                    float2 dh01 = make_float2(0.f, 0.f), dh23 = make_float2(0.f, 0.f);
+                    const float ac = counted ? a : 0.f;
+                    const float2 aa = make_float2(ac, ac);
 #pragma unroll
-                for (int q4 = 0; q4 < NC4; ++q4) {
-                    const float4 d = dr[u * NC4 + q4];
-                    dh01 = __ffma2_rn(make_float2(d.x, d.y), w2[2 * q4], dh01);
-                    dh23 = __ffma2_rn(make_float2(d.z, d.w), w2[2 * q4 + 1], dh23);
-                    gw2[2 * q4] = __ffma2_rn(aa, make_float2(d.x, d.y), gw2[2 * q4]);
-                    gw2[2 * q4 + 1] = __ffma2_rn(aa, make_float2(d.z, d.w), gw2[2 * q4 + 1]);
+                    for (int q4 = 0; q4 < NC4; ++q4) {
+                        const float4 d = dr[u * NC4 + q4];
+                        dh01 = __ffma2_rn(make_float2(d.x, d.y), w2[2 * q4], dh01);
+                        dh23 = __ffma2_rn(make_float2(d.z, d.w), w2[2 * q4 + 1], dh23);
+                        gw2[2 * q4] = __ffma2_rn(aa, make_float2(d.x, d.y), gw2[2 * q4]);
+                        gw2[2 * q4 + 1] = __ffma2_rn(aa, make_float2(d.z, d.w), gw2[2 * q4 + 1]);
+                    }
+                    const bool in_range = live && (full || r0 + b + u < r_end);
+                    float dh = (dh01.x + dh01.y) + (dh23.x + dh23.y);
+                    if (acc_in && in_range) dh += *zp;  // (the same thread wrote it in the previous pass)
+                    const float dz = final_pass ? ((a > 0.f) ? dh * scale : 0.f) : dh;
+                    if (counted) gb += dz;
+                    if (in_range) *zp = dz;
+                    zp += ldz;
                 }
-                const bool in_range = live && (full || r0 + b + u < r_end);
-                float dh = (dh01.x + dh01.y) + (dh23.x + dh23.y);
-                if (acc_in && in_range) dh += *zp;  // (the same thread wrote it in the previous pass)
-                const float dz = final_pass ? ((a > 0.f) ? dh * scale : 0.f) : dh;
-                gb += dz;
-                if (in_range) *zp = dz;
-                zp += ldz;
-            }
+            };
+            if (cnt_rows >= kHdBatch) batch(std::true_type{});
+            else batch(std::false_type{});
 #pragma unroll
             for (int u = 0; u < kHdBatch; ++u) hv[u] = hn[u];
         }
@@ -606,7 +624,7 @@ static bool dense_hidden_enabled() {
 template <int NC4>
 static int launch_hidden_bwd(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw,
                              float scale, float* dZ1, int64_t ldz, float* dW2, float* db1, float* partials, int64_t n,
-                             int h, int c, cudaStream_t st) {
+                             int h, int c, int64_t n_count, cudaStream_t st) {
     if (h <= 256 && dense_hidden_enabled()) {
         // dense FFMA2 kernel: three CTAs of 256 threads per SM
         int64_t grid = 2 * kNumSM;
@@ -614,7 +632,7 @@ static int launch_hidden_bwd(const float* H1, int64_t ldh, const float* dS2, int
         rpb = ceil_div64(rpb, kHdTile) * kHdTile;
         grid = ceil_div64(n > 0 ? n : 1, rpb);
         const int threads = ((h + 31) / 32) * 32;
-        hidden_bwd_dense_kernel<NC4><<<(unsigned)grid, threads, 0, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, 0, 1);
+        hidden_bwd_dense_kernel<NC4, false><<<(unsigned)grid, threads, 0, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, 0, 1, n_count);
         TG_LAUNCH_CHECK();
         const int64_t n_elem = (int64_t)h * (c + 1);
         sum_partials_kernel<<<(unsigned)ceil_div64(n_elem * 8, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1, c, c);
@@ -636,15 +654,15 @@ static int launch_hidden_bwd(const float* H1, int64_t ldh, const float* dS2, int
     if (threads <= 256) {
         TG_CUDA(cudaFuncSetAttribute(hidden_bwd_kernel<NC4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         hidden_bwd_kernel<NC4, 256><<<(unsigned)grid, threads, smem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz,
-                                                                           partials, n, h, c, rpb, vec_ok, out_vec);
+                                                                           partials, n, h, c, rpb, vec_ok, out_vec, n_count);
     } else if (threads <= 512) {
         TG_CUDA(cudaFuncSetAttribute(hidden_bwd_kernel<NC4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         hidden_bwd_kernel<NC4, 512><<<(unsigned)grid, threads, smem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz,
-                                                                           partials, n, h, c, rpb, vec_ok, out_vec);
+                                                                           partials, n, h, c, rpb, vec_ok, out_vec, n_count);
     } else {
         TG_CUDA(cudaFuncSetAttribute(hidden_bwd_kernel<NC4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         hidden_bwd_kernel<NC4, 1024><<<(unsigned)grid, threads, smem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz,
-                                                                            partials, n, h, c, rpb, vec_ok, out_vec);
+                                                                            partials, n, h, c, rpb, vec_ok, out_vec, n_count);
     }
     TG_LAUNCH_CHECK();
     const int64_t n_elem = (int64_t)h * (c + 1);
@@ -659,14 +677,14 @@ static int launch_hidden_bwd(const float* H1, int64_t ldh, const float* dS2, int
 template <int NC4>
 static int launch_hidden_block(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw,
                                float scale, float* dZ1, int64_t ldz, float* dW2, int64_t ldg, float* db1, float* partials,
-                               int64_t n, int hb, int cb, int acc_in, int final_pass, cudaStream_t st) {
+                               int64_t n, int hb, int cb, int acc_in, int final_pass, int64_t n_count, cudaStream_t st) {
     int64_t grid = 2 * kNumSM;
     int64_t rpb = ceil_div64(n > 0 ? n : 1, grid);
     rpb = ceil_div64(rpb, kHdTile) * kHdTile;
     grid = ceil_div64(n > 0 ? n : 1, rpb);
     const int threads = ((hb + 31) / 32) * 32;
-    hidden_bwd_dense_kernel<NC4><<<(unsigned)grid, threads, 0, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, hb, cb, rpb,
-                                                                     acc_in, final_pass);
+    hidden_bwd_dense_kernel<NC4, true><<<(unsigned)grid, threads, 0, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, hb, cb, rpb,
+                                                                     acc_in, final_pass, n_count);
     TG_LAUNCH_CHECK();
     const int64_t n_elem = (int64_t)hb * (cb + 1);
     sum_partials_kernel<<<(unsigned)ceil_div64(n_elem * 8, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)hb * cb,
@@ -677,7 +695,7 @@ static int launch_hidden_block(const float* H1, int64_t ldh, const float* dS2, i
 
 static int hidden_bwd_blocked(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw, float scale,
                               float* dZ1, int64_t ldz, float* dW2, float* db1, float* partials, int64_t n, int h, int c,
-                              cudaStream_t st) {
+                              int64_t n_count, cudaStream_t st) {
     for (int j0 = 0; j0 < h; j0 += 256) {
         const int hb = (h - j0 < 256) ? (h - j0) : 256;
         for (int c0 = 0; c0 < c; c0 += 32) {
@@ -687,14 +705,14 @@ static int hidden_bwd_blocked(const float* H1, int64_t ldh, const float* dS2, in
             float *dz = dZ1 + j0, *dw = dW2 + (int64_t)j0 * c + c0, *db = db1 + j0;
             int rc;
             switch ((cb + 3) / 4) {
-                case 1: rc = launch_hidden_block<1>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
-                case 2: rc = launch_hidden_block<2>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
-                case 3: rc = launch_hidden_block<3>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
-                case 4: rc = launch_hidden_block<4>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
-                case 5: rc = launch_hidden_block<5>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
-                case 6: rc = launch_hidden_block<6>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
-                case 7: rc = launch_hidden_block<7>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
-                default: rc = launch_hidden_block<8>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, st); break;
+                case 1: rc = launch_hidden_block<1>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, n_count, st); break;
+                case 2: rc = launch_hidden_block<2>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, n_count, st); break;
+                case 3: rc = launch_hidden_block<3>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, n_count, st); break;
+                case 4: rc = launch_hidden_block<4>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, n_count, st); break;
+                case 5: rc = launch_hidden_block<5>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, n_count, st); break;
+                case 6: rc = launch_hidden_block<6>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, n_count, st); break;
+                case 7: rc = launch_hidden_block<7>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, n_count, st); break;
+                default: rc = launch_hidden_block<8>(h1, ldh, ds, ldd, w2, ldw, scale, dz, ldz, dw, c, db, partials, n, hb, cb, acc_in, final_pass, n_count, st); break;
             }
             if (rc != TG_OK) return rc;
         }
@@ -867,25 +885,32 @@ int64_t tg_hidden_bwd_scratch_floats(int64_t n, int32_t h, int32_t c) {
     return (int64_t)tg::kHbMaxGrid * h * (c + 1);
 }
 
-int tg_hidden_bwd_f32(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw,
-                      float scale, float* dZ1, int64_t ldz, float* dW2, float* db1, float* partials, int64_t n,
-                      int32_t h, int32_t c, void* stream) {
+int tg_hidden_bwd_rows_f32(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw,
+                           float scale, float* dZ1, int64_t ldz, float* dW2, float* db1, float* partials, int64_t n,
+                           int32_t h, int32_t c, int64_t n_count, void* stream) {
     using namespace tg;
     TG_REQUIRE(H1 && dS2 && W2 && dZ1 && dW2 && db1 && partials, TG_ERR_INVALID_ARG, "null pointer");
     TG_REQUIRE(n >= 0 && h > 0 && c > 0 && ldh >= h && ldd >= c && ldw >= c && ldz >= h, TG_ERR_INVALID_ARG, "bad shape");
+    TG_REQUIRE(n_count >= 0 && n_count <= n, TG_ERR_INVALID_ARG, "n_count must be in [0, n]");
     cudaStream_t st = as_stream(stream);
-    if (c > 32 || h > 1024) return hidden_bwd_blocked(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
+    if (c > 32 || h > 1024) return hidden_bwd_blocked(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
     const int nc4 = (c + 3) / 4;
     switch (nc4) {
-        case 1: return launch_hidden_bwd<1>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
-        case 2: return launch_hidden_bwd<2>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
-        case 3: return launch_hidden_bwd<3>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
-        case 4: return launch_hidden_bwd<4>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
-        case 5: return launch_hidden_bwd<5>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
-        case 6: return launch_hidden_bwd<6>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
-        case 7: return launch_hidden_bwd<7>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
-        default: return launch_hidden_bwd<8>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, st);
+        case 1: return launch_hidden_bwd<1>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
+        case 2: return launch_hidden_bwd<2>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
+        case 3: return launch_hidden_bwd<3>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
+        case 4: return launch_hidden_bwd<4>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
+        case 5: return launch_hidden_bwd<5>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
+        case 6: return launch_hidden_bwd<6>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
+        case 7: return launch_hidden_bwd<7>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
+        default: return launch_hidden_bwd<8>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
     }
+}
+
+int tg_hidden_bwd_f32(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw,
+                      float scale, float* dZ1, int64_t ldz, float* dW2, float* db1, float* partials, int64_t n,
+                      int32_t h, int32_t c, void* stream) {
+    return tg_hidden_bwd_rows_f32(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n, stream);
 }
 
 int64_t tg_gemm_scratch_floats(int32_t trans_a, int64_t m, int64_t n, int64_t k) {

@@ -288,9 +288,10 @@ def relu_dropout_backward(H: torch.Tensor, dH: torch.Tensor, scale: float) -> to
 
 
 def hidden_backward(H1: torch.Tensor, dS2: torch.Tensor, W2: torch.Tensor, scale: float,
-                    out_dZ1: Optional[torch.Tensor] = None):
-    """(dZ1, dW2, db1) — fused backward of S2 = H1 @ W2, dropout, relu, +b1: tg_hidden_bwd_f32.  Any class count and hidden
-    width: up to 32 classes (and 1024 hidden units) in one pass over H1, more in blocks of 32 classes / 256 units."""
+                    out_dZ1: Optional[torch.Tensor] = None, n_count: Optional[int] = None):
+    """(dZ1, dW2, db1) — fused backward of S2 = H1 @ W2, dropout, relu, +b1: tg_hidden_bwd_rows_f32.  Any class count and
+    hidden width: up to 32 classes (and 1024 hidden units) in one pass over H1, more in blocks of 32 classes / 256 units.
+    n_count: rows from n_count on get their dZ1 but do not count into dW2 / db1 (default: every row counts)."""
     H1 = _dense2d(H1, "H1")
     dS2 = _dense2d(dS2, "dS2")
     W2 = _dense2d(W2, "W2")
@@ -302,10 +303,10 @@ def hidden_backward(H1: torch.Tensor, dS2: torch.Tensor, W2: torch.Tensor, scale
     scratch = torch.empty(int(N.lib().tg_hidden_bwd_scratch_floats(n, h, c)), dtype=torch.float32, device=dev)
     blocks = 1 if (c <= 32 and h <= 1024) else ((c + 31) // 32) * ((h + 255) // 256)
     with torch.cuda.device(dev), _call("hidden_bwd", 2 * blocks, n=n, h=h, c=c):
-        N.check(N.lib().tg_hidden_bwd_f32(N.ptr(H1), _ld(H1), N.ptr(dS2), _ld(dS2), N.ptr(W2), _ld(W2), float(scale),
-                                          N.ptr(dZ1), _ld(dZ1), N.ptr(dW2), N.ptr(db1), N.ptr(scratch), n, h, c,
-                                          _stream()),
-                "tg_hidden_bwd_f32")
+        N.check(N.lib().tg_hidden_bwd_rows_f32(N.ptr(H1), _ld(H1), N.ptr(dS2), _ld(dS2), N.ptr(W2), _ld(W2), float(scale),
+                                               N.ptr(dZ1), _ld(dZ1), N.ptr(dW2), N.ptr(db1), N.ptr(scratch), n, h, c,
+                                               n if n_count is None else int(n_count), _stream()),
+                "tg_hidden_bwd_rows_f32")
     return dZ1, dW2, db1
 
 

@@ -26,6 +26,7 @@ single GPU without waiting kernels).
 """
 from __future__ import annotations
 
+import functools
 import threading
 from dataclasses import dataclass
 from typing import Callable, List, Optional
@@ -301,11 +302,12 @@ class ShardedGCN(torch.nn.Module):
             index = lg.train_idx if index is None else index
             if labels.is_cuda and index.is_cuda:
                 row_label = ops.make_row_label(lg.n_local, labels, index)
-            else:
-                row_label = ops.make_row_label_async(lg.n_local, labels, index, self.gc1.weight.device)
+            else:  # host labels: a callable, so that the copies are queued (side stream) only after layer 1 has been launched
+                row_label = functools.partial(ops.make_row_label_async, lg.n_local, labels, index, self.gc1.weight.device)
         self._calls += int(self.training)
+        defer = bool(self.training and torch.is_grad_enabled() and self.comm.world > 1)  # (decided here: grad mode is off inside Function.forward)
         return _ShardedLoss.apply(self.gc1.weight, self.gc1.bias, self.gc2.weight, self.gc2.bias, self, row_label,
-                                  keep_mask)
+                                  keep_mask, defer)
 
 
 class _Fork:
@@ -347,6 +349,8 @@ def sharded_forward(model: ShardedGCN, W1, b1, W2, b2, row_label, keep_mask, def
     seed_doc, seed_top = model.dropout_seeds() if (training and p > 0 and keep_mask is None) else (0, 0)
     # layer 1: document rows get the fused epilogue, topic rows are stored raw, summed over ranks, then finished
     H1 = ops.gc1_forward(csr, W1, b1, p, training, keep_mask, seed_doc, model._calls, raw_row_begin=D)
+    if callable(row_label):  # host labels: start their copy only now, with layer 1 already queued on the device
+        row_label = row_label()
     S2 = torch.empty((lg.n_local, int(W2.shape[1])), dtype=torch.float32, device=H1.device)
     top = H1[D:]
     with _Fork(model.side_stream()) as side:
@@ -367,7 +371,7 @@ def sharded_forward(model: ShardedGCN, W1, b1, W2, b2, row_label, keep_mask, def
 def sharded_backward(model: ShardedGCN, W2, saved, dloss=None, loss_partial: Optional[torch.Tensor] = None):
     """Backward on one rank: returns (dW1, db1, dW2, db2), replicated gradients already summed over ranks.
 
-    Collectives: the K x C topic rows of dS2 (side stream, behind the document rows of the hidden-layer backward) and ONE
+    Collectives: the K x C topic rows of dS2 (side stream, behind the column sums that give db2) and ONE
     packed all-reduce at the end: the K x H topic rows of dW1, dW2, db1, db2 and — when `loss_partial` is given — the
     deferred loss sum, which is written back into `loss_partial` in place.  `dloss` (the upstream gradient of the
     scalar loss, a device scalar) is folded into dS2 by the SpMM epilogue and into db2 on C elements: no pass over dZ2."""
@@ -377,19 +381,15 @@ def sharded_backward(model: ShardedGCN, W2, saved, dloss=None, loss_partial: Opt
     H1, dZ2 = saved
     g = None if dloss is None else dloss.reshape(()).to(torch.float32).contiguous()
     scale = 1.0 / (1.0 - model.dropout) if (model.training and model.dropout > 0) else 1.0
-    db2 = ops.colsum(dZ2)  # topic rows of dZ2 are zero: every rank contributes its documents only
-    if g is not None:
-        db2 = db2 * g
     dS2 = ops.spmm(csr, dZ2, out_scale=g)
-    dZ1 = torch.empty_like(H1)
     with _Fork(model.side_stream()) as side:
         comm.all_reduce(dS2[D:])
-        _, dW2_t, db1_t = ops.hidden_backward(H1[D:], dS2[D:], W2, scale, out_dZ1=dZ1[D:])
-    _, dW2, db1 = ops.hidden_backward(H1[:D], dS2[:D], W2, scale, out_dZ1=dZ1[:D])
+    db2 = ops.colsum(dZ2)  # (independent of the all-reduce: hides its latency; topic rows of dZ2 are zero)
+    if g is not None:
+        db2 = db2 * g
     side.join()
-    if comm.rank == 0:  # the replicated topic rows count once
-        dW2 = dW2 + dW2_t
-        db1 = db1 + db1_t
+    # one launch over all rows; the replicated topic rows give their dZ1 everywhere but count into dW2 / db1 on rank 0 only
+    dZ1, dW2, db1 = ops.hidden_backward(H1, dS2, W2, scale, n_count=(lg.n_local if comm.rank == 0 else D))
     dW1 = ops.spmm(csr, dZ1)
     h, c = dW2.shape
     parts = [dW1[D:].reshape(-1), dW2.reshape(-1), db1, db2]
@@ -407,8 +407,7 @@ def sharded_backward(model: ShardedGCN, W2, saved, dloss=None, loss_partial: Opt
 
 class _ShardedLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, W1, b1, W2, b2, model, row_label, keep_mask):
-        defer = bool(model.training and torch.is_grad_enabled() and model.comm.world > 1)
+    def forward(ctx, W1, b1, W2, b2, model, row_label, keep_mask, defer):
         loss, saved = sharded_forward(model, W1, b1, W2, b2, row_label, keep_mask, defer_loss=defer)
         ctx.model = model
         ctx.loss_partial = loss.detach() if defer else None  # (an alias of the output's storage, without its autograd node)
@@ -419,7 +418,7 @@ class _ShardedLoss(torch.autograd.Function):
     def backward(ctx, dloss):
         W2, H1, dZ2 = ctx.saved_tensors
         dW1, db1, dW2, db2 = sharded_backward(ctx.model, W2, (H1, dZ2), dloss, loss_partial=ctx.loss_partial)
-        return dW1, db1, dW2, db2, None, None, None
+        return dW1, db1, dW2, db2, None, None, None, None
 
 
 def run_threads(world: int, fn: Callable[[int, ThreadComm], object]) -> list:

@@ -187,6 +187,11 @@ int64_t tg_hidden_bwd_scratch_floats(int64_t n, int32_t h, int32_t c);
 int tg_hidden_bwd_f32(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2,
                       int64_t ldw, float scale, float* dZ1, int64_t ldz, float* dW2, float* db1,
                       float* partials, int64_t n, int32_t h, int32_t c, void* stream);
+/* the same with a row limit for the two reductions: rows >= n_count get their dZ1 but do not count into dW2 / db1 (the
+ * replicated topic rows of a document-sharded graph count on one rank only, yet every rank needs their dZ1) */
+int tg_hidden_bwd_rows_f32(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2,
+                           int64_t ldw, float scale, float* dZ1, int64_t ldz, float* dW2, float* db1,
+                           float* partials, int64_t n, int32_t h, int32_t c, int64_t n_count, void* stream);
 int64_t tg_colsum_scratch_floats(int64_t n, int32_t c);
 int tg_colsum_f32(const float* X, int64_t ldx, int64_t n, int32_t c, float* scratch, float* out,
                   void* stream);

@@ -1009,3 +1009,23 @@ def test_dropout_p_one_drops_everything(tg, small_golden):
     assert torch.isfinite(logits).all() and torch.equal(logits.detach(), b2.expand_as(logits).contiguous())   # H1 = 0: logits = b2
     logits.sum().backward()
     assert float(model.gc1.weight.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n,h,c,n_count", [(5000, 256, 20, 4700), (3000, 300, 8, 0), (2000, 200, 52, 1999)])
+def test_hidden_backward_row_limit(tg, n, h, c, n_count):
+    """tg_hidden_bwd_rows_f32: rows >= n_count get their dZ1 but stay out of dW2 / db1 (replicated rows of a sharded graph)."""
+    from topicgcn_b200 import ops
+    rng = np.random.default_rng(n)
+    H1 = np.maximum(rng.normal(size=(n, h)), 0).astype(np.float32) * 2.0
+    dS2 = rng.normal(size=(n, c)).astype(np.float32)
+    W2 = rng.normal(size=(h, c)).astype(np.float32)
+    dZ1, dW2, db1 = ops.hidden_backward(torch.tensor(H1, device=dev()), torch.tensor(dS2, device=dev()),
+                                        torch.tensor(W2, device=dev()), 2.0, n_count=n_count)
+    dZ1_ref = np.where(H1 > 0, (dS2.astype(np.float64) @ W2.astype(np.float64).T) * 2.0, 0.0)
+    assert rel_err(dZ1.cpu().numpy(), dZ1_ref) <= 1e-5
+    want_w = H1[:n_count].astype(np.float64).T @ dS2[:n_count].astype(np.float64)
+    want_b = dZ1_ref[:n_count].sum(axis=0)
+    if n_count == 0:
+        assert not dW2.cpu().numpy().any() and not db1.cpu().numpy().any()
+    else:
+        assert rel_err(dW2.cpu().numpy(), want_w) <= 2e-5 and rel_err(db1.cpu().numpy(), want_b) <= 2e-5
