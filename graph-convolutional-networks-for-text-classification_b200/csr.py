@@ -62,11 +62,13 @@ class DeviceCSR:
         self.doc_nq = (int(info[7]) >> 24) & 0xFF       # float4 chunks per lane of the document role (slice = 32 * nq columns)
         self.hub_gs = (int(info[7]) >> 32) & 0xFF       # lanes per hub slot sub-group (32 / 16 / 8: 256 / 512 / 1024 slots per group)
 
-    def spmm_launches(self, B: torch.Tensor, n_feat: int, philox: bool = False, out_vec4_ok: bool = True) -> int:
+    def spmm_launches(self, B: torch.Tensor, n_feat: int, philox: bool = False, out_vec4_ok: bool = True,
+                      loss: bool = False) -> int:
         """Kernels one tg_spmm* / tg_gc* call on this matrix launches (tg_plan_spmm_launches: the library's own kernel
-        selection, no Python mirror of it)."""
+        selection, no Python mirror of it).  philox: the call draws a Philox dropout mask; loss: it is the fused loss forward."""
         ld = int(B.stride(0)) if B.shape[0] > 1 else int(B.shape[1])
-        return int(N.lib().tg_plan_spmm_launches(self._plan, N.ptr(B), ld, int(n_feat), int(bool(philox)), int(bool(out_vec4_ok))))
+        mode = 2 if loss else int(bool(philox))
+        return int(N.lib().tg_plan_spmm_launches(self._plan, N.ptr(B), ld, int(n_feat), mode, int(bool(out_vec4_ok))))
 
     def __del__(self):
         try:

@@ -413,7 +413,8 @@ int tg_plan_spmm_launches(const tg_plan* pl, const float* B, int64_t ldb, int32_
     if (!pl || n_feat <= 0) return 0;
     if (out_vec4_ok) {
         tg::StreamCall sc{nullptr, nullptr, B, ldb, n_feat, nullptr, 0};
-        const int k = tg::roles2_launches(pl, sc, philox != 0);
+        // philox = 2: the call is the fused loss forward (row-wise epilogue)
+        const int k = tg::roles2_launches(pl, sc, philox == 1, philox == 2);
         if (k > 0) return k;
     }
     return 1;  // gather kernel: split rows are finished by the last arriver inside the same launch

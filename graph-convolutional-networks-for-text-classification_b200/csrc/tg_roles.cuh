@@ -26,10 +26,13 @@ void roles2_plan_free(tg_plan* pl);
 size_t roles2_workspace_bytes(const tg_plan* pl, int32_t n_feat);
 
 // kernels of this file one product launches (0: the role kernels do not apply and the gather kernel runs)
-int roles2_launches(const tg_plan* pl, const StreamCall& c, bool philox);
+int roles2_launches(const tg_plan* pl, const StreamCall& c, bool philox, bool whole_row);
 
-bool roles2_applicable(const tg_plan* pl, const StreamCall& c);          // 64 <= n_feat <= 1024, n_feat % 4 == 0
+// 64 <= n_feat <= 1024 (n_feat % 4 == 0); plans with 64 / 32-column slices (more than 256 hub rows) also take class-sized
+// operands (n_feat <= 32 nq) and then the row-wise loss epilogue (whole_row)
+bool roles2_applicable(const tg_plan* pl, const StreamCall& c, bool whole_row);
 int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st);
+int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiLoss& epi, cudaStream_t st);
 bool roles2_rect_applicable(const tg_plan* pl, const StreamCall& c);
 int roles2_rect_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st);
 bool roles2_narrow_applicable(const tg_plan* pl, const StreamCall& c);   // n_feat <= 32 (class-sized operands)

@@ -265,9 +265,13 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
 // slice width (with one row per group the narrow slices were latency bound: 1.7 us per job for a quarter of the work).
 // TABLE: B is only the resident table (X * W with a sparse feature matrix X): no self loops to prefetch, every entry
 // addresses the table.
-template <int NQ, bool TABLE>
-__device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, const CUtensorMap* tmap_job, unsigned char* smem,
+template <int NQ, bool TABLE, class Epi>
+__device__ __forceinline__ void doc_role(const R2Args& a, const Epi& epi, const CUtensorMap* tmap_job, unsigned char* smem,
                                          uint64_t* bars, int bid) {
+    // Epi = EpiStore: elementwise epilogue with the per-thread constants in registers (any width).  Epi = EpiLoss (row-wise
+    // log-softmax / cross-entropy): the row must lie inside ONE slice (n_feat <= 32 NQ), so that the 8 lanes of a group hold
+    // the whole row — the class-sized products of graphs whose plan uses narrow slices (K = 1 024 topics).
+    constexpr bool kStore = std::is_same<Epi, EpiStore>::value;
     constexpr int R = 4 / NQ;              // rows per group and job; plan jobs (64 rows) per super job
     constexpr int kSliceCols = 32 * NQ;
     constexpr int kRowB = kSliceCols * 4;  // bytes of a resident row
@@ -352,10 +356,13 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
     };
     // per-thread constants of the epilogue: this lane's bias values, the optional upstream scale
     float4 bias4[NQ];
+    float gscale = 1.f;
+    if constexpr (kStore) {
 #pragma unroll
-    for (int u = 0; u < NQ; ++u)
-        bias4[u] = (epi.bias && valid[u]) ? __ldg(reinterpret_cast<const float4*>(epi.bias + (int64_t)(q0 + 8 * u) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float gscale = epi.out_scale ? __ldg(epi.out_scale) : 1.f;
+        for (int u = 0; u < NQ; ++u)
+            bias4[u] = (epi.bias && valid[u]) ? __ldg(reinterpret_cast<const float4*>(epi.bias + (int64_t)(q0 + 8 * u) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gscale = epi.out_scale ? __ldg(epi.out_scale) : 1.f;
+    }
     // bit-packed mask: four words per 128 columns; chunk q lives in word q / 8 at bits 4 (q % 8) .. — this lane's NQ words
     // of a row are the words slice * NQ + u
     const int mask_words = ((a.n_chunks4 + 31) / 32) * 4;
@@ -386,11 +393,17 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
         return b;
     };
     const float* selfp = a.B + ((int64_t)dl * kSJRows + grp) * a.ldb + (int64_t)q0 * 4;
-    float* yp = epi.Y + ((int64_t)dl * kSJRows + grp) * epi.ldy + (int64_t)q0 * 4;
-    const int64_t yrow_stride = (int64_t)kJobRows * epi.ldy;
-    const int64_t ysj_stride = (int64_t)a.doc_lanes * kSJRows * epi.ldy;
-    // nothing to do after the sums: plain product without bias / activation / scale / dropout
-    const bool plain = !epi.bias && !epi.relu && !epi.out_scale && !a.keep_bits && epi.drop_mode != 2;
+    float* yp = nullptr;
+    int64_t yrow_stride = 0, ysj_stride = 0;
+    bool plain = false;
+    if constexpr (kStore) {
+        yp = epi.Y + ((int64_t)dl * kSJRows + grp) * epi.ldy + (int64_t)q0 * 4;
+        yrow_stride = (int64_t)kJobRows * epi.ldy;
+        ysj_stride = (int64_t)a.doc_lanes * kSJRows * epi.ldy;
+        // nothing to do after the sums: plain product without bias / activation / scale / dropout
+        plain = !epi.bias && !epi.relu && !epi.out_scale && !a.keep_bits && epi.drop_mode != 2;
+    }
+    const unsigned gmask = group_mask<8>(lane);
     float4 cur[R][NQ];
     load_self(cur, dl, selfp);
     Bits kbits = load_bits(dl);
@@ -537,8 +550,15 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (!produce[r]) continue;
-            // fused epilogue (EpiStore semantics, tg_epilogue.cuh) with the per-thread constants held in registers
             const int64_t row = (int64_t)sj * kSJRows + r * kJobRows + grp;
+            if constexpr (!kStore) {
+                // row-wise epilogue: the group holds the whole row (chunk gl + 8 u of lane gl)
+                Chunk<4> out[NQ];
+#pragma unroll
+                for (int u = 0; u < NQ; ++u) { out[u].v[0] = acc[r][u].x; out[u].v[1] = acc[r][u].y; out[u].v[2] = acc[r][u].z; out[u].v[3] = acc[r][u].w; }
+                epi.template apply<4, 8, NQ>(row, gl, gmask, a.n_chunks4, out);
+            } else {
+            // fused epilogue (EpiStore semantics, tg_epilogue.cuh) with the per-thread constants held in registers
             float* yrow = yp + r * yrow_stride;
             if (plain || row >= epi.raw_row_begin) {
 #pragma unroll
@@ -574,6 +594,7 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const EpiStore& epi, c
                     }
                     *reinterpret_cast<float4*>(yrow + u * 32) = make_float4(y[0], y[1], y[2], y[3]);
                 }
+            }
             }
         }
         yp += ysj_stride;
@@ -636,8 +657,8 @@ __global__ void __launch_bounds__(256) r2_keep_bits_half_kernel(uint32_t* __rest
     }
 }
 
-template <int GS, int NQ, bool TABLE>
-__global__ void __launch_bounds__(kThreads, 1) roles2_kernel(const R2Args a, const EpiStore epi, const __grid_constant__ CUtensorMap tmapB,
+template <int GS, int NQ, bool TABLE, class Epi>
+__global__ void __launch_bounds__(kThreads, 1) roles2_kernel(const R2Args a, const Epi epi, const __grid_constant__ CUtensorMap tmapB,
                                                             const __grid_constant__ CUtensorMap tmapJob) {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bars[2 * kStages + 2];
@@ -650,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) roles2_kernel(const R2Args a, con
         hub_role<GS>(a, &tmapB, smem, bars, bid);
     } else {
         if (a.only_role == 1) return;
-        doc_role<NQ, TABLE>(a, epi, &tmapJob, smem, bars, bid - n_hub_ctas);
+        doc_role<NQ, TABLE, Epi>(a, epi, &tmapJob, smem, bars, bid - n_hub_ctas);
     }
 }
 
@@ -1502,12 +1523,21 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
     return TG_OK;
 }
 
-bool roles2_applicable(const tg_plan* pl, const StreamCall& c) {
+// whole_row: the epilogue needs a whole output row inside one lane group (EpiLoss)
+bool roles2_applicable(const tg_plan* pl, const StreamCall& c, bool whole_row) {
     if (!pl || !pl->r2_ok || pl->r2_rect != 0) return false;
-    if (c.n_feat < 64 || c.n_feat % 4 != 0 || c.n_feat > 1024) return false;
-    // below ~16 K rows a launch is a few microseconds of work and the 148-CTA prologue (resident hub rows, barriers, TMA
-    // descriptors) costs more than it saves (R8 shape: 0.150 vs 0.113 ms per captured step on the gather kernel)
-    if (pl->n_rows < (int64_t)pl->r2_min_rows) return false;
+    if (c.n_feat < 4 || c.n_feat % 4 != 0 || c.n_feat > 1024) return false;
+    if (c.n_feat < 64) {
+        // class-sized operands: plans with warp-per-slot hub CTAs (gs = 32: 128-column slices) have their own narrow kernels;
+        // plans with 64 / 32-column slices run them here as a one-slice product (TMA zero-fills the rest of the box)
+        if (pl->r2_gs == 32 || !pl->r2_narrow_ok || c.n_feat > 32 * pl->r2_nq) return false;
+        if (pl->n_rows < (int64_t)pl->r2_narrow_min_rows) return false;  // small graphs: the operand is L2 resident, the gather kernel is faster
+    } else {
+        // below ~16 K rows a launch is a few microseconds of work and the 148-CTA prologue (resident hub rows, barriers, TMA
+        // descriptors) costs more than it saves (R8 shape: 0.150 vs 0.113 ms per captured step on the gather kernel)
+        if (pl->n_rows < (int64_t)pl->r2_min_rows) return false;
+    }
+    if (whole_row && (c.n_feat > 32 * pl->r2_nq || pl->r2_gs == 32)) return false;
     if (c.ldb % 4 != 0 || !aligned16(c.B) || !encode_tiled_fn()) return false;
     return true;
 }
@@ -1532,9 +1562,9 @@ size_t roles2_workspace_bytes(const tg_plan* pl, int32_t n_feat) {
     return part + (size_t)pl->n_rows * (((ld + kFT - 1) / kFT) * 16) + 256;
 }
 
-int roles2_launches(const tg_plan* pl, const StreamCall& c, bool philox) {
-    if (roles2_rect_applicable(pl, c) && !(pl->r2_rect == 1 && philox)) return pl->r2_rect;  // resident-table product: one kernel; all-hub product: hub role + finish
-    if (roles2_applicable(pl, c)) return 2 + (philox ? 1 : 0);
+int roles2_launches(const tg_plan* pl, const StreamCall& c, bool philox, bool whole_row) {
+    if (!whole_row && roles2_rect_applicable(pl, c) && !(pl->r2_rect == 1 && philox)) return pl->r2_rect;  // resident-table product: one kernel; all-hub product: hub role + finish
+    if (roles2_applicable(pl, c, whole_row)) return 2 + (philox ? 1 : 0);
     if (roles2_narrow_applicable(pl, c)) return 2;
     return 0;
 }
@@ -1568,20 +1598,20 @@ void split_sms(double hub_w, double doc_w, int hub_unit, int doc_unit, int n_chu
     *doc_lanes_out = std::min(best_d, std::max(n_jobs, 1));
 }
 
-template <int GS, int NQ, bool TABLE>
-int launch_roles(const R2Args& a, const EpiStore& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem, unsigned grid,
+template <int GS, int NQ, bool TABLE, class Epi>
+int launch_roles(const R2Args& a, const Epi& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem, unsigned grid,
                  cudaStream_t st) {
-    TG_CUDA(cudaFuncSetAttribute(roles2_kernel<GS, NQ, TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    roles2_kernel<GS, NQ, TABLE><<<grid, kThreads, smem, st>>>(a, epi, tmap, tmap_job);
+    TG_CUDA(cudaFuncSetAttribute(roles2_kernel<GS, NQ, TABLE, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roles2_kernel<GS, NQ, TABLE, Epi><<<grid, kThreads, smem, st>>>(a, epi, tmap, tmap_job);
     TG_LAUNCH_CHECK();
     return TG_OK;
 }
 template <int GS>
 int launch_wide_gs(int nq, const R2Args& a, const EpiStore& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem,
                    unsigned grid, cudaStream_t st) {
-    if (nq == 4) return launch_roles<GS, 4, false>(a, epi, tmap, tmap_job, smem, grid, st);
-    if (nq == 2) return launch_roles<GS, 2, false>(a, epi, tmap, tmap_job, smem, grid, st);
-    return launch_roles<GS, 1, false>(a, epi, tmap, tmap_job, smem, grid, st);
+    if (nq == 4) return launch_roles<GS, 4, false, EpiStore>(a, epi, tmap, tmap_job, smem, grid, st);
+    if (nq == 2) return launch_roles<GS, 2, false, EpiStore>(a, epi, tmap, tmap_job, smem, grid, st);
+    return launch_roles<GS, 1, false, EpiStore>(a, epi, tmap, tmap_job, smem, grid, st);
 }
 int launch_wide(int gs, int nq, const R2Args& a, const EpiStore& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem,
                 unsigned grid, cudaStream_t st) {
@@ -1589,11 +1619,22 @@ int launch_wide(int gs, int nq, const R2Args& a, const EpiStore& epi, const CUte
     if (gs == 16) return launch_wide_gs<16>(nq, a, epi, tmap, tmap_job, smem, grid, st);
     return launch_wide_gs<8>(nq, a, epi, tmap, tmap_job, smem, grid, st);
 }
+// row-wise loss epilogue: plans with narrow slices only (gs = 16 / 8; the warp-per-slot plans have their own narrow kernels)
+int launch_wide(int gs, int nq, const R2Args& a, const EpiLoss& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem,
+                unsigned grid, cudaStream_t st) {
+    if (gs == 16 && nq == 4) return launch_roles<16, 4, false, EpiLoss>(a, epi, tmap, tmap_job, smem, grid, st);
+    if (gs == 16 && nq == 2) return launch_roles<16, 2, false, EpiLoss>(a, epi, tmap, tmap_job, smem, grid, st);
+    if (gs == 16 && nq == 1) return launch_roles<16, 1, false, EpiLoss>(a, epi, tmap, tmap_job, smem, grid, st);
+    if (gs == 8 && nq == 2) return launch_roles<8, 2, false, EpiLoss>(a, epi, tmap, tmap_job, smem, grid, st);
+    if (gs == 8 && nq == 1) return launch_roles<8, 1, false, EpiLoss>(a, epi, tmap, tmap_job, smem, grid, st);
+    set_error("role kernels: no loss-epilogue instance for gs = %d, nq = %d", gs, nq);
+    return TG_ERR_UNSUPPORTED;
+}
 int launch_table(int nq, const R2Args& a, const EpiStore& epi, const CUtensorMap& tmap, const CUtensorMap& tmap_job, size_t smem,
                  unsigned grid, cudaStream_t st) {
-    if (nq == 4) return launch_roles<32, 4, true>(a, epi, tmap, tmap_job, smem, grid, st);
-    if (nq == 2) return launch_roles<32, 2, true>(a, epi, tmap, tmap_job, smem, grid, st);
-    return launch_roles<32, 1, true>(a, epi, tmap, tmap_job, smem, grid, st);
+    if (nq == 4) return launch_roles<32, 4, true, EpiStore>(a, epi, tmap, tmap_job, smem, grid, st);
+    if (nq == 2) return launch_roles<32, 2, true, EpiStore>(a, epi, tmap, tmap_job, smem, grid, st);
+    return launch_roles<32, 1, true, EpiStore>(a, epi, tmap, tmap_job, smem, grid, st);
 }
 
 void fill_common(R2Args& a, const tg_plan* pl, const StreamCall& c) {
@@ -1614,7 +1655,8 @@ void fill_common(R2Args& a, const tg_plan* pl, const StreamCall& c) {
 
 }  // namespace
 
-int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st) {
+template <class Epi>
+static int roles2_run_t(const tg_plan* pl, const StreamCall& c, const Epi& epi, cudaStream_t st) {
     R2Args a;
     fill_common(a, pl, c);
     const int nq = pl->r2_nq, gs = pl->r2_gs, nsub = 32 / gs;
@@ -1626,7 +1668,8 @@ int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cuda
     // Philox dropout: the keep mask is drawn by a separate ALU-bound kernel into a bit-packed side buffer (1 bit per
     // element) instead of inside the document role, whose CTAs have no issue slots to spare (ncu: the in-kernel RNG
     // cost 0.4 ms at 1M x 256).  Same mask, bit for bit, as the definition in tg_common.cuh.
-    if (epi.drop_mode == 1) {
+    if constexpr (std::is_same<Epi, EpiStore>::value) {
+      if (epi.drop_mode == 1) {
         const size_t part_bytes = partial_bytes(pl, c.n_feat);
         const size_t mask_bytes = (size_t)pl->n_rows * (size_t)slices128 * 16;
         TG_REQUIRE(c.workspace_bytes >= part_bytes + mask_bytes + 16, TG_ERR_WORKSPACE, "workspace %zu B < required %zu B (dropout mask)",
@@ -1647,6 +1690,7 @@ int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cuda
         }
         TG_LAUNCH_CHECK();
         a.keep_bits = bits;
+      }
     }
     // share of the SMs given to the hub role: both fronts must advance together so that the second reader of a row of B
     // hits L2 (split_sms).  Weights in shared-memory wavefronts / issue slots per 128 columns (measured per role, profiles/):
@@ -1674,6 +1718,9 @@ int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cuda
     FinishArgs f{a.partials, a.ldp, a.hub_lanes, a.Kh, a.Kv, pl->r2_vmap, pl->r2_vcnt, pl->hub_rows, a.n_chunks4};
     return finish_run(f, epi, st);
 }
+
+int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiStore& epi, cudaStream_t st) { return roles2_run_t(pl, c, epi, st); }
+int roles2_run(const tg_plan* pl, const StreamCall& c, const EpiLoss& epi, cudaStream_t st) { return roles2_run_t(pl, c, epi, st); }
 
 static void narrow_smem(const tg_plan* pl, int n_feat, size_t* hub_s, size_t* doc_s, size_t* lane_s) {
     const size_t rowb = (size_t)n_feat * 4;

@@ -280,6 +280,9 @@ static int rowwise_loss_vec(const float* Z, int64_t ldz, int64_t n_rows, int n_c
     return TG_ERR_UNSUPPORTED;
 }
 
+template <class Epi> struct EpiTraits { static constexpr bool whole_row = false; };
+template <> struct EpiTraits<EpiLoss> { static constexpr bool whole_row = true; };  // log-softmax needs the whole row in one lane group
+
 template <class Epi>
 static int run_spmm(const tg_plan* pl, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                     const float* B, int64_t ldb, int32_t n_feat, bool out_vec4_ok, const Epi& epi, void* workspace,
@@ -298,8 +301,8 @@ static int run_spmm(const tg_plan* pl, const int32_t* rowptr, const int32_t* col
             // rectangular operands (sparse feature matrix x weight, and the transpose product): one role each
             // (the resident-table kernel has no Philox path: a dropout epilogue on X * W takes the gather kernel)
             if (roles2_rect_applicable(pl, sc) && !(pl->r2_rect == 1 && epi.drop_mode == 1)) return roles2_rect_run(pl, sc, epi, st);
-            if (roles2_applicable(pl, sc)) return roles2_run(pl, sc, epi, st);
         }
+        if (roles2_applicable(pl, sc, EpiTraits<Epi>::whole_row)) return roles2_run(pl, sc, epi, st);
         if (roles2_narrow_applicable(pl, sc)) return roles2_narrow_run(pl, sc, epi, st);
     }
     SpmmArgs a;

@@ -53,12 +53,13 @@ class _call:
         return False
 
 
-def _spmm_launches(csr, B: torch.Tensor, n_feat: int, philox: bool = False, out: Optional[torch.Tensor] = None) -> int:
+def _spmm_launches(csr, B: torch.Tensor, n_feat: int, philox: bool = False, out: Optional[torch.Tensor] = None,
+                   loss: bool = False) -> int:
     """Kernels one SpMM-type call launches: the product itself, the finishing kernel of the streaming paths (hub rows =
     fixed-order sum of the per-CTA partials + epilogue) and, for Philox dropout on the wide streaming path, the kernel
     that draws the bit-packed keep mask.  Asked of the library (tg_plan_spmm_launches), not mirrored here."""
     ok4 = out is None or (out.data_ptr() % 16 == 0 and (out.shape[0] <= 1 or out.stride(0) % 4 == 0))
-    return csr.spmm_launches(B, n_feat, philox, ok4)
+    return csr.spmm_launches(B, n_feat, philox, ok4, loss=loss)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -211,7 +212,7 @@ def gc2_loss_forward(csr: DeviceCSR, S2: torch.Tensor, bias: Optional[torch.Tens
     dZ2 = torch.empty((csr.n_rows, Cc), dtype=torch.float32, device=dev) if want_grad else None
     row_loss = torch.empty(csr.n_rows, dtype=torch.float32, device=dev)
     ws, ws_bytes = csr.workspace(Cc)
-    with torch.cuda.device(dev), _call("gc2_loss_fwd", _spmm_launches(csr, S2, Cc), n_feat=Cc, csr=csr):
+    with torch.cuda.device(dev), _call("gc2_loss_fwd", _spmm_launches(csr, S2, Cc, loss=True), n_feat=Cc, csr=csr):
         N.check(N.lib().tg_gc2_loss_fwd_f32(csr.plan, N.ptr(csr.rowptr), N.ptr(csr.colidx), N.ptr(csr.vals), N.ptr(S2),
                                             _ld(S2), N.ptr(bias), N.ptr(row_label), float(inv_count), N.ptr(logits),
                                             Cc, N.ptr(dZ2), Cc, N.ptr(row_loss), Cc, ws, ws_bytes, _stream()),

@@ -96,7 +96,8 @@ int tg_plan_info(const tg_plan* plan, int64_t info_host[8]);
 /* bytes of scratch a tg_spmm* / tg_gc* call with `n_feat` columns needs (partials of split hub rows) */
 size_t tg_plan_workspace_bytes(const tg_plan* plan, int32_t n_feat);
 /* number of kernels a tg_spmm* / tg_gc* call on this plan launches for a dense operand B (device pointer, only its
- * alignment is inspected) with leading dimension ldb and `n_feat` columns; philox: the call draws a Philox dropout mask;
+ * alignment is inspected) with leading dimension ldb and `n_feat` columns; philox: 1 = the call draws a Philox dropout
+ * mask, 2 = the call is tg_gc2_loss_fwd_f32 (row-wise loss epilogue), 0 = neither;
  * out_vec4_ok: outputs / bias are 16-byte aligned with leading dimensions that are multiples of 4.  Instrumentation
  * only (the launch counter of bench.py); mirrors the kernel selection of the compute entry points exactly. */
 int tg_plan_spmm_launches(const tg_plan* plan, const float* B, int64_t ldb, int32_t n_feat, int32_t philox,

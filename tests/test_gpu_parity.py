@@ -564,8 +564,8 @@ def test_roles2_narrow_kernel_parity(tg, monkeypatch, n_docs, n_topics, thr, C):
     assert torch.equal(y, tg.spmm(csr, S2d))
     csr_g = tg.DeviceCSR(csr.rowptr, csr.colidx, csr.vals, g.n, g.n, hub_threshold=thr, segment_nnz=max(8, thr // 2), streaming=False)
     y_g = tg.spmm(csr_g, S2d)
-    # (the narrow role kernels are written for the warp-per-slot layout, <= 256 hub rows: more topics take the gather kernel)
-    assert csr.spmm_launches(S2d, C) == (2 if n_topics <= 256 else 1) and csr_g.spmm_launches(S2d, C) == 1
+    # (<= 256 hub rows: the narrow role kernels; more: the wide kernel's 64 / 32-column slices take the operand as one slice)
+    assert csr.spmm_launches(S2d, C) == 2 and csr.spmm_launches(S2d, C, loss=True) == 2 and csr_g.spmm_launches(S2d, C) == 1
     assert float((y_g - y).abs().max() / y.abs().max()) <= SPMM_RTOL
     target = rng.integers(0, C, size=n_docs)
     index = np.sort(rng.choice(n_docs, size=n_docs * 2 // 3, replace=False))
@@ -819,6 +819,7 @@ def test_c4_shape_narrow_products(tg, c4_small, C):
     S2 = rng.normal(size=(g.n, C)).astype(np.float32)
     b2 = rng.normal(size=C).astype(np.float32)
     S2d = torch.tensor(S2, device=dev())
+    assert csr.spmm_launches(S2d, C) == 2 and csr.spmm_launches(S2d, C, loss=True) == 2   # one 32-column slice of the wide kernel
     ref, ref64 = O.spmm(coo, S2), O.spmm_f64(coo, S2)
     y = tg.spmm(csr, S2d)
     yn = y.cpu().numpy()
@@ -860,7 +861,7 @@ def test_empty_rows_on_the_role_kernels(tg, monkeypatch, n_docs, n_topics):
     for F in (128, 20):
         B = torch.randn(g.n, F, device=dev(), generator=gen)
         bias = torch.randn(F, device=dev(), generator=gen)
-        assert csr.spmm_launches(B, F) == (2 if (F > 32 or n_topics <= 256) else 1)   # (narrow role kernels: <= 256 hub rows)
+        assert csr.spmm_launches(B, F) == 2
         ref = O.spmm(coo, B.cpu().numpy())
         out = torch.full((g.n, F), float("nan"), device=dev())    # poisoned output buffer
         y = tg.spmm(csr, B, bias, out=out).cpu().numpy()
