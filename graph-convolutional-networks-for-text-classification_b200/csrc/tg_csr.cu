@@ -272,7 +272,10 @@ int tg_plan_create(const int32_t* rowptr, const int32_t* colidx, const float* va
     TG_REQUIRE(rowptr && plan_out, TG_ERR_INVALID_ARG, "null pointer");
     TG_REQUIRE(n_rows >= 0 && n_rows < (int64_t)INT32_MAX && nnz < (int64_t)INT32_MAX, TG_ERR_OVERFLOW,
                "n_rows/nnz must fit int32");
-    if (segment_nnz <= 0 && hub_threshold <= 0 && n_rows > 0 && nnz <= (int64_t)32 << 20 && nnz / n_rows >= 24) {
+    if (segment_nnz <= 0 && hub_threshold <= 0 && n_rows > 0 &&
+        ((nnz <= (int64_t)32 << 20 && nnz / n_rows >= 24) || nnz <= (int64_t)4 << 20)) {
+        // Small graphs (R8 / 20NG shapes: a step is ~0.1 ms of kernels) take the same budget: a 256-entry segment is 64
+        // dependent batches of L2 gathers for one warp — the critical path of the whole launch — where 64 entries are 16.
         // Graphs whose TYPICAL row is long (TextGCN-style word rows: median ~200 entries, reference build_graph.py PMI edges):
         // with the 512-entry threshold almost every row would be a "short" row walked serially by one lane group (a 2-lane
         // group for an 8-column operand).  A budget of 64 entries per segment turns them into warp-cooperative segments —

@@ -1697,7 +1697,10 @@ static int roles2_run_t(const tg_plan* pl, const StreamCall& c, const Epi& epi, 
     // lock-stepped sub-groups and one-float4 document slices pay more instructions per entry and row.
     // (narrow-slice hub role: ~3x the instructions per entry — thin (slot, chunk) runs walked in lock step; measured per role)
     const double hub_w = ((nsub > 1 ? 14.0 : 5.0) * (double)pl->hub_nnz + 4.0 * (double)a.groups * (double)pl->n_rows) / 0.82;
-    const double doc_w = (4.0 * (double)(pl->nnz - pl->hub_nnz - pl->n_rows) + 14.0 * (4.0 / nq) * (double)pl->n_rows) / 0.67;
+    double doc_w = (4.0 * (double)(pl->nnz - pl->hub_nnz - pl->n_rows) + 14.0 * (4.0 / nq) * (double)pl->n_rows) / 0.67;
+    // the row-wise loss epilogue (exp / log / shuffles on 8 lanes per row) more than doubles the document role's work on a
+    // class-sized operand (C4 shard, role-only runs: 2.46 ms against 1.08 ms on the same CTAs)
+    if (!std::is_same<Epi, EpiStore>::value) doc_w *= 2.4;
     split_sms(hub_w, doc_w, hslices * a.groups, dslices, a.n_chunks, (a.n_jobs + 4 / nq - 1) / (4 / nq), pl->r2_hub_pct, &a.hub_lanes,
               &a.doc_lanes);
     const size_t need = (size_t)a.hub_lanes * a.Kv * a.ldp * sizeof(float);

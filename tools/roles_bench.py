@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--scale", type=float, default=None)
     ap.add_argument("--configs", default="both;TG_ROLES_ONLY=1;TG_ROLES_ONLY=2")
+    ap.add_argument("--op", default="spmm", choices=["spmm", "loss"], help="plain product or the fused loss forward (class-sized --feat)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     g, hidden, n_class = graphgen.make_config(WORKLOADS[args.workload], device=dev, scale=args.scale)
@@ -42,13 +43,22 @@ def main():
         for F in [int(f) for f in args.feat.split(",")]:
             B = torch.randn(g.n, F, device=dev)
             Y = torch.empty(g.n, F, device=dev)
+            bias = torch.randn(F, device=dev)
+            row_label = ops.make_row_label(g.n, g.labels % F, g.train_idx)
+
+            def run():
+                if args.op == "spmm":
+                    ops.spmm(csr, B, None, out=Y)
+                else:
+                    ops.gc2_loss_forward(csr, B, bias, row_label, 1.0 / g.train_idx.numel(), want_logits=False, want_grad=True)
+
             for _ in range(2):
-                ops.spmm(csr, B, None, out=Y)
+                run()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(args.reps):
-                ops.spmm(csr, B, None, out=Y)
+                run()
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.reps
