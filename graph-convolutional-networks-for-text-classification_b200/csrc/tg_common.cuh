@@ -80,6 +80,7 @@ struct tg_plan {
     int32_t r2_min_rows = 16384, r2_narrow_min_rows = 131072, r2_hub_pct = -1, r2_narrow_hub_pct = -1, r2_only_role = 0;
     int32_t r2_narrow_lane = 1;
     bool r2_narrow_ok = true;
+    int32_t r2_hub_pf = -1;          // hub role: tiles prefetched into L2 ahead (chunks per lane); -1 = chosen at plan build
 };
 
 namespace tg {

@@ -79,6 +79,7 @@ struct R2Args {
     int64_t ldp;
     int32_t hub_slices, hub_lanes, doc_slices, doc_lanes, only_role;
     int32_t n_stages;    // document-role ring depth actually used (<= kStages)
+    int32_t hub_pf;      // hub role: chunks (per chunk lane) whose tiles are prefetched into L2 ahead; 0 = no prefetch
     const uint32_t* __restrict__ keep_bits;  // bit-packed dropout keep mask [n][n_feat/32] (bit b of word w = column 32w+b) or null
 };
 
@@ -159,14 +160,13 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
         if (tid == 0) {
             issue(0, c, __ldg(cdesc + c));
             if (c + a.hub_lanes < a.n_chunks) d_next = __ldg(cdesc + c + a.hub_lanes);
-            if (grp == 0) {
+            if (grp == 0 && a.hub_pf >= 2) {
                 // the tiles of the next steps: into L2 now, so that the TMA loads one step ahead see L2 latency, not HBM
                 // latency (the double buffer alone does not cover an HBM round trip when a stage is ~1 us of work); one
                 // slot group per chunk lane prefetches for all of them
-#pragma unroll
-                for (int i = 2; i < kHubL2PF; ++i)
+                for (int i = 2; i < a.hub_pf; ++i)
                     if (c + i * a.hub_lanes < a.n_chunks) prefetch(__ldg(cdesc + c + i * a.hub_lanes).z);
-                if (c + kHubL2PF * a.hub_lanes < a.n_chunks) d_pf = __ldg(cdesc + c + kHubL2PF * a.hub_lanes).z;
+                if (c + a.hub_pf * a.hub_lanes < a.n_chunks) d_pf = __ldg(cdesc + c + a.hub_pf * a.hub_lanes).z;
             }
         }
         for (int it = 0; c < a.n_chunks; c += a.hub_lanes, ++it) {
@@ -176,8 +176,8 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
                 issue(buf ^ 1, cn, d_next);
                 if (cn + a.hub_lanes < a.n_chunks) d_next = __ldg(cdesc + cn + a.hub_lanes);
             }
-            if (tid == 0 && grp == 0) {
-                const int cp = c + kHubL2PF * a.hub_lanes;
+            if (tid == 0 && grp == 0 && a.hub_pf >= 2) {
+                const int cp = c + a.hub_pf * a.hub_lanes;
                 if (cp < a.n_chunks) prefetch(d_pf);
                 if (cp + a.hub_lanes < a.n_chunks) d_pf = __ldg(cdesc + cp + a.hub_lanes).z;
             }
@@ -1264,6 +1264,7 @@ void read_knobs(tg_plan* pl) {
     pl->r2_only_role = env_int2("TG_ROLES_ONLY", 0);
     pl->r2_narrow_lane = env_int2("TG_ROLES2_NARROW_LANE", 1);
     pl->r2_narrow_ok = env_int2("TG_ROLES2_NARROW", 1) != 0;
+    pl->r2_hub_pf = env_int2("TG_ROLES2_HUB_PF", -1);
 }
 
 }  // namespace
@@ -1471,6 +1472,7 @@ int roles2_plan_build(tg_plan* pl, const int32_t* rowptr, const int32_t* colidx,
         pl->r2_cap_hub = cap;
         pl->r2_groups = G;
         pl->r2_gs = gs;
+        if (pl->r2_hub_pf < 0) pl->r2_hub_pf = kHubL2PF;
     }
     // the sort scratch is not needed any more: release it before the document side allocates
     cudaFree(keys_a); cudaFree(keys_b); cudaFree(src_a); cudaFree(src_b); cudaFree(tab_abs); cudaFree(tmp);
@@ -1651,6 +1653,7 @@ void fill_common(R2Args& a, const tg_plan* pl, const StreamCall& c) {
     a.keep_bits = nullptr;
     a.n_stages = pl->r2_stages;
     a.only_role = pl->r2_only_role;
+    a.hub_pf = pl->r2_hub_pf;
 }
 
 }  // namespace
@@ -1697,7 +1700,9 @@ static int roles2_run_t(const tg_plan* pl, const StreamCall& c, const Epi& epi, 
     // lock-stepped sub-groups and one-float4 document slices pay more instructions per entry and row.
     // (narrow-slice hub role: ~3x the instructions per entry — thin (slot, chunk) runs walked in lock step; measured per role)
     const double hub_w = ((nsub > 1 ? 14.0 : 5.0) * (double)pl->hub_nnz + 4.0 * (double)a.groups * (double)pl->n_rows) / 0.82;
-    double doc_w = (4.0 * (double)(pl->nnz - pl->hub_nnz - pl->n_rows) + 14.0 * (4.0 / nq) * (double)pl->n_rows) / 0.67;
+    // (document role, 128-column slices: 59 CTA-ms per 1 M documents in the role-only run of round 2 -> 0.715; narrower slices keep
+    // the figure their sweeps were made with)
+    double doc_w = (4.0 * (double)(pl->nnz - pl->hub_nnz - pl->n_rows) + 14.0 * (4.0 / nq) * (double)pl->n_rows) / (nq == 4 ? 0.715 : 0.67);
     // the row-wise loss epilogue (exp / log / shuffles on 8 lanes per row) more than doubles the document role's work on a
     // class-sized operand (C4 shard, role-only runs: 2.46 ms against 1.08 ms on the same CTAs)
     if (!std::is_same<Epi, EpiStore>::value) doc_w *= 2.4;
