@@ -428,6 +428,8 @@ def measure_workload(name: str, args, world: int, rank: int, dev, hook, steps: i
             with open(tpath) as fh:
                 tj = json.load(fh)
             traffic = tj.get(name)  # dram bytes per launch from the committed ncu --set full capture of this kernel
+            if not isinstance(traffic, (int, float)):
+                traffic = None
             traffic_src = "static: profiles/roofline_traffic.json (dram__bytes of a committed ncu --set full capture, not measured in this run)"
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name(csr, hidden),

@@ -176,9 +176,13 @@ _cache: dict = {}
 
 
 def _cache_key(t: torch.Tensor):
+    # identity + storage + version counters: an in-place edit of the values or indices (same storage) bumps `_version`, so the
+    # next call converts again instead of serving the stale CSR (torch.spmm would see the new values too)
     if t.layout == torch.sparse_coo:
-        return (id(t), t._values().data_ptr(), t._indices().data_ptr(), t._nnz(), tuple(t.shape))
-    return (id(t), t.values().data_ptr(), t.col_indices().data_ptr(), tuple(t.shape))
+        v, i = t._values(), t._indices()
+        return (id(t), v.data_ptr(), i.data_ptr(), v._version, i._version, t._nnz(), tuple(t.shape))
+    v, c = t.values(), t.col_indices()
+    return (id(t), v.data_ptr(), c.data_ptr(), v._version, c._version, tuple(t.shape))
 
 
 def cached_csr(t: torch.Tensor, **plan_kw) -> DeviceCSR:

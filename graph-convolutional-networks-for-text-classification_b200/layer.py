@@ -54,7 +54,7 @@ def _is_identity(x) -> bool:
         return False
     if x.shape[0] != x.shape[1] or x._nnz() != x.shape[0]:
         return False
-    key = (id(x), x._values().data_ptr(), x._nnz())
+    key = (id(x), x._values().data_ptr(), x._values()._version, x._indices()._version, x._nnz())
     hit = _identity_memo.get(key)
     if hit is None:
         idx, val = x._indices(), x._values()

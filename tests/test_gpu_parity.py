@@ -1030,3 +1030,16 @@ def test_hidden_backward_row_limit(tg, n, h, c, n_count):
         assert not dW2.cpu().numpy().any() and not db1.cpu().numpy().any()
     else:
         assert rel_err(dW2.cpu().numpy(), want_w) <= 2e-5 and rel_err(db1.cpu().numpy(), want_b) <= 2e-5
+
+
+def test_cached_csr_sees_in_place_edits(tg, small_golden):
+    """The per-tensor CSR cache keys on the version counters: scaling the adjacency values in place changes the next product."""
+    g = small_golden
+    n = int(g["n_docs"] + g["n_topics"])
+    adj = _sparse(g["adj_rows"], g["adj_cols"], g["adj_vals"], (n, n))
+    B = torch.randn(n, 8, device=dev())
+    y1 = tg.spmm(tg.cached_csr(adj), B)
+    assert tg.cached_csr(adj) is tg.cached_csr(adj)
+    adj._values().mul_(2.0)
+    y2 = tg.spmm(tg.cached_csr(adj), B)
+    assert float((y2 - 2.0 * y1).abs().max()) <= 1e-6 * float(y1.abs().max())
