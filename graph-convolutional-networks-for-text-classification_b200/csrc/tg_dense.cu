@@ -589,6 +589,270 @@ __global__ void __launch_bounds__(256, 2) hidden_bwd_dense_kernel(const float* _
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Tensor-core variant of the fused hidden-layer backward (c <= 24 classes, h <= 256 hidden units, 16-byte aligned rows).
+// The FFMA2 kernel above sits on the FMA pipe (10.2 G multiply-adds at C3, 0.66 ms); the two products of the backward
+// are contractions, so they move to the tensor cores with the same 3xTF32 split as the forward product
+// (hi*hi + hi*lo + lo*hi in fp32):
+//   P1  dH1^T [j x rows] = W2 [j x c] * dS2^T [c x rows]      (M = hidden units, N = 8 rows, K = classes in steps of 8)
+//   P2  dW2   [j x c]   += H1^T [j x rows] * dS2 [rows x c]   (M = hidden units, N = classes in tiles of 8, K = 8 rows)
+// A warp owns 16 hidden units (one m16 tile) and walks the rows in groups of 8; the sixteen warps of a CTA share the rows,
+// so the dS2 tile is staged (already split into hi / lo) once per CTA.  Index choices that make every H1 element travel
+// exactly once, as one 64-bit load per lane and row, and every dZ1 element leave as one 64-bit store:
+//   * m-slot g is hidden unit j0, m-slot g + 8 unit j0 + 1 with j0 = 16 warp + 2 g — a lane's two units are adjacent in
+//     memory (the m index only names rows of W2 / dW2, any bijection works);
+//   * k-slot t of P2 is row 2t of the group, slot t + 4 row 2t + 1 (k is a summation index) — P2's A fragment
+//     {(g,t),(g+8,t),(g,t+4),(g+8,t+4)} is then the SAME set of elements as P1's C fragment {(g,2t),(g,2t+1),(g+8,2t),
+//     (g+8,2t+1)}: the H1 values a lane loaded for the mask of its dH1 outputs are its operand of P2.
+// W2 hi / lo fragments live in registers for the whole kernel; dW2 accumulates in the MMA accumulators for one 64-row tile
+// and is then added to fp32 master registers with ordinary round-to-nearest adds (the tensor core's accumulation of a long
+// chain is not round-to-nearest).  Per-CTA partial dW2 / db1 go through sum_partials_kernel like the other variants:
+// deterministic.  Staged dS2 rows have a stride of 28 floats: both fragment patterns (row g, class t) and (row 2t, class g)
+// are then bank-conflict free.  Measured mma.sync rate on this part: 917 m16n8k8 TF32 MMAs per microsecond and SM
+// (tools/micro/mma_sync_rate.cu); the 36 M MMAs of the C3 shape are 0.27 ms of tensor pipe, the 2.1 GB 0.32 ms of HBM.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kHmThreads = 512;  // 16 warps x 16 hidden units
+constexpr int kHmTile = 64;      // rows per staged dS2 tile (8 groups of 8 rows)
+constexpr int kHmStride = 28;    // floats per staged dS2 row
+constexpr int kHmDepth = 8;      // 8-row groups of H1 a warp keeps in flight (= kHmTile / 8: ring slot = group of the tile)
+constexpr int kHmHStride = 20;   // floats per row of a warp's private H1 ring (16 units + pad: conflict-free 64-bit reads)
+constexpr size_t kHmSmem = (size_t)(4 * kHmTile * kHmStride + 2 * kHmTile * 24 + (kHmThreads / 32) * kHmDepth * 8 * kHmHStride) * sizeof(float);
+
+__device__ __forceinline__ void mma_tf32_nv(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    // not volatile: a pure function of its operands, the scheduler may interleave independent chains
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// hi / lo split in four integer / float instructions (cvt.rna.tf32.f32 compiles to a nine-instruction sequence and this kernel
+// is issue bound): hi = x rounded to 10 mantissa bits (add half an ulp to the bit pattern, clear the low 13 bits — ties
+// away from zero like cvt.rna; an operand at the very top of the fp32 range would carry into the exponent, H1 / dS2 never
+// are), lo = x - hi exactly, truncated to tf32 (|error| < 2^-21 |x|, the size of the dropped lo*lo term).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+}
+
+template <int KS>   // k8 steps over the classes = n8 tiles of dW2: ceil(c / 8)
+__global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const float* __restrict__ H1, int64_t ldh,
+                                                                       const float* __restrict__ dS2, int64_t ldd,
+                                                                       const float* __restrict__ W2, int64_t ldw, float scale,
+                                                                       float* __restrict__ dZ1, int64_t ldz,
+                                                                       float* __restrict__ partials, int64_t n, int h, int c,
+                                                                       int64_t rows_per_block, int64_t n_count) {
+    constexpr int CPK = 8 * KS;                                               // padded class count
+    constexpr int kStage = (kHmTile * CPK + kHmThreads - 1) / kHmThreads;     // dS2 elements a thread stages per tile
+    extern __shared__ __align__(16) float hm_smem[];
+    float (*Dhi)[kHmTile * kHmStride] = reinterpret_cast<float (*)[kHmTile * kHmStride]>(hm_smem);
+    float (*Dlo)[kHmTile * kHmStride] = reinterpret_cast<float (*)[kHmTile * kHmStride]>(hm_smem + 2 * kHmTile * kHmStride);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int j0 = 16 * warp + 2 * g;
+    // the warp's private H1 ring: kHmDepth groups x 8 rows x 16 units.  A group is one coalesced cp.async of 16 bytes per lane
+    // (lane l: row l / 4, units 4 (l % 4) ..), read back as (row 2t, units 2g, 2g + 1) after a __syncwarp
+    float* hs_w = hm_smem + 4 * kHmTile * kHmStride + 2 * kHmTile * 24 + warp * (kHmDepth * 8 * kHmHStride);
+    float* hs_cp = hs_w + (lane >> 2) * kHmHStride + 4 * (lane & 3);
+    const float* hs = hs_w + (2 * t) * kHmHStride + 2 * g;
+    float* draw = hm_smem + 4 * kHmTile * kHmStride;   // raw dS2 tiles [2][kHmTile * CPK]
+    const bool jok = j0 < h;                                  // h is a multiple of 4: units are inside or outside in fours
+    const bool cp_ok = 16 * warp + 4 * (lane & 3) < h;        // the four units this lane copies
+
+    // P1's A operand: W2 fragments  a0:(slot g, k t) a1:(slot g+8, k t) a2:(slot g, k t+4) a3:(slot g+8, k t+4)
+    uint32_t whi[KS][4], wlo[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = j0 + (e & 1), kk = 8 * ks + t + 4 * (e >> 1);
+            const float w = (jok && kk < c) ? __ldg(W2 + (int64_t)j * ldw + kk) : 0.f;
+            whi[ks][e] = to_tf32(w);
+            wlo[ks][e] = to_tf32(w - __uint_as_float(whi[ks][e]));
+        }
+    float gwm[KS][4];   // fp32 master copy of the lane's dW2 elements
+#pragma unroll
+    for (int nt = 0; nt < KS; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) gwm[nt][e] = 0.f;
+    float gb[2] = {0.f, 0.f};
+
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r_end = min(n, r_begin + rows_per_block);
+    const int n_tiles = (int)((r_end - r_begin + kHmTile - 1) / kHmTile);
+
+    // dS2 staging.  Tile 0: global -> registers -> hi / lo in shared memory.  Later tiles travel as raw fp32 with cp.async,
+    // issued two tiles ahead inside the commit group of an H1 group (a register prefetch ended up next to its consumer and
+    // exposed a full DRAM latency per tile); every thread splits the elements it copied itself at the end of the tile
+    // before their use, so the hand-over needs no barrier of its own.
+    auto stage_tile0 = [&]() {
+#pragma unroll
+        for (int i = 0; i < kStage; ++i) {
+            const int idx = threadIdx.x + kHmThreads * i;
+            if (idx < kHmTile * CPK) {
+                const int rr = idx / CPK, q = idx % CPK;
+                const bool ok = r_begin + rr < r_end && q < c;
+                const float v = ok ? __ldg(dS2 + (r_begin + rr) * ldd + q) : 0.f;
+                uint32_t hi, lo;
+                split_tf32(v, hi, lo);
+                Dhi[0][rr * kHmStride + q] = __uint_as_float(hi);
+                Dlo[0][rr * kHmStride + q] = __uint_as_float(lo);
+            }
+        }
+    };
+    auto stage_issue = [&](int tile) {   // raw tile -> draw[tile & 1]  (zero-filled past the range / the class count)
+        const int64_t r0 = r_begin + (int64_t)tile * kHmTile;
+#pragma unroll
+        for (int i = 0; i < kStage; ++i) {
+            const int idx = threadIdx.x + kHmThreads * i;
+            if (idx < kHmTile * CPK) {
+                const int rr = idx / CPK, q = idx % CPK;
+                const bool ok = r0 + rr < r_end && q < c;
+                hb_cp4(draw + (tile & 1) * (kHmTile * CPK) + idx, ok ? dS2 + (r0 + rr) * ldd + q : dS2, ok);
+            }
+        }
+    };
+    auto stage_split = [&](int tile) {   // draw[tile & 1] -> hi / lo [tile & 1]
+#pragma unroll
+        for (int i = 0; i < kStage; ++i) {
+            const int idx = threadIdx.x + kHmThreads * i;
+            if (idx < kHmTile * CPK) {
+                const int rr = idx / CPK, q = idx % CPK;
+                uint32_t hi, lo;
+                split_tf32(draw[(tile & 1) * (kHmTile * CPK) + idx], hi, lo);
+                Dhi[tile & 1][rr * kHmStride + q] = __uint_as_float(hi);
+                Dlo[tile & 1][rr * kHmStride + q] = __uint_as_float(lo);
+            }
+        }
+    };
+    stage_tile0();
+    stage_issue(1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // H1 ring: the next kHmDepth groups travel global -> shared memory asynchronously (a register ring left the distance
+    // between a load and its use to the instruction scheduler, which under the 128-register cap moved the loads next to
+    // their consumers: ncu showed 40 % of the samples on long-scoreboard stalls)
+    const float* hp = H1 + (r_begin + (lane >> 2)) * ldh + 16 * warp + 4 * (lane & 3);   // this lane's piece of the next group
+    int64_t hrow = r_begin + (lane >> 2);
+    float* zp = dZ1 + (r_begin + 2 * t) * ldz + j0;         // row 2t of the next group to store
+    const int64_t ldh8 = 8 * ldh, ldz8 = 8 * ldz;
+    auto load_group = [&](int slot, auto full_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;
+        if (cp_ok) hb_cp16(hs_cp + slot * (8 * kHmHStride), hp, kFull || hrow < r_end);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        hp += ldh8;
+        hrow += 8;
+    };
+#pragma unroll
+    for (int d = 0; d < kHmDepth; ++d) load_group(d, std::false_type{});
+    __syncthreads();
+
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        const int buf = tile & 1;
+        stage_issue(tile + 2);   // joins the commit group of this tile's first H1 refill: landed by the next tile's first wait
+        const int64_t r0 = r_begin + (int64_t)tile * kHmTile;
+        float gw[KS][4];
+#pragma unroll
+        for (int nt = 0; nt < KS; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gw[nt][e] = 0.f;
+        const float* dhi = Dhi[buf];
+        const float* dlo = Dlo[buf];
+        auto run_tile = [&](auto full_tag) {
+            constexpr bool kFull = decltype(full_tag)::value;
+#pragma unroll
+            for (int grp = 0; grp < kHmTile / 8; ++grp) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(kHmDepth - 1) : "memory");   // this group has landed
+                __syncwarp();
+                float2 xa = make_float2(0.f, 0.f), xb = xa;
+                if (jok) {
+                    xa = *reinterpret_cast<const float2*>(hs + grp * (8 * kHmHStride));
+                    xb = *reinterpret_cast<const float2*>(hs + grp * (8 * kHmHStride) + kHmHStride);
+                }
+                __syncwarp();                // every lane has read the slot ...
+                load_group(grp, full_tag);   // ... before it is refilled with the group kHmDepth ahead
+                // ---- P1: pre-activation gradient of the lane's 2 units x 2 rows
+                float dh[4] = {0.f, 0.f, 0.f, 0.f}, dhs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int o = (8 * grp + g) * kHmStride + 8 * ks + t;
+                    const uint32_t bhi[2] = {__float_as_uint(dhi[o]), __float_as_uint(dhi[o + 4])};
+                    const uint32_t blo[2] = {__float_as_uint(dlo[o]), __float_as_uint(dlo[o + 4])};
+                    mma_tf32_nv(dhs, wlo[ks], bhi);   // small terms in their own chain
+                    mma_tf32_nv(dhs, whi[ks], blo);
+                    mma_tf32_nv(dh, whi[ks], bhi);
+                }
+                // c0:(unit j0, row 2t) c1:(j0, row 2t+1) c2:(j0+1, row 2t) c3:(j0+1, row 2t+1)
+                const float za0 = (xa.x > 0.f) ? (dh[0] + dhs[0]) * scale : 0.f;
+                const float zb0 = (xb.x > 0.f) ? (dh[1] + dhs[1]) * scale : 0.f;
+                const float za1 = (xa.y > 0.f) ? (dh[2] + dhs[2]) * scale : 0.f;
+                const float zb1 = (xb.y > 0.f) ? (dh[3] + dhs[3]) * scale : 0.f;
+                float v[4] = {xa.x, xa.y, xb.x, xb.y};   // P2's A fragment order: (j0, 2t) (j0+1, 2t) (j0, 2t+1) (j0+1, 2t+1)
+                if (kFull) {
+                    if (jok) {
+                        *reinterpret_cast<float2*>(zp) = make_float2(za0, za1);
+                        *reinterpret_cast<float2*>(zp + ldz) = make_float2(zb0, zb1);
+                    }
+                    gb[0] += za0 + zb0;
+                    gb[1] += za1 + zb1;
+                } else {
+                    const int64_t row0 = r0 + 8 * grp + 2 * t;
+                    if (jok && row0 < r_end) *reinterpret_cast<float2*>(zp) = make_float2(za0, za1);
+                    if (jok && row0 + 1 < r_end) *reinterpret_cast<float2*>(zp + ldz) = make_float2(zb0, zb1);
+                    const bool cnt_a = row0 < n_count && row0 < r_end, cnt_b = row0 + 1 < n_count && row0 + 1 < r_end;
+                    gb[0] += (cnt_a ? za0 : 0.f) + (cnt_b ? zb0 : 0.f);
+                    gb[1] += (cnt_a ? za1 : 0.f) + (cnt_b ? zb1 : 0.f);
+                    if (!cnt_a) v[0] = v[1] = 0.f;
+                    if (!cnt_b) v[2] = v[3] = 0.f;
+                }
+                zp += ldz8;
+                // ---- P2: dW2 += H1^T dS2 over the group's 8 rows
+                uint32_t ahi[4], alo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_tf32(v[e], ahi[e], alo[e]);
+#pragma unroll
+                for (int nt = 0; nt < KS; ++nt) {
+                    const int o = (8 * grp + 2 * t) * kHmStride + 8 * nt + g;
+                    const uint32_t bhi[2] = {__float_as_uint(dhi[o]), __float_as_uint(dhi[o + kHmStride])};
+                    const uint32_t blo[2] = {__float_as_uint(dlo[o]), __float_as_uint(dlo[o + kHmStride])};
+                    mma_tf32_nv(gw[nt], alo, bhi);
+                    mma_tf32_nv(gw[nt], ahi, blo);
+                    mma_tf32_nv(gw[nt], ahi, bhi);
+                }
+            }
+        };
+        // every row of this tile and of the look-ahead groups is inside the block's range and counted: no per-row tests
+        if (r0 + kHmTile + 8 * kHmDepth <= r_end && r0 + kHmTile <= n_count) run_tile(std::true_type{});
+        else run_tile(std::false_type{});
+#pragma unroll
+        for (int nt = 0; nt < KS; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gwm[nt][e] += gw[nt][e];
+        if (tile + 1 < n_tiles) stage_split(tile + 1);   // (the last readers of that hi / lo buffer passed the previous barrier)
+        __syncthreads();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // dW2 fragment  c0:(unit j0, class 8nt+2t) c1:(j0, 8nt+2t+1) c2:(unit j0+1, 8nt+2t) c3:(j0+1, 8nt+2t+1)
+    float* out = partials + (int64_t)blockIdx.x * h * (c + 1);
+    if (jok) {
+#pragma unroll
+        for (int nt = 0; nt < KS; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + (e >> 1), q = 8 * nt + 2 * t + (e & 1);
+                if (q < c) out[(int64_t)j * c + q] = gwm[nt][e];
+            }
+    }
+    // db1: the four lanes of a quad hold different rows of the same units
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        gb[u] += __shfl_xor_sync(0xffffffffu, gb[u], 1);
+        gb[u] += __shfl_xor_sync(0xffffffffu, gb[u], 2);
+    }
+    if (jok && t == 0) {
+        out[(int64_t)h * c + j0] = gb[0];
+        out[(int64_t)h * c + j0 + 1] = gb[1];
+    }
+}
+
 // Fixed-order sum of per-block partial rows.  Eight lanes per element take the blocks b = l, l + 8, ... (each in
 // ascending order, four loads in flight) and their eight sums meet in a fixed shuffle tree: deterministic, and the
 // latency of a serial walk over hundreds of L2-resident rows no longer sits on the step's critical path.
@@ -617,8 +881,46 @@ __global__ void sum_partials_kernel(const float* __restrict__ partials, int64_t 
 }
 
 static bool dense_hidden_enabled() {
-    const char* v = getenv("TG_HIDDEN_DENSE");
-    return !(v && *v) || atoi(v) != 0;
+    static const bool on = [] {
+        const char* v = getenv("TG_HIDDEN_DENSE");
+        return !(v && *v) || atoi(v) != 0;
+    }();
+    return on;
+}
+static bool mma_hidden_enabled() {   // TG_HIDDEN_MMA=0 selects the CUDA-core kernels (read once)
+    static const bool on = [] {
+        const char* v = getenv("TG_HIDDEN_MMA");
+        return !(v && *v) || atoi(v) != 0;
+    }();
+    return on;
+}
+
+// tensor-core kernel: one CTA of sixteen warps per SM, every CTA a contiguous range of rows (a multiple of the 64-row tile)
+static int launch_hidden_bwd_mma(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw,
+                                 float scale, float* dZ1, int64_t ldz, float* dW2, float* db1, float* partials, int64_t n,
+                                 int h, int c, int64_t n_count, cudaStream_t st) {
+    int64_t grid = kNumSM;
+    int64_t rpb = ceil_div64(n > 0 ? n : 1, grid);
+    rpb = ceil_div64(rpb, kHmTile) * kHmTile;
+    grid = ceil_div64(n > 0 ? n : 1, rpb);
+    const int threads = kHmThreads;   // warps past the hidden width only help staging dS2
+    static const int attr_rc = [] {
+        int rc = (int)cudaFuncSetAttribute(hidden_bwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHmSmem);
+        rc |= (int)cudaFuncSetAttribute(hidden_bwd_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHmSmem);
+        rc |= (int)cudaFuncSetAttribute(hidden_bwd_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHmSmem);
+        return rc;
+    }();
+    TG_REQUIRE(attr_rc == 0, TG_ERR_CUDA, "cudaFuncSetAttribute failed for the hidden-layer backward");
+    switch ((c + 7) / 8) {
+        case 1: hidden_bwd_mma_kernel<1><<<(unsigned)grid, threads, kHmSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count); break;
+        case 2: hidden_bwd_mma_kernel<2><<<(unsigned)grid, threads, kHmSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count); break;
+        default: hidden_bwd_mma_kernel<3><<<(unsigned)grid, threads, kHmSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count); break;
+    }
+    TG_LAUNCH_CHECK();
+    const int64_t n_elem = (int64_t)h * (c + 1);
+    sum_partials_kernel<<<(unsigned)ceil_div64(n_elem * 8, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1, c, c);
+    TG_LAUNCH_CHECK();
+    return TG_OK;
 }
 
 template <int NC4>
@@ -894,6 +1196,12 @@ int tg_hidden_bwd_rows_f32(const float* H1, int64_t ldh, const float* dS2, int64
     TG_REQUIRE(n_count >= 0 && n_count <= n, TG_ERR_INVALID_ARG, "n_count must be in [0, n]");
     cudaStream_t st = as_stream(stream);
     if (c > 32 || h > 1024) return hidden_bwd_blocked(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
+    {
+        const bool aligned = (ldh % 4 == 0) && (ldz % 2 == 0) && (h % 4 == 0) &&
+                             ((reinterpret_cast<uintptr_t>(H1) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(dZ1) & 7u) == 0);
+        if (c <= 24 && h <= 256 && aligned && mma_hidden_enabled())
+            return launch_hidden_bwd_mma(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
+    }
     const int nc4 = (c + 3) / 4;
     switch (nc4) {
         case 1: return launch_hidden_bwd<1>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
