@@ -612,9 +612,9 @@ __global__ void __launch_bounds__(256, 2) hidden_bwd_dense_kernel(const float* _
 // (tools/micro/mma_sync_rate.cu); the 36 M MMAs of the C3 shape are 0.27 ms of tensor pipe, the 2.1 GB 0.32 ms of HBM.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kHmThreads = 512;  // 16 warps x 16 hidden units
-constexpr int kHmTile = 64;      // rows per staged dS2 tile (8 groups of 8 rows)
+constexpr int kHmTile = 128;     // rows per staged dS2 tile (two runs of 8 groups of 8 rows): one CTA barrier per tile
 constexpr int kHmStride = 28;    // floats per staged dS2 row
-constexpr int kHmDepth = 8;      // 8-row groups of H1 a warp keeps in flight (= kHmTile / 8: ring slot = group of the tile)
+constexpr int kHmDepth = 8;      // 8-row groups of H1 a warp keeps in flight (ring slot = group of the 64-row run)
 constexpr int kHmHStride = 20;   // floats per row of a warp's private H1 ring (16 units + pad: conflict-free 64-bit reads)
 constexpr size_t kHmSmem = (size_t)(4 * kHmTile * kHmStride + 2 * kHmTile * 24 + (kHmThreads / 32) * kHmDepth * 8 * kHmHStride) * sizeof(float);
 
@@ -754,12 +754,16 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
         for (int nt = 0; nt < KS; ++nt)
 #pragma unroll
             for (int e = 0; e < 4; ++e) gw[nt][e] = 0.f;
-        const float* dhi = Dhi[buf];
-        const float* dlo = Dlo[buf];
+        const float* dhi_t = Dhi[buf];
+        const float* dlo_t = Dlo[buf];
         auto run_tile = [&](auto full_tag) {
             constexpr bool kFull = decltype(full_tag)::value;
+#pragma unroll 1
+            for (int run = 0; run < kHmTile / 64; ++run) {
+            const float* dhi = dhi_t + run * (64 * kHmStride);
+            const float* dlo = dlo_t + run * (64 * kHmStride);
 #pragma unroll
-            for (int grp = 0; grp < kHmTile / 8; ++grp) {
+            for (int grp = 0; grp < kHmDepth; ++grp) {
                 asm volatile("cp.async.wait_group %0;" ::"n"(kHmDepth - 1) : "memory");   // this group has landed
                 __syncwarp();
                 float2 xa = make_float2(0.f, 0.f), xb = xa;
@@ -794,7 +798,7 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
                     gb[0] += za0 + zb0;
                     gb[1] += za1 + zb1;
                 } else {
-                    const int64_t row0 = r0 + 8 * grp + 2 * t;
+                    const int64_t row0 = r0 + 64 * run + 8 * grp + 2 * t;
                     if (jok && row0 < r_end) *reinterpret_cast<float2*>(zp) = make_float2(za0, za1);
                     if (jok && row0 + 1 < r_end) *reinterpret_cast<float2*>(zp + ldz) = make_float2(zb0, zb1);
                     const bool cnt_a = row0 < n_count && row0 < r_end, cnt_b = row0 + 1 < n_count && row0 + 1 < r_end;
@@ -817,6 +821,7 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
                     mma_tf32_nv(gw[nt], ahi, blo);
                     mma_tf32_nv(gw[nt], ahi, bhi);
                 }
+            }
             }
         };
         // every row of this tile and of the look-ahead groups is inside the block's range and counted: no per-row tests
