@@ -641,7 +641,6 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
                                                                        float* __restrict__ partials, int64_t n, int h, int c,
                                                                        int64_t rows_per_block, int64_t n_count) {
     constexpr int CPK = 8 * KS;                                               // padded class count
-    constexpr int kStage = (kHmTile * CPK + kHmThreads - 1) / kHmThreads;     // dS2 elements a thread stages per tile
     extern __shared__ __align__(16) float hm_smem[];
     float (*Dhi)[kHmTile * kHmStride] = reinterpret_cast<float (*)[kHmTile * kHmStride]>(hm_smem);
     float (*Dlo)[kHmTile * kHmStride] = reinterpret_cast<float (*)[kHmTile * kHmStride]>(hm_smem + 2 * kHmTile * kHmStride);
@@ -675,51 +674,61 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
         for (int e = 0; e < 4; ++e) gwm[nt][e] = 0.f;
     float gb[2] = {0.f, 0.f};
 
+    // everything below is relative to the block's first row, in 32-bit arithmetic (the launcher checks that a block's rows
+    // times the leading dimensions fit): 64-bit row bookkeeping cost enough registers to spill under the 128-register cap,
+    // and the reloads showed up as 14 % long-scoreboard stalls
     const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
-    const int64_t r_end = min(n, r_begin + rows_per_block);
-    const int n_tiles = (int)((r_end - r_begin + kHmTile - 1) / kHmTile);
+    const int nrows = (int)(min(n, r_begin + rows_per_block) - r_begin);                       // rows of this block
+    const int ncnt = (int)max((int64_t)0, min(n_count - r_begin, (int64_t)nrows));             // ... that count into dW2 / db1
+    const int n_tiles = (nrows + kHmTile - 1) / kHmTile;
+    const float* __restrict__ H1b = H1 + r_begin * ldh;
+    const float* __restrict__ dSb = dS2 + r_begin * ldd;
+    float* __restrict__ dZb = dZ1 + r_begin * ldz;
+    const int ldh_i = (int)ldh, ldz_i = (int)ldz, ldd_i = (int)ldd;
 
     // dS2 staging.  Tile 0: global -> registers -> hi / lo in shared memory.  Later tiles travel as raw fp32 with cp.async,
     // issued two tiles ahead inside the commit group of an H1 group (a register prefetch ended up next to its consumer and
     // exposed a full DRAM latency per tile); every thread splits the elements it copied itself at the end of the tile
-    // before their use, so the hand-over needs no barrier of its own.
+    // before their use, so the hand-over needs no barrier of its own.  Thread -> (class q = tid % 32, rows tid / 32 + 16 i).
+    constexpr int kSRows = kHmThreads / 32;          // rows one pass of the CTA covers
+    constexpr int kSPass = kHmTile / kSRows;         // passes per tile
+    const int sq = threadIdx.x & 31, sr = threadIdx.x >> 5;
+    const bool s_act = sq < CPK;
     auto stage_tile0 = [&]() {
+        if (s_act) {
 #pragma unroll
-        for (int i = 0; i < kStage; ++i) {
-            const int idx = threadIdx.x + kHmThreads * i;
-            if (idx < kHmTile * CPK) {
-                const int rr = idx / CPK, q = idx % CPK;
-                const bool ok = r_begin + rr < r_end && q < c;
-                const float v = ok ? __ldg(dS2 + (r_begin + rr) * ldd + q) : 0.f;
+            for (int i = 0; i < kSPass; ++i) {
+                const int rr = sr + kSRows * i;
+                const float v = (rr < nrows && sq < c) ? __ldg(dSb + rr * ldd_i + sq) : 0.f;
                 uint32_t hi, lo;
                 split_tf32(v, hi, lo);
-                Dhi[0][rr * kHmStride + q] = __uint_as_float(hi);
-                Dlo[0][rr * kHmStride + q] = __uint_as_float(lo);
+                Dhi[0][rr * kHmStride + sq] = __uint_as_float(hi);
+                Dlo[0][rr * kHmStride + sq] = __uint_as_float(lo);
             }
         }
     };
     auto stage_issue = [&](int tile) {   // raw tile -> draw[tile & 1]  (zero-filled past the range / the class count)
-        const int64_t r0 = r_begin + (int64_t)tile * kHmTile;
+        if (s_act) {
+            float* dst = draw + (tile & 1) * (kHmTile * CPK) + sr * CPK + sq;
+            const int row0 = tile * kHmTile + sr;
 #pragma unroll
-        for (int i = 0; i < kStage; ++i) {
-            const int idx = threadIdx.x + kHmThreads * i;
-            if (idx < kHmTile * CPK) {
-                const int rr = idx / CPK, q = idx % CPK;
-                const bool ok = r0 + rr < r_end && q < c;
-                hb_cp4(draw + (tile & 1) * (kHmTile * CPK) + idx, ok ? dS2 + (r0 + rr) * ldd + q : dS2, ok);
+            for (int i = 0; i < kSPass; ++i) {
+                const bool ok = row0 + kSRows * i < nrows && sq < c;
+                hb_cp4(dst + kSRows * i * CPK, ok ? dSb + (row0 + kSRows * i) * ldd_i + sq : dSb, ok);
             }
         }
     };
     auto stage_split = [&](int tile) {   // draw[tile & 1] -> hi / lo [tile & 1]
+        if (s_act) {
+            const float* src = draw + (tile & 1) * (kHmTile * CPK) + sr * CPK + sq;
+            float* ohi = Dhi[tile & 1] + sr * kHmStride + sq;
+            float* olo = Dlo[tile & 1] + sr * kHmStride + sq;
 #pragma unroll
-        for (int i = 0; i < kStage; ++i) {
-            const int idx = threadIdx.x + kHmThreads * i;
-            if (idx < kHmTile * CPK) {
-                const int rr = idx / CPK, q = idx % CPK;
+            for (int i = 0; i < kSPass; ++i) {
                 uint32_t hi, lo;
-                split_tf32(draw[(tile & 1) * (kHmTile * CPK) + idx], hi, lo);
-                Dhi[tile & 1][rr * kHmStride + q] = __uint_as_float(hi);
-                Dlo[tile & 1][rr * kHmStride + q] = __uint_as_float(lo);
+                split_tf32(src[kSRows * i * CPK], hi, lo);
+                ohi[kSRows * i * kHmStride] = __uint_as_float(hi);
+                olo[kSRows * i * kHmStride] = __uint_as_float(lo);
             }
         }
     };
@@ -730,15 +739,14 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
     // H1 ring: the next kHmDepth groups travel global -> shared memory asynchronously (a register ring left the distance
     // between a load and its use to the instruction scheduler, which under the 128-register cap moved the loads next to
     // their consumers: ncu showed 40 % of the samples on long-scoreboard stalls)
-    const float* hp = H1 + (r_begin + (lane >> 2)) * ldh + 16 * warp + 4 * (lane & 3);   // this lane's piece of the next group
-    int64_t hrow = r_begin + (lane >> 2);
-    float* zp = dZ1 + (r_begin + 2 * t) * ldz + j0;         // row 2t of the next group to store
-    const int64_t ldh8 = 8 * ldh, ldz8 = 8 * ldz;
+    int hoff = (lane >> 2) * ldh_i + 16 * warp + 4 * (lane & 3);   // this lane's piece of the next group to load
+    int hrow = lane >> 2;
+    int zoff = (2 * t) * ldz_i + j0;                               // row 2t of the next group to store
     auto load_group = [&](int slot, auto full_tag) {
         constexpr bool kFull = decltype(full_tag)::value;
-        if (cp_ok) hb_cp16(hs_cp + slot * (8 * kHmHStride), hp, kFull || hrow < r_end);
+        if (cp_ok) hb_cp16(hs_cp + slot * (8 * kHmHStride), H1b + hoff, kFull || hrow < nrows);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        hp += ldh8;
+        hoff += 8 * ldh_i;
         hrow += 8;
     };
 #pragma unroll
@@ -748,7 +756,7 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
     for (int tile = 0; tile < n_tiles; ++tile) {
         const int buf = tile & 1;
         stage_issue(tile + 2);   // joins the commit group of this tile's first H1 refill: landed by the next tile's first wait
-        const int64_t r0 = r_begin + (int64_t)tile * kHmTile;
+        const int r0 = tile * kHmTile;
         float gw[KS][4];
 #pragma unroll
         for (int nt = 0; nt < KS; ++nt)
@@ -790,24 +798,25 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
                 const float za1 = (xa.y > 0.f) ? (dh[2] + dhs[2]) * scale : 0.f;
                 const float zb1 = (xb.y > 0.f) ? (dh[3] + dhs[3]) * scale : 0.f;
                 float v[4] = {xa.x, xa.y, xb.x, xb.y};   // P2's A fragment order: (j0, 2t) (j0+1, 2t) (j0, 2t+1) (j0+1, 2t+1)
+                float* zp = dZb + zoff;
                 if (kFull) {
                     if (jok) {
                         *reinterpret_cast<float2*>(zp) = make_float2(za0, za1);
-                        *reinterpret_cast<float2*>(zp + ldz) = make_float2(zb0, zb1);
+                        *reinterpret_cast<float2*>(zp + ldz_i) = make_float2(zb0, zb1);
                     }
                     gb[0] += za0 + zb0;
                     gb[1] += za1 + zb1;
                 } else {
-                    const int64_t row0 = r0 + 64 * run + 8 * grp + 2 * t;
-                    if (jok && row0 < r_end) *reinterpret_cast<float2*>(zp) = make_float2(za0, za1);
-                    if (jok && row0 + 1 < r_end) *reinterpret_cast<float2*>(zp + ldz) = make_float2(zb0, zb1);
-                    const bool cnt_a = row0 < n_count && row0 < r_end, cnt_b = row0 + 1 < n_count && row0 + 1 < r_end;
+                    const int row0 = r0 + 64 * run + 8 * grp + 2 * t;
+                    if (jok && row0 < nrows) *reinterpret_cast<float2*>(zp) = make_float2(za0, za1);
+                    if (jok && row0 + 1 < nrows) *reinterpret_cast<float2*>(zp + ldz_i) = make_float2(zb0, zb1);
+                    const bool cnt_a = row0 < ncnt, cnt_b = row0 + 1 < ncnt;
                     gb[0] += (cnt_a ? za0 : 0.f) + (cnt_b ? zb0 : 0.f);
                     gb[1] += (cnt_a ? za1 : 0.f) + (cnt_b ? zb1 : 0.f);
                     if (!cnt_a) v[0] = v[1] = 0.f;
                     if (!cnt_b) v[2] = v[3] = 0.f;
                 }
-                zp += ldz8;
+                zoff += 8 * ldz_i;
                 // ---- P2: dW2 += H1^T dS2 over the group's 8 rows
                 uint32_t ahi[4], alo[4];
 #pragma unroll
@@ -825,7 +834,7 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
             }
         };
         // every row of this tile and of the look-ahead groups is inside the block's range and counted: no per-row tests
-        if (r0 + kHmTile + 8 * kHmDepth <= r_end && r0 + kHmTile <= n_count) run_tile(std::true_type{});
+        if (r0 + kHmTile + 8 * kHmDepth <= nrows && r0 + kHmTile <= ncnt) run_tile(std::true_type{});
         else run_tile(std::false_type{});
 #pragma unroll
         for (int nt = 0; nt < KS; ++nt)
@@ -1204,7 +1213,9 @@ int tg_hidden_bwd_rows_f32(const float* H1, int64_t ldh, const float* dS2, int64
     {
         const bool aligned = (ldh % 4 == 0) && (ldz % 2 == 0) && (h % 4 == 0) &&
                              ((reinterpret_cast<uintptr_t>(H1) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(dZ1) & 7u) == 0);
-        if (c <= 24 && h <= 256 && aligned && mma_hidden_enabled())
+        const int64_t blk_rows = ceil_div64(n > 0 ? n : 1, kNumSM) + kHmTile;   // (32-bit offsets inside a block of rows)
+        const bool fits = blk_rows * ldh < (int64_t)1 << 30 && blk_rows * ldz < (int64_t)1 << 30 && blk_rows * ldd < (int64_t)1 << 30;
+        if (c <= 24 && h <= 256 && aligned && fits && mma_hidden_enabled())
             return launch_hidden_bwd_mma(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, dW2, db1, partials, n, h, c, n_count, st);
     }
     const int nc4 = (c + 3) / 4;
