@@ -1012,7 +1012,8 @@ def test_dropout_p_one_drops_everything(tg, small_golden):
     assert float(model.gc1.weight.grad.abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("n,h,c,n_count", [(5000, 256, 20, 4700), (3000, 300, 8, 0), (2000, 200, 52, 1999)])
+@pytest.mark.parametrize("n,h,c,n_count", [(5000, 256, 20, 4700), (3000, 300, 8, 0), (2000, 200, 52, 1999), (4000, 200, 20, 0),
+                                           (130, 64, 5, 77), (9000, 256, 24, 8999), (20000, 256, 20, 19744)])
 def test_hidden_backward_row_limit(tg, n, h, c, n_count):
     """tg_hidden_bwd_rows_f32: rows >= n_count get their dZ1 but stay out of dW2 / db1 (replicated rows of a sharded graph)."""
     from topicgcn_b200 import ops
@@ -1030,6 +1031,34 @@ def test_hidden_backward_row_limit(tg, n, h, c, n_count):
         assert not dW2.cpu().numpy().any() and not db1.cpu().numpy().any()
     else:
         assert rel_err(dW2.cpu().numpy(), want_w) <= 2e-5 and rel_err(db1.cpu().numpy(), want_b) <= 2e-5
+
+
+@pytest.mark.parametrize("n,h,c", [(3000, 256, 20), (1111, 200, 20), (640, 128, 8), (2500, 202, 20)])
+def test_hidden_backward_strided_operands(tg, n, h, c):
+    """The tensor-core kernel (hidden_bwd_mma_kernel: c <= 24, h <= 256, h % 4 == 0, 16-byte aligned rows) on operands that are
+    column blocks of wider matrices (leading dimension > width), written into a strided dZ1; h = 202 is not a multiple of 4 and
+    takes the CUDA-core kernel — same results either way.  Bitwise reproducible."""
+    from topicgcn_b200 import ops
+    rng = np.random.default_rng(n * 7 + h)
+    pad = 4 * ((h + 3) // 4)
+    H1w = np.maximum(rng.normal(size=(n, pad + 8)), 0).astype(np.float32) * (rng.random(size=(n, pad + 8)) < 0.5)
+    dS2w = rng.normal(size=(n, c + 5)).astype(np.float32)
+    W2w = rng.normal(size=(h, c + 3)).astype(np.float32)
+    H1d, dS2d, W2d = torch.tensor(H1w, device=dev()), torch.tensor(dS2w, device=dev()), torch.tensor(W2w, device=dev())
+    H1v, dS2v, W2v = H1d[:, 4:4 + h], dS2d[:, 1:1 + c], W2d[:, 2:2 + c]
+    outw = torch.full((n, pad + 12), 7.0, device=dev())
+    out = outw[:, 4:4 + h]
+    dZ1, dW2, db1 = ops.hidden_backward(H1v, dS2v, W2v, 1.5, out_dZ1=out)
+    H1, dS2, W2 = H1w[:, 4:4 + h], dS2w[:, 1:1 + c], W2w[:, 2:2 + c]
+    dZ1_ref = np.where(H1 > 0, (dS2.astype(np.float64) @ W2.astype(np.float64).T) * 1.5, 0.0)
+    assert dZ1.data_ptr() == out.data_ptr()
+    assert rel_err(out.cpu().numpy(), dZ1_ref) <= 1e-5
+    assert rel_err(dW2.cpu().numpy(), H1.astype(np.float64).T @ dS2.astype(np.float64)) <= 2e-5
+    assert rel_err(db1.cpu().numpy(), dZ1_ref.sum(axis=0)) <= 2e-5
+    keep = outw.cpu().numpy()
+    assert (keep[:, :4] == 7.0).all() and (keep[:, 4 + h:] == 7.0).all()       # nothing written outside the block
+    dZ1b, dW2b, db1b = ops.hidden_backward(H1v, dS2v, W2v, 1.5)
+    assert torch.equal(dW2, dW2b) and torch.equal(db1, db1b) and torch.equal(dZ1b, out)
 
 
 def test_cached_csr_sees_in_place_edits(tg, small_golden):
