@@ -138,6 +138,15 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// hi / lo split in four integer / float instructions (cvt.rna.tf32.f32 compiles to a nine-instruction sequence and this kernel
+// is issue bound): hi = x rounded to 10 mantissa bits (add half an ulp to the bit pattern, clear the low 13 bits — ties
+// away from zero like cvt.rna; an operand at the very top of the fp32 range would carry into the exponent, H1 / dS2 never
+// are), lo = x - hi exactly, truncated to tf32 (|error| < 2^-21 |x|, the size of the dropped lo*lo term).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+}
+
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -221,10 +230,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) dense_nn_mma_kernel(const floa
                 const float x[4] = {sstep ? lo_row.z : lo_row.x, sstep ? hi_row.z : hi_row.x,
                                     sstep ? lo_row.w : lo_row.y, sstep ? hi_row.w : hi_row.y};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    ahi[m][e] = to_tf32(x[e]);
-                    alo[m][e] = to_tf32(x[e] - __uint_as_float(ahi[m][e]));
-                }
+                for (int e = 0; e < 4; ++e) split_tf32(x[e], ahi[m][e], alo[m][e]);   // four integer / float instructions per element
             }
             const int kb = k16 + 4 * t + 2 * sstep;  // actual k of slot t; slot t+4 is kb + 1
 #pragma unroll
@@ -624,15 +630,6 @@ __device__ __forceinline__ void mma_tf32_nv(float (&d)[4], const uint32_t (&a)[4
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-// hi / lo split in four integer / float instructions (cvt.rna.tf32.f32 compiles to a nine-instruction sequence and this kernel
-// is issue bound): hi = x rounded to 10 mantissa bits (add half an ulp to the bit pattern, clear the low 13 bits — ties
-// away from zero like cvt.rna; an operand at the very top of the fp32 range would carry into the exponent, H1 / dS2 never
-// are), lo = x - hi exactly, truncated to tf32 (|error| < 2^-21 |x|, the size of the dropped lo*lo term).
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
-}
-
 template <int KS>   // k8 steps over the classes = n8 tiles of dW2: ceil(c / 8)
 __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const float* __restrict__ H1, int64_t ldh,
                                                                        const float* __restrict__ dS2, int64_t ldd,
