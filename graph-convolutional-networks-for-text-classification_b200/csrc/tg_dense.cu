@@ -915,17 +915,13 @@ static int launch_hidden_bwd_mma(const float* H1, int64_t ldh, const float* dS2,
     rpb = ceil_div64(rpb, kHmTile) * kHmTile;
     grid = ceil_div64(n > 0 ? n : 1, rpb);
     const int threads = kHmThreads;   // warps past the hidden width only help staging dS2
-    static const int attr_rc = [] {
-        int rc = (int)cudaFuncSetAttribute(hidden_bwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHmSmem);
-        rc |= (int)cudaFuncSetAttribute(hidden_bwd_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHmSmem);
-        rc |= (int)cudaFuncSetAttribute(hidden_bwd_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHmSmem);
-        return rc;
-    }();
-    TG_REQUIRE(attr_rc == 0, TG_ERR_CUDA, "cudaFuncSetAttribute failed for the hidden-layer backward");
     switch ((c + 7) / 8) {
-        case 1: hidden_bwd_mma_kernel<1><<<(unsigned)grid, threads, kHmSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count); break;
-        case 2: hidden_bwd_mma_kernel<2><<<(unsigned)grid, threads, kHmSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count); break;
-        default: hidden_bwd_mma_kernel<3><<<(unsigned)grid, threads, kHmSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count); break;
+        case 1: TG_CUDA(cudaFuncSetAttribute(hidden_bwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHmSmem));
+                 hidden_bwd_mma_kernel<1><<<(unsigned)grid, threads, kHmSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count); break;
+        case 2: TG_CUDA(cudaFuncSetAttribute(hidden_bwd_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHmSmem));
+                 hidden_bwd_mma_kernel<2><<<(unsigned)grid, threads, kHmSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count); break;
+        default: TG_CUDA(cudaFuncSetAttribute(hidden_bwd_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHmSmem));
+                 hidden_bwd_mma_kernel<3><<<(unsigned)grid, threads, kHmSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count); break;
     }
     TG_LAUNCH_CHECK();
     const int64_t n_elem = (int64_t)h * (c + 1);
