@@ -102,6 +102,51 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c
 
 __device__ __forceinline__ float4 lds128(const unsigned char* p) { return *reinterpret_cast<const float4*>(p); }
 
+// One lock-step trip of the GS < 32 hub role: up to two entries (positions q and q + 1, each below h1) of this sub-group's run.
+// No branch (the sub-groups of a warp disagree and a branch serialises them).  The loads carry their predicates — a skipped
+// entry moves no data — and write into the caller's scratch registers `t`, which keep their previous contents when the load
+// is skipped; the FMAs are unconditional, with the value of a skipped entry replaced by 0.  The scratch rows are cleared at
+// the start of every slot, so what a skipped entry multiplies by 0 is either 0 or a row that already went into this very
+// slot: no 0 * x product can turn a non-finite value of an unrelated row of B into a NaN of this slot.  Shared memory is
+// addressed with 32-bit shared-window addresses and the accumulators are the packed pairs the FFMA2s work on.  The C++ form
+// of this trip compiled to 31 instructions, among them a generic-to-shared address conversion (S2R SR_CgaCtaId) per entry
+// and six register clears; a variant with unpredicated loads from an all-zero row saved as many instructions but moved the
+// skipped entries' rows through the shared-memory pipe (+50 % wavefronts: hub role 58 % -> 90 % of the pipe, no gain).
+//   he_q: shared address of entry q; bl: shared address of this lane's float4 of tile row 0
+struct HubScratch {
+    unsigned x0, y0, x1, y1;
+    unsigned long long a01, a23, b01, b23;
+};
+__device__ __forceinline__ void hub_trip2(unsigned long long& acc01, unsigned long long& acc23, HubScratch& t, unsigned he_q,
+                                          unsigned bl, int q, int h1) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p0, p1;\n"
+        ".reg .b32 q1, z0, z1;\n"
+        ".reg .b64 v0, v1;\n"
+        "setp.lt.s32 p0, %12, %13;\n"
+        "add.s32 q1, %12, 1;\n"
+        "setp.lt.s32 p1, q1, %13;\n"
+        "@p0 ld.shared.v2.b32 {%2, %3}, [%10];\n"
+        "@p1 ld.shared.v2.b32 {%4, %5}, [%10+8];\n"
+        "@p0 add.u32 %2, %2, %11;\n"
+        "@p1 add.u32 %4, %4, %11;\n"
+        "@p0 ld.shared.v2.b64 {%6, %7}, [%2];\n"
+        "@p1 ld.shared.v2.b64 {%8, %9}, [%4];\n"
+        "selp.b32 z0, %3, 0, p0;\n"
+        "selp.b32 z1, %5, 0, p1;\n"
+        "mov.b64 v0, {z0, z0};\n"
+        "mov.b64 v1, {z1, z1};\n"
+        "fma.rn.f32x2 %0, v0, %6, %0;\n"
+        "fma.rn.f32x2 %1, v0, %7, %1;\n"
+        "fma.rn.f32x2 %0, v1, %8, %0;\n"
+        "fma.rn.f32x2 %1, v1, %9, %1;\n"
+        "}\n"
+        : "+l"(acc01), "+l"(acc23), "+r"(t.x0), "+r"(t.y0), "+r"(t.x1), "+r"(t.y1), "+l"(t.a01), "+l"(t.a23), "+l"(t.b01), "+l"(t.b23)
+        : "r"(he_q), "r"(bl), "r"(q), "r"(h1)
+        : "memory");
+}
+
 // =============================================== hub role ===============================================================
 // GS lanes per slot sub-group: the 32 lanes of a warp form NSUB = 32 / GS sub-groups; a sub-group owns 16 hub slots and its
 // GS lanes cover a slice of 4 GS columns with one float4 each (sixteen float4 accumulators per lane, whatever GS is).
@@ -151,8 +196,12 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
         for (int r0 = 0; r0 < a.T; r0 += box_rows) tma_prefetch_l2_2d(tmap, slice * kCols, row0 + r0);
     };
     float4 acc[kKPW];
+    unsigned long long acc2[kKPW][2];   // the same accumulators as packed pairs (GS < 32: lock-step trips in PTX)
 #pragma unroll
-    for (int kk = 0; kk < kKPW; ++kk) acc[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kk = 0; kk < kKPW; ++kk) {
+        acc[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+        acc2[kk][0] = acc2[kk][1] = 0ull;
+    }
     int c = hl;
     if (c < a.n_chunks) {
         int4 d_next = make_int4(0, 0, 0, 0);
@@ -224,6 +273,9 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
                     }
                 }
             } else {
+                const unsigned bl_s = smem_u32(Bl), he_s = smem_u32(he);
+                HubScratch scr;
+                scr.x0 = scr.y0 = scr.x1 = scr.y1 = 0u;
                 // NSUB sub-groups in lock step: the warp makes as many trips as the longest of its NSUB runs needs, two entries
                 // per trip; a sub-group past the end of its run sits the trip out.  Predicated, not branched: the sub-groups
                 // disagree on the predicates and a branch would serialise them (measured: 22 ms against 16 ms at the
@@ -233,18 +285,10 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
                     int q = hofs[kk];
                     const int h1 = hofs[kk + 1];
                     const int n_trip = (__reduce_max_sync(0xffffffffu, h1 - q) + 1) >> 1;
+                    unsigned hq = he_s + 8u * (unsigned)q;
+                    scr.a01 = scr.a23 = scr.b01 = scr.b23 = 0ull;   // (what a skipped entry multiplies by 0: see hub_trip2)
 #pragma unroll 1
-                    for (int t = 0; t < n_trip; ++t, q += 2) {
-                        const bool p0 = q < h1, p1 = q + 1 < h1;
-                        int2 e0 = make_int2(0, 0), e1 = make_int2(0, 0);
-                        if (p0) e0 = he[q];
-                        if (p1) e1 = he[q + 1];
-                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                        if (p0) b0 = lds128(Bl + e0.x);
-                        if (p1) b1 = lds128(Bl + e1.x);
-                        if (p0) fma4p(acc[kk], __int_as_float(e0.y), b0);
-                        if (p1) fma4p(acc[kk], __int_as_float(e1.y), b1);
-                    }
+                    for (int t = 0; t < n_trip; ++t, q += 2, hq += 16u) hub_trip2(acc2[kk][0], acc2[kk][1], scr, hq, bl_s, q, h1);
                 }
             }
             __syncthreads();
@@ -253,7 +297,82 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
     float* dst = a.partials + ((int64_t)hl * a.Kv + grp * kSlots + (warp * NSUB + sub) * kKPW) * a.ldp + (int64_t)(slice * GS + gl) * 4;
     if (slice * GS + gl < a.n_chunks4) {  // (the last slice of a width that is no multiple of the slice width is narrower; TMA zero-fills it)
 #pragma unroll
-        for (int kk = 0; kk < kKPW; ++kk) *reinterpret_cast<float4*>(dst + (int64_t)kk * a.ldp) = acc[kk];
+        for (int kk = 0; kk < kKPW; ++kk) {
+            if (NSUB == 1) {
+                *reinterpret_cast<float4*>(dst + (int64_t)kk * a.ldp) = acc[kk];
+            } else {
+                const uint2 lo = *reinterpret_cast<const uint2*>(&acc2[kk][0]), hi = *reinterpret_cast<const uint2*>(&acc2[kk][1]);
+                *reinterpret_cast<float4*>(dst + (int64_t)kk * a.ldp) =
+                    make_float4(__uint_as_float(lo.x), __uint_as_float(lo.y), __uint_as_float(hi.x), __uint_as_float(hi.y));
+            }
+        }
+    }
+}
+
+// One predicated step of the document role's lock-step tail (R > 1): row r takes its entry p if it has one (p < n).  Loads
+// are predicated into the caller's scratch (they keep their previous contents when skipped), the FMAs are unconditional with
+// the value of a missing entry replaced by 0: what a missing entry multiplies by 0 is either 0 (the scratch is cleared at the
+// start of the tail) or a hub row that already went into this very output row.  ea: shared address of the entry; bh: shared
+// address of this lane's float4 of resident hub row 0; entries address hub row h as h * 128, a resident row is 128 NQ bytes.
+template <int NQ>
+struct DocTailScratch {
+    unsigned x, y;
+    unsigned long long b[NQ][2];
+};
+__device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+template <int NQ>
+__device__ __forceinline__ void doc_tail_step(unsigned long long (&acc)[NQ][2], DocTailScratch<NQ>& t, unsigned ea, unsigned bh, int p,
+                                              int n) {
+    static_assert(NQ == 1 || NQ == 2, "the lock-step tail is written for one or two float4 chunks per lane");
+    if (NQ == 1) {
+        asm volatile(
+            "{\n"
+            ".reg .pred q;\n"
+            ".reg .b32 z;\n"
+            ".reg .b64 v;\n"
+            "setp.lt.s32 q, %8, %9;\n"
+            "@q ld.shared.v2.b32 {%2, %3}, [%6];\n"
+            "@q add.u32 %2, %2, %7;\n"
+            "@q ld.shared.v2.b64 {%4, %5}, [%2];\n"
+            "selp.b32 z, %3, 0, q;\n"
+            "mov.b64 v, {z, z};\n"
+            "fma.rn.f32x2 %0, v, %4, %0;\n"
+            "fma.rn.f32x2 %1, v, %5, %1;\n"
+            "}\n"
+            : "+l"(acc[0][0]), "+l"(acc[0][1]), "+r"(t.x), "+r"(t.y), "+l"(t.b[0][0]), "+l"(t.b[0][1])
+            : "r"(ea), "r"(bh), "r"(p), "r"(n)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred q;\n"
+            ".reg .b32 z;\n"
+            ".reg .b64 v;\n"
+            "setp.lt.s32 q, %12, %13;\n"
+            "@q ld.shared.v2.b32 {%4, %5}, [%10];\n"
+            "@q mad.lo.u32 %4, %4, 2, %11;\n"
+            "@q ld.shared.v2.b64 {%6, %7}, [%4];\n"
+            "@q ld.shared.v2.b64 {%8, %9}, [%4+128];\n"
+            "selp.b32 z, %5, 0, q;\n"
+            "mov.b64 v, {z, z};\n"
+            "fma.rn.f32x2 %0, v, %6, %0;\n"
+            "fma.rn.f32x2 %1, v, %7, %1;\n"
+            "fma.rn.f32x2 %2, v, %8, %2;\n"
+            "fma.rn.f32x2 %3, v, %9, %3;\n"
+            "}\n"
+            : "+l"(acc[0][0]), "+l"(acc[0][1]), "+l"(acc[NQ - 1][0]), "+l"(acc[NQ - 1][1]), "+r"(t.x), "+r"(t.y), "+l"(t.b[0][0]),
+              "+l"(t.b[0][1]), "+l"(t.b[NQ - 1][0]), "+l"(t.b[NQ - 1][1])
+            : "r"(ea), "r"(bh), "r"(p), "r"(n)
+            : "memory");
     }
 }
 
@@ -479,7 +598,7 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const Epi& epi, const 
         load_self(cur, sj + a.doc_lanes, selfp);  // next job's self-loop operand: in flight during the hub-column loop
 #pragma unroll
         for (int r = 0; r < R; ++r) ent[r] += n_nh[r];
-        if (R == 1) {
+        if constexpr (R == 1) {
             // one row per group: two entries per trip
             int p = 0;
 #pragma unroll 1
@@ -530,15 +649,45 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const Epi& epi, const 
                     for (int u = 0; u < NQ; ++u) fma4p(acc[r][u], v, b[r][u]);
                 }
             }
+            // The entries beyond the warp's shortest row: all R rows of all groups stay in lock step up to the warp's LONGEST
+            // row, a row that has run out loads nothing and adds 0 (doc_tail_step).  Walking them row by row — divergent
+            // loops of dependent shared-memory loads, one row after the other — took as many instructions as the whole
+            // unpredicated loop above and 16 % of the role's stall samples at the C4 shape.
+            int max_hub_w = n_hub[0];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                for (int p = min_hub; p < n_hub[r]; ++p) {
-                    const int2 e0 = ent[r][p];
-                    const unsigned char* rp = BHl + e0.x * NQ;
-                    const float v = __int_as_float(e0.y);
+            for (int r = 1; r < R; ++r) max_hub_w = max(max_hub_w, n_hub[r]);
+            max_hub_w = __reduce_max_sync(0xffffffffu, max_hub_w);
+            if (max_hub_w > min_hub) {
+                const unsigned bh_s = smem_u32(BHl);
+                unsigned ea[R];
+                DocTailScratch<NQ> scr[R];
+                unsigned long long pa[R][NQ][2];
 #pragma unroll
-                    for (int u = 0; u < NQ; ++u) fma4p(acc[r][u], v, lds128(rp + 128 * u));
+                for (int r = 0; r < R; ++r) {
+                    ea[r] = smem_u32(ent[r] + min_hub);
+                    scr[r].x = scr[r].y = 0u;
+#pragma unroll
+                    for (int u = 0; u < NQ; ++u) {
+                        scr[r].b[u][0] = scr[r].b[u][1] = 0ull;
+                        pa[r][u][0] = pack_f2(acc[r][u].x, acc[r][u].y);
+                        pa[r][u][1] = pack_f2(acc[r][u].z, acc[r][u].w);
+                    }
                 }
+#pragma unroll 1
+                for (int p = min_hub; p < max_hub_w; ++p) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        doc_tail_step<NQ>(pa[r], scr[r], ea[r], bh_s, p, n_hub[r]);
+                        ea[r] += 8u;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int u = 0; u < NQ; ++u) {
+                        const float2 lo = unpack_f2(pa[r][u][0]), hi = unpack_f2(pa[r][u][1]);
+                        acc[r][u] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    }
             }
         }
         __syncwarp();
@@ -1698,8 +1847,10 @@ static int roles2_run_t(const tg_plan* pl, const StreamCall& c, const Epi& epi, 
     // share of the SMs given to the hub role: both fronts must advance together so that the second reader of a row of B
     // hits L2 (split_sms).  Weights in shared-memory wavefronts / issue slots per 128 columns (measured per role, profiles/):
     // lock-stepped sub-groups and one-float4 document slices pay more instructions per entry and row.
-    // (narrow-slice hub role: ~3x the instructions per entry — thin (slot, chunk) runs walked in lock step; measured per role)
-    const double hub_w = ((nsub > 1 ? 14.0 : 5.0) * (double)pl->hub_nnz + 4.0 * (double)a.groups * (double)pl->n_rows) / 0.82;
+    // (narrow-slice hub role: ~2.5x the cost per entry — thin (slot, chunk) runs walked in lock step.  Role-only runs at the C4
+    // shape, 1.9 M documents, with the lock-step trips of both roles in PTX: hub 144 CTA-ms on 72 CTAs (160 on 64), documents
+    // 149 CTA-ms — an even split again)
+    const double hub_w = ((nsub > 1 ? 12.5 : 5.0) * (double)pl->hub_nnz + 4.0 * (double)a.groups * (double)pl->n_rows) / 0.82;
     // (document role, 128-column slices: 59 CTA-ms per 1 M documents in the role-only run of round 2 -> 0.715; narrower slices keep
     // the figure their sweeps were made with)
     double doc_w = (4.0 * (double)(pl->nnz - pl->hub_nnz - pl->n_rows) + 14.0 * (4.0 / nq) * (double)pl->n_rows) / (nq == 4 ? 0.715 : 0.67);
