@@ -102,7 +102,7 @@ class EventHook:
     """Records a CUDA event pair on the launching (current torch) stream around selected C-ABI calls."""
 
     def __init__(self, tags):
-        self.tags, self.records, self.enabled = set(tags), [], False
+        self.tags, self.records, self.dense, self.enabled = set(tags), [], [], False
 
     def start(self, tag, info):
         import torch
@@ -115,7 +115,17 @@ class EventHook:
     def stop(self, tok):
         tag, info, a, b = tok
         b.record()
-        self.records.append((tag, info.get("n_feat"), info.get("csr"), a, b))
+        if "csr" in info:
+            self.records.append((tag, info.get("n_feat"), info.get("csr"), a, b))
+        else:
+            self.dense.append((tag, info.get("n"), info.get("h"), info.get("c"), a, b))
+
+    def dense_summary(self):
+        """{(tag, n, h, c): [ms, ...]} of the skinny dense kernels (H1 W2 and the fused hidden-layer backward)."""
+        out = {}
+        for tag, n, h, c, a, b in self.dense:
+            out.setdefault((tag, n, h, c), []).append(a.elapsed_time(b))
+        return out
 
     def summary(self):
         out = {}
@@ -393,6 +403,7 @@ def measure_workload(name: str, args, world: int, rank: int, dev, hook, steps: i
         return ms, ops.Stats.launches, clocks
 
     hook.records.clear()
+    hook.dense.clear()
     # ---- device-resident timing (value) + live per-kernel events ------------------------------------------------------
     ms_total, launches, clocks = timed(step_device, steps, warmup, use_hook=True)
     ms_step = ms_total / steps
@@ -414,6 +425,14 @@ def measure_workload(name: str, args, world: int, rank: int, dev, hook, steps: i
         avg_ms = sum(ts) / len(ts)
         detail[f"{tag}_F{f}"] = {"launches": len(ts), "avg_ms": avg_ms, "algorithmic_GB": nbytes / 1e9,
                                  "GBps": nbytes / 1e6 / avg_ms, "frac_of_peak": nbytes / 1e6 / avg_ms / hbm_peak}
+    # the skinny dense kernels of the step: bytes = the [n x h] operand once (dense_nn) / read + written once (hidden_bwd)
+    for (tag, n_r, h_r, c_r), ts in hook.dense_summary().items():
+        if n_r != csr.n_rows:
+            continue  # (sharded mode: the product on the K replicated topic rows)
+        nbytes = (1.0 if tag == "dense_nn" else 2.0) * n_r * h_r * 4.0 + n_r * c_r * 4.0 + h_r * c_r * 4.0
+        avg_ms = sum(ts) / len(ts)
+        detail[f"{tag}_{h_r}x{c_r}"] = {"launches": len(ts), "avg_ms": avg_ms, "algorithmic_GB": nbytes / 1e9,
+                                         "GBps": nbytes / 1e6 / avg_ms, "frac_of_peak": nbytes / 1e6 / avg_ms / hbm_peak}
     out["kernels"] = detail
     roof = None
     dom = [(k, v) for k, v in detail.items() if k.endswith(f"_F{hidden}")]
@@ -568,7 +587,7 @@ def run_ours(args):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     tg._native.lib()
-    hook = EventHook({"spmm", "gc1_fwd", "gc2_loss_fwd"})
+    hook = EventHook({"spmm", "gc1_fwd", "gc2_loss_fwd", "dense_nn", "hidden_bwd"})
     ops.set_kernel_hook(hook)
 
     name = WORKLOADS[args.workload]
