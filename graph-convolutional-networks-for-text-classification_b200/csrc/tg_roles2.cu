@@ -287,7 +287,7 @@ __device__ __forceinline__ void hub_role(const R2Args& a, const CUtensorMap* tma
                     const int n_trip = (__reduce_max_sync(0xffffffffu, h1 - q) + 1) >> 1;
                     unsigned hq = he_s + 8u * (unsigned)q;
                     scr.a01 = scr.a23 = scr.b01 = scr.b23 = 0ull;   // (what a skipped entry multiplies by 0: see hub_trip2)
-#pragma unroll 1
+#pragma unroll 1   // (unrolled by two the body grows to 42 instructions for two trips — register shuffles around the asm blocks)
                     for (int t = 0; t < n_trip; ++t, q += 2, hq += 16u) hub_trip2(acc2[kk][0], acc2[kk][1], scr, hq, bl_s, q, h1);
                 }
             }
@@ -515,12 +515,29 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const Epi& epi, const 
     float* yp = nullptr;
     int64_t yrow_stride = 0, ysj_stride = 0;
     bool plain = false;
+    int fast_mode = 0;        // 1: bias + ReLU + bit-packed dropout mask, 2: bias + ReLU (see below)
+    float drop_scale = 1.f;
+    float4 bias_s[NQ];        // bias * 1 / (1 - p)
+#pragma unroll
+    for (int u = 0; u < NQ; ++u) bias_s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     if constexpr (kStore) {
         yp = epi.Y + ((int64_t)dl * kSJRows + grp) * epi.ldy + (int64_t)q0 * 4;
         yrow_stride = (int64_t)kJobRows * epi.ldy;
         ysj_stride = (int64_t)a.doc_lanes * kSJRows * epi.ldy;
         // nothing to do after the sums: plain product without bias / activation / scale / dropout
         plain = !epi.bias && !epi.relu && !epi.out_scale && !a.keep_bits && epi.drop_mode != 2;
+        // The two epilogues of the layer-1 forward get paths of their own, chosen once per thread: the general path tests its
+        // five flags and reloads their constants for every float4 — 40 instructions per chunk, as many per row as the whole
+        // entry loop (bias alone cost 0.085 ms on top of the 0.78 ms plain product at C3).
+        bool all_valid = true;
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) all_valid = all_valid && valid[u];
+        if (all_valid && epi.bias && epi.relu && !epi.out_scale && epi.drop_mode != 2) fast_mode = a.keep_bits ? 1 : 2;
+        drop_scale = epi.scale;
+        if (!(drop_scale > 0.f)) fast_mode = fast_mode == 1 ? 0 : fast_mode;   // (p = 1: scale 0 — the general path)
+#pragma unroll
+        for (int u = 0; u < NQ; ++u)
+            bias_s[u] = make_float4(bias4[u].x * drop_scale, bias4[u].y * drop_scale, bias4[u].z * drop_scale, bias4[u].w * drop_scale);
     }
     const unsigned gmask = group_mask<8>(lane);
     float4 cur[R][NQ];
@@ -713,6 +730,36 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const Epi& epi, const 
 #pragma unroll
                 for (int u = 0; u < NQ; ++u)
                     if (valid[u]) *reinterpret_cast<float4*>(yrow + u * 32) = acc[r][u];
+            } else if (fast_mode == 1) {
+                // layer-1 forward in training: max(acc + bias, 0), kept elements times 1 / (1 - p) — nothing else to test
+#pragma unroll
+                for (int u = 0; u < NQ; ++u) {
+                    const uint32_t w = kb.w[r][u] >> (4 * gl);
+                    // max(acc + b, 0) * s = max(acc * s + b * s, 0) for the positive scale s = 1 / (1 - p): two packed FMAs
+                    // instead of four adds and four multiplies (bit-identical for p = 0.5, where the scale is a power of two)
+                    float4 v = bias_s[u];
+                    fma4p(v, drop_scale, acc[r][u]);
+                    v.x = fmaxf(v.x, 0.f);
+                    v.y = fmaxf(v.y, 0.f);
+                    v.z = fmaxf(v.z, 0.f);
+                    v.w = fmaxf(v.w, 0.f);
+                    v.x = (w & 1u) ? v.x : 0.f;
+                    v.y = (w & 2u) ? v.y : 0.f;
+                    v.z = (w & 4u) ? v.z : 0.f;
+                    v.w = (w & 8u) ? v.w : 0.f;
+                    *reinterpret_cast<float4*>(yrow + u * 32) = v;
+                }
+            } else if (fast_mode == 2) {
+                // layer-1 forward in evaluation: max(acc + bias, 0)
+#pragma unroll
+                for (int u = 0; u < NQ; ++u) {
+                    float4 v = acc[r][u];
+                    v.x = fmaxf(v.x + bias4[u].x, 0.f);
+                    v.y = fmaxf(v.y + bias4[u].y, 0.f);
+                    v.z = fmaxf(v.z + bias4[u].z, 0.f);
+                    v.w = fmaxf(v.w + bias4[u].w, 0.f);
+                    *reinterpret_cast<float4*>(yrow + u * 32) = v;
+                }
             } else {
 #pragma unroll
                 for (int u = 0; u < NQ; ++u) {
