@@ -517,6 +517,7 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const Epi& epi, const 
     bool plain = false;
     int fast_mode = 0;        // 1: bias + ReLU + bit-packed dropout mask, 2: bias + ReLU (see below)
     float drop_scale = 1.f;
+    bool scale_pow2 = false;
     float4 bias_s[NQ];        // bias * 1 / (1 - p)
 #pragma unroll
     for (int u = 0; u < NQ; ++u) bias_s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -535,6 +536,7 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const Epi& epi, const 
         if (all_valid && epi.bias && epi.relu && !epi.out_scale && epi.drop_mode != 2) fast_mode = a.keep_bits ? 1 : 2;
         drop_scale = epi.scale;
         if (!(drop_scale > 0.f)) fast_mode = fast_mode == 1 ? 0 : fast_mode;   // (p = 1: scale 0 — the general path)
+        scale_pow2 = (__float_as_uint(drop_scale) & 0x007fffffu) == 0u && drop_scale > 0.f;
 #pragma unroll
         for (int u = 0; u < NQ; ++u)
             bias_s[u] = make_float4(bias4[u].x * drop_scale, bias4[u].y * drop_scale, bias4[u].z * drop_scale, bias4[u].w * drop_scale);
@@ -735,14 +737,25 @@ __device__ __forceinline__ void doc_role(const R2Args& a, const Epi& epi, const 
 #pragma unroll
                 for (int u = 0; u < NQ; ++u) {
                     const uint32_t w = kb.w[r][u] >> (4 * gl);
-                    // max(acc + b, 0) * s = max(acc * s + b * s, 0) for the positive scale s = 1 / (1 - p): two packed FMAs
-                    // instead of four adds and four multiplies (bit-identical for p = 0.5, where the scale is a power of two)
-                    float4 v = bias_s[u];
-                    fma4p(v, drop_scale, acc[r][u]);
-                    v.x = fmaxf(v.x, 0.f);
-                    v.y = fmaxf(v.y, 0.f);
-                    v.z = fmaxf(v.z, 0.f);
-                    v.w = fmaxf(v.w, 0.f);
+                    float4 v;
+                    if (scale_pow2) {
+                        // max(acc + b, 0) * s = max(acc * s + b * s, 0): two packed FMAs instead of four adds and four
+                        // multiplies — only when s = 1 / (1 - p) is a power of two (p = 0.5, the reference's setting), where
+                        // the two forms are bit-identical; otherwise the rounding of b * s can flip the sign of an element
+                        // that cancels to almost zero, and with it the ReLU gate the backward reads from H1
+                        v = bias_s[u];
+                        fma4p(v, drop_scale, acc[r][u]);
+                        v.x = fmaxf(v.x, 0.f);
+                        v.y = fmaxf(v.y, 0.f);
+                        v.z = fmaxf(v.z, 0.f);
+                        v.w = fmaxf(v.w, 0.f);
+                    } else {
+                        v = acc[r][u];
+                        v.x = fmaxf(v.x + bias4[u].x, 0.f) * drop_scale;
+                        v.y = fmaxf(v.y + bias4[u].y, 0.f) * drop_scale;
+                        v.z = fmaxf(v.z + bias4[u].z, 0.f) * drop_scale;
+                        v.w = fmaxf(v.w + bias4[u].w, 0.f) * drop_scale;
+                    }
                     v.x = (w & 1u) ? v.x : 0.f;
                     v.y = (w & 2u) ? v.y : 0.f;
                     v.z = (w & 4u) ? v.z : 0.f;
