@@ -1061,6 +1061,32 @@ def test_hidden_backward_strided_operands(tg, n, h, c):
     assert torch.equal(dW2, dW2b) and torch.equal(db1, db1b) and torch.equal(dZ1b, out)
 
 
+def test_hidden_backward_c3_size_against_float64(tg):
+    """The hidden-layer backward at the benchmarked size (1 000 256 rows x 256 units x 20 classes, H1 with the ~75 % zeros that
+    ReLU and dropout leave): dW2 and db1 — sums over a million rows, accumulated in the tensor-core accumulators per 128-row
+    tile and in fp32 master registers across tiles — against float64; dZ1 on a row sample."""
+    from topicgcn_b200 import ops
+    n, h, c = 1_000_256, 256, 20
+    gen = torch.Generator(device="cuda:0").manual_seed(5)
+    H1 = torch.relu(torch.randn(n, h, device=dev(), generator=gen)) * (torch.rand(n, h, device=dev(), generator=gen) < 0.5) * 2.0
+    dS2 = torch.randn(n, c, device=dev(), generator=gen) * 1e-6       # gradients of a mean over ~1e6 rows are this small
+    W2 = torch.randn(h, c, device=dev(), generator=gen) * 0.1
+    dZ1, dW2, db1 = ops.hidden_backward(H1, dS2, W2, 2.0)
+    H64, D64, W64 = H1.double(), dS2.double(), W2.double()
+    dW2_ref = (H64.t() @ D64).cpu().numpy()
+    dZ1_ref_full = torch.where(H1 > 0, (D64 @ W64.t()) * 2.0, torch.zeros((), dtype=torch.float64, device=dev()))
+    db1_ref = dZ1_ref_full.sum(dim=0).cpu().numpy()
+    assert rel_err(dW2.cpu().numpy(), dW2_ref) <= 2e-5
+    assert rel_err(db1.cpu().numpy(), db1_ref) <= 2e-5
+    rows = torch.randint(0, n, (4096,), device=dev(), generator=gen)
+    rows = torch.cat([rows, torch.arange(n - 300, n, device=dev()), torch.arange(0, 300, device=dev())])
+    assert rel_err(dZ1[rows].cpu().numpy(), dZ1_ref_full[rows].cpu().numpy()) <= 1e-5
+    assert not bool(((H1 == 0) & (dZ1 != 0)).any())   # dZ1 is exactly zero wherever H1 is
+    del dZ1_ref_full, H64, D64
+    dZ1b, dW2b, db1b = ops.hidden_backward(H1, dS2, W2, 2.0)
+    assert torch.equal(dW2, dW2b) and torch.equal(db1, db1b) and torch.equal(dZ1, dZ1b)
+
+
 def test_cached_csr_sees_in_place_edits(tg, small_golden):
     """The per-tensor CSR cache keys on the version counters: scaling the adjacency values in place changes the next product."""
     g = small_golden
