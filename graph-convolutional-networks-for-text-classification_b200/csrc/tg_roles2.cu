@@ -107,7 +107,8 @@ __device__ __forceinline__ float4 lds128(const unsigned char* p) { return *reint
 // entry moves no data — and write into the caller's scratch registers `t`, which keep their previous contents when the load
 // is skipped; the FMAs are unconditional, with the value of a skipped entry replaced by 0.  The scratch rows are cleared at
 // the start of every slot, so what a skipped entry multiplies by 0 is either 0 or a row that already went into this very
-// slot: no 0 * x product can turn a non-finite value of an unrelated row of B into a NaN of this slot.  Shared memory is
+// slot: no 0 * x product can turn a non-finite value of an unrelated row of B into a NaN of this slot (a slot that received an
+// infinite term may end up NaN instead of infinite — non-finite either way, and confined to the rows the reference taints).  Shared memory is
 // addressed with 32-bit shared-window addresses and the accumulators are the packed pairs the FFMA2s work on.  The C++ form
 // of this trip compiled to 31 instructions, among them a generic-to-shared address conversion (S2R SR_CgaCtaId) per entry
 // and six register clears; a variant with unpredicated loads from an all-zero row saved as many instructions but moved the
