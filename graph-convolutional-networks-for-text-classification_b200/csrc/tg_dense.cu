@@ -617,12 +617,16 @@ __global__ void __launch_bounds__(256, 2) hidden_bwd_dense_kernel(const float* _
 // are then bank-conflict free.  Measured mma.sync rate on this part: 917 m16n8k8 TF32 MMAs per microsecond and SM
 // (tools/micro/mma_sync_rate.cu); the 36 M MMAs of the C3 shape are 0.27 ms of tensor pipe, the 2.1 GB 0.32 ms of HBM.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kHmThreads = 512;  // 16 warps x 16 hidden units
 constexpr int kHmTile = 128;     // rows per staged dS2 tile (two runs of 8 groups of 8 rows): one CTA barrier per tile
 constexpr int kHmStride = 28;    // floats per staged dS2 row
 constexpr int kHmDepth = 8;      // 8-row groups of H1 a warp keeps in flight (ring slot = group of the 64-row run)
-constexpr int kHmHStride = 20;   // floats per row of a warp's private H1 ring (16 units + pad: conflict-free 64-bit reads)
-constexpr size_t kHmSmem = (size_t)(4 * kHmTile * kHmStride + 2 * kHmTile * 24 + (kHmThreads / 32) * kHmDepth * 8 * kHmHStride) * sizeof(float);
+// MT = m16 tiles (16 hidden units each) per warp: 1 -> 16 warps per CTA, 128 registers; 2 -> 8 warps, the dS2 fragments of a
+// group feed twice the MMAs.  Row stride of a warp's private H1 ring: 16 MT units + pad, conflict-free fragment reads.
+template <int MT> struct HmCfg {
+    static constexpr int kThreads = 512 / MT;
+    static constexpr int kHStride = MT == 1 ? 20 : 36;
+    static constexpr size_t kSmem = (size_t)(4 * kHmTile * kHmStride + 2 * kHmTile * 24 + (kThreads / 32) * kHmDepth * 8 * kHStride) * sizeof(float);
+};
 
 __device__ __forceinline__ void mma_tf32_nv(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     // not volatile: a pure function of its operands, the scheduler may interleave independent chains
@@ -630,46 +634,56 @@ __device__ __forceinline__ void mma_tf32_nv(float (&d)[4], const uint32_t (&a)[4
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-template <int KS>   // k8 steps over the classes = n8 tiles of dW2: ceil(c / 8)
-__global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const float* __restrict__ H1, int64_t ldh,
-                                                                       const float* __restrict__ dS2, int64_t ldd,
-                                                                       const float* __restrict__ W2, int64_t ldw, float scale,
-                                                                       float* __restrict__ dZ1, int64_t ldz,
-                                                                       float* __restrict__ partials, int64_t n, int h, int c,
-                                                                       int64_t rows_per_block, int64_t n_count) {
-    constexpr int CPK = 8 * KS;                                               // padded class count
+template <int KS, int MT>   // KS: k8 steps over the classes = n8 tiles of dW2: ceil(c / 8)
+__global__ void __launch_bounds__(HmCfg<MT>::kThreads, 1) hidden_bwd_mma_kernel(const float* __restrict__ H1, int64_t ldh,
+                                                                                const float* __restrict__ dS2, int64_t ldd,
+                                                                                const float* __restrict__ W2, int64_t ldw, float scale,
+                                                                                float* __restrict__ dZ1, int64_t ldz,
+                                                                                float* __restrict__ partials, int64_t n, int h, int c,
+                                                                                int64_t rows_per_block, int64_t n_count) {
+    constexpr int CPK = 8 * KS;                     // padded class count
+    constexpr int kThreads = HmCfg<MT>::kThreads;
+    constexpr int kHS = HmCfg<MT>::kHStride;
+    constexpr int NU = 2 * MT;                      // hidden units per lane (adjacent in memory)
     extern __shared__ __align__(16) float hm_smem[];
     float (*Dhi)[kHmTile * kHmStride] = reinterpret_cast<float (*)[kHmTile * kHmStride]>(hm_smem);
     float (*Dlo)[kHmTile * kHmStride] = reinterpret_cast<float (*)[kHmTile * kHmStride]>(hm_smem + 2 * kHmTile * kHmStride);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int j0 = 16 * warp + 2 * g;
-    // the warp's private H1 ring: kHmDepth groups x 8 rows x 16 units.  A group is one coalesced cp.async of 16 bytes per lane
-    // (lane l: row l / 4, units 4 (l % 4) ..), read back as (row 2t, units 2g, 2g + 1) after a __syncwarp
-    float* hs_w = hm_smem + 4 * kHmTile * kHmStride + 2 * kHmTile * 24 + warp * (kHmDepth * 8 * kHmHStride);
-    float* hs_cp = hs_w + (lane >> 2) * kHmHStride + 4 * (lane & 3);
-    const float* hs = hs_w + (2 * t) * kHmHStride + 2 * g;
+    const int j0 = 16 * MT * warp + NU * g;         // m-slot g + 8 hh of m-tile mt is unit j0 + 2 mt + hh
+    // the warp's private H1 ring: kHmDepth groups x 8 rows x 16 MT units.  A group is MT coalesced cp.async of 16 bytes per lane
+    // (lane l: rows l / (4 MT) + (8 / MT) i, units 4 (l % (4 MT)) ..), read back as (row 2t, units NU g ..) after a __syncwarp
+    float* hs_w = hm_smem + 4 * kHmTile * kHmStride + 2 * kHmTile * 24 + warp * (kHmDepth * 8 * kHS);
+    constexpr int kCpl = 4 * MT;                    // 16-byte pieces per row of the warp's slice
+    float* hs_cp = hs_w + (lane / kCpl) * kHS + 4 * (lane % kCpl);
+    const float* hs = hs_w + (2 * t) * kHS + NU * g;
     float* draw = hm_smem + 4 * kHmTile * kHmStride;   // raw dS2 tiles [2][kHmTile * CPK]
-    const bool jok = j0 < h;                                  // h is a multiple of 4: units are inside or outside in fours
-    const bool cp_ok = 16 * warp + 4 * (lane & 3) < h;        // the four units this lane copies
+    const bool jok = j0 < h;                                           // h is a multiple of 4: units are inside or outside in fours
+    const bool cp_ok = 16 * MT * warp + 4 * (lane % kCpl) < h;         // the four units this lane copies
 
     // P1's A operand: W2 fragments  a0:(slot g, k t) a1:(slot g+8, k t) a2:(slot g, k t+4) a3:(slot g+8, k t+4)
-    uint32_t whi[KS][4], wlo[KS][4];
+    uint32_t whi[MT][KS][4], wlo[MT][KS][4];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int j = j0 + (e & 1), kk = 8 * ks + t + 4 * (e >> 1);
-            const float w = (jok && kk < c) ? __ldg(W2 + (int64_t)j * ldw + kk) : 0.f;
-            whi[ks][e] = to_tf32(w);
-            wlo[ks][e] = to_tf32(w - __uint_as_float(whi[ks][e]));
-        }
-    float gwm[KS][4];   // fp32 master copy of the lane's dW2 elements
+        for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-    for (int nt = 0; nt < KS; ++nt)
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + 2 * mt + (e & 1), kk = 8 * ks + t + 4 * (e >> 1);
+                const float w = (jok && kk < c) ? __ldg(W2 + (int64_t)j * ldw + kk) : 0.f;
+                whi[mt][ks][e] = to_tf32(w);
+                wlo[mt][ks][e] = to_tf32(w - __uint_as_float(whi[mt][ks][e]));
+            }
+    float gwm[MT][KS][4];   // fp32 master copy of the lane's dW2 elements
 #pragma unroll
-        for (int e = 0; e < 4; ++e) gwm[nt][e] = 0.f;
-    float gb[2] = {0.f, 0.f};
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < KS; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gwm[mt][nt][e] = 0.f;
+    float gb[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) gb[u] = 0.f;
 
     // everything below is relative to the block's first row, in 32-bit arithmetic (the launcher checks that a block's rows
     // times the leading dimensions fit): 64-bit row bookkeeping cost enough registers to spill under the 128-register cap,
@@ -686,8 +700,8 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
     // dS2 staging.  Tile 0: global -> registers -> hi / lo in shared memory.  Later tiles travel as raw fp32 with cp.async,
     // issued two tiles ahead inside the commit group of an H1 group (a register prefetch ended up next to its consumer and
     // exposed a full DRAM latency per tile); every thread splits the elements it copied itself at the end of the tile
-    // before their use, so the hand-over needs no barrier of its own.  Thread -> (class q = tid % 32, rows tid / 32 + 16 i).
-    constexpr int kSRows = kHmThreads / 32;          // rows one pass of the CTA covers
+    // before their use, so the hand-over needs no barrier of its own.  Thread -> (class q = tid % 32, rows tid / 32 + kSRows i).
+    constexpr int kSRows = kThreads / 32;            // rows one pass of the CTA covers
     constexpr int kSPass = kHmTile / kSRows;         // passes per tile
     const int sq = threadIdx.x & 31, sr = threadIdx.x >> 5;
     const bool s_act = sq < CPK;
@@ -736,12 +750,17 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
     // H1 ring: the next kHmDepth groups travel global -> shared memory asynchronously (a register ring left the distance
     // between a load and its use to the instruction scheduler, which under the 128-register cap moved the loads next to
     // their consumers: ncu showed 40 % of the samples on long-scoreboard stalls)
-    int hoff = (lane >> 2) * ldh_i + 16 * warp + 4 * (lane & 3);   // this lane's piece of the next group to load
-    int hrow = lane >> 2;
-    int zoff = (2 * t) * ldz_i + j0;                               // row 2t of the next group to store
+    constexpr int kCpRows = 32 / kCpl;               // rows one cp.async instruction of the warp covers
+    int hoff = (lane / kCpl) * ldh_i + 16 * MT * warp + 4 * (lane % kCpl);   // this lane's first piece of the next group to load
+    int hrow = lane / kCpl;
+    int zoff = (2 * t) * ldz_i + j0;                                          // row 2t of the next group to store
     auto load_group = [&](int slot, auto full_tag) {
         constexpr bool kFull = decltype(full_tag)::value;
-        if (cp_ok) hb_cp16(hs_cp + slot * (8 * kHmHStride), H1b + hoff, kFull || hrow < nrows);
+        if (cp_ok) {
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+                hb_cp16(hs_cp + slot * (8 * kHS) + i * kCpRows * kHS, H1b + hoff + i * kCpRows * ldh_i, kFull || hrow + i * kCpRows < nrows);
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
         hoff += 8 * ldh_i;
         hrow += 8;
@@ -754,11 +773,13 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
         const int buf = tile & 1;
         stage_issue(tile + 2);   // joins the commit group of this tile's first H1 refill: landed by the next tile's first wait
         const int r0 = tile * kHmTile;
-        float gw[KS][4];
+        float gw[MT][KS][4];
 #pragma unroll
-        for (int nt = 0; nt < KS; ++nt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) gw[nt][e] = 0.f;
+            for (int nt = 0; nt < KS; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) gw[mt][nt][e] = 0.f;
         const float* dhi_t = Dhi[buf];
         const float* dlo_t = Dlo[buf];
         auto run_tile = [&](auto full_tag) {
@@ -771,61 +792,96 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
             for (int grp = 0; grp < kHmDepth; ++grp) {
                 asm volatile("cp.async.wait_group %0;" ::"n"(kHmDepth - 1) : "memory");   // this group has landed
                 __syncwarp();
-                float2 xa = make_float2(0.f, 0.f), xb = xa;
+                float xa[NU], xb[NU];   // rows 2t and 2t + 1 of the group, the lane's NU units
+#pragma unroll
+                for (int u = 0; u < NU; ++u) xa[u] = xb[u] = 0.f;
                 if (jok) {
-                    xa = *reinterpret_cast<const float2*>(hs + grp * (8 * kHmHStride));
-                    xb = *reinterpret_cast<const float2*>(hs + grp * (8 * kHmHStride) + kHmHStride);
+                    if (MT == 1) {
+                        const float2 a2 = *reinterpret_cast<const float2*>(hs + grp * (8 * kHS));
+                        const float2 b2 = *reinterpret_cast<const float2*>(hs + grp * (8 * kHS) + kHS);
+                        xa[0] = a2.x; xa[1] = a2.y; xb[0] = b2.x; xb[1] = b2.y;
+                    } else {
+                        const float4 a4 = *reinterpret_cast<const float4*>(hs + grp * (8 * kHS));
+                        const float4 b4 = *reinterpret_cast<const float4*>(hs + grp * (8 * kHS) + kHS);
+                        xa[0] = a4.x; xa[1] = a4.y; xa[NU - 2] = a4.z; xa[NU - 1] = a4.w;
+                        xb[0] = b4.x; xb[1] = b4.y; xb[NU - 2] = b4.z; xb[NU - 1] = b4.w;
+                    }
                 }
                 __syncwarp();                // every lane has read the slot ...
                 load_group(grp, full_tag);   // ... before it is refilled with the group kHmDepth ahead
-                // ---- P1: pre-activation gradient of the lane's 2 units x 2 rows
-                float dh[4] = {0.f, 0.f, 0.f, 0.f}, dhs[4] = {0.f, 0.f, 0.f, 0.f};
+                // ---- P1: pre-activation gradient of the lane's NU units x 2 rows
+                float dh[MT][4], dhs[MT][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dh[mt][e] = dhs[mt][e] = 0.f;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
                     const int o = (8 * grp + g) * kHmStride + 8 * ks + t;
                     const uint32_t bhi[2] = {__float_as_uint(dhi[o]), __float_as_uint(dhi[o + 4])};
                     const uint32_t blo[2] = {__float_as_uint(dlo[o]), __float_as_uint(dlo[o + 4])};
-                    mma_tf32_nv(dhs, wlo[ks], bhi);   // small terms in their own chain
-                    mma_tf32_nv(dhs, whi[ks], blo);
-                    mma_tf32_nv(dh, whi[ks], bhi);
-                }
-                // c0:(unit j0, row 2t) c1:(j0, row 2t+1) c2:(j0+1, row 2t) c3:(j0+1, row 2t+1)
-                const float za0 = (xa.x > 0.f) ? (dh[0] + dhs[0]) * scale : 0.f;
-                const float zb0 = (xb.x > 0.f) ? (dh[1] + dhs[1]) * scale : 0.f;
-                const float za1 = (xa.y > 0.f) ? (dh[2] + dhs[2]) * scale : 0.f;
-                const float zb1 = (xb.y > 0.f) ? (dh[3] + dhs[3]) * scale : 0.f;
-                float v[4] = {xa.x, xa.y, xb.x, xb.y};   // P2's A fragment order: (j0, 2t) (j0+1, 2t) (j0, 2t+1) (j0+1, 2t+1)
-                float* zp = dZb + zoff;
-                if (kFull) {
-                    if (jok) {
-                        *reinterpret_cast<float2*>(zp) = make_float2(za0, za1);
-                        *reinterpret_cast<float2*>(zp + ldz_i) = make_float2(zb0, zb1);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_tf32_nv(dhs[mt], wlo[mt][ks], bhi);   // small terms in their own chain
+                        mma_tf32_nv(dhs[mt], whi[mt][ks], blo);
+                        mma_tf32_nv(dh[mt], whi[mt][ks], bhi);
                     }
-                    gb[0] += za0 + zb0;
-                    gb[1] += za1 + zb1;
-                } else {
+                }
+                // c0:(unit j0 + 2 mt, row 2t) c1:(same unit, row 2t+1) c2:(unit j0 + 2 mt + 1, row 2t) c3:(.., row 2t+1)
+                float za[NU], zb[NU];
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const int mt = u >> 1, hh = u & 1;
+                    za[u] = (xa[u] > 0.f) ? (dh[mt][2 * hh] + dhs[mt][2 * hh]) * scale : 0.f;
+                    zb[u] = (xb[u] > 0.f) ? (dh[mt][2 * hh + 1] + dhs[mt][2 * hh + 1]) * scale : 0.f;
+                }
+                float* zp = dZb + zoff;
+                bool cnt_a = true, cnt_b = true, st_a = jok, st_b = jok;
+                if (!kFull) {
                     const int row0 = r0 + 64 * run + 8 * grp + 2 * t;
-                    if (jok && row0 < nrows) *reinterpret_cast<float2*>(zp) = make_float2(za0, za1);
-                    if (jok && row0 + 1 < nrows) *reinterpret_cast<float2*>(zp + ldz_i) = make_float2(zb0, zb1);
-                    const bool cnt_a = row0 < ncnt, cnt_b = row0 + 1 < ncnt;
-                    gb[0] += (cnt_a ? za0 : 0.f) + (cnt_b ? zb0 : 0.f);
-                    gb[1] += (cnt_a ? za1 : 0.f) + (cnt_b ? zb1 : 0.f);
-                    if (!cnt_a) v[0] = v[1] = 0.f;
-                    if (!cnt_b) v[2] = v[3] = 0.f;
+                    st_a = jok && row0 < nrows;
+                    st_b = jok && row0 + 1 < nrows;
+                    cnt_a = row0 < ncnt;
+                    cnt_b = row0 + 1 < ncnt;
+                }
+                if (MT == 1) {
+                    if (st_a) *reinterpret_cast<float2*>(zp) = make_float2(za[0], za[1]);
+                    if (st_b) *reinterpret_cast<float2*>(zp + ldz_i) = make_float2(zb[0], zb[1]);
+                } else {
+                    if (st_a) *reinterpret_cast<float4*>(zp) = make_float4(za[0], za[1], za[NU - 2], za[NU - 1]);
+                    if (st_b) *reinterpret_cast<float4*>(zp + ldz_i) = make_float4(zb[0], zb[1], zb[NU - 2], zb[NU - 1]);
                 }
                 zoff += 8 * ldz_i;
-                // ---- P2: dW2 += H1^T dS2 over the group's 8 rows
-                uint32_t ahi[4], alo[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) split_tf32(v[e], ahi[e], alo[e]);
+                for (int u = 0; u < NU; ++u) {
+                    if (kFull) {
+                        gb[u] += za[u] + zb[u];
+                    } else {
+                        gb[u] += (cnt_a ? za[u] : 0.f) + (cnt_b ? zb[u] : 0.f);
+                        if (!cnt_a) xa[u] = 0.f;
+                        if (!cnt_b) xb[u] = 0.f;
+                    }
+                }
+                // ---- P2: dW2 += H1^T dS2 over the group's 8 rows;  A fragment order (j, 2t) (j + 1, 2t) (j, 2t+1) (j + 1, 2t+1)
+                uint32_t ahi[MT][4], alo[MT][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    split_tf32(xa[2 * mt], ahi[mt][0], alo[mt][0]);
+                    split_tf32(xa[2 * mt + 1], ahi[mt][1], alo[mt][1]);
+                    split_tf32(xb[2 * mt], ahi[mt][2], alo[mt][2]);
+                    split_tf32(xb[2 * mt + 1], ahi[mt][3], alo[mt][3]);
+                }
 #pragma unroll
                 for (int nt = 0; nt < KS; ++nt) {
                     const int o = (8 * grp + 2 * t) * kHmStride + 8 * nt + g;
                     const uint32_t bhi[2] = {__float_as_uint(dhi[o]), __float_as_uint(dhi[o + kHmStride])};
                     const uint32_t blo[2] = {__float_as_uint(dlo[o]), __float_as_uint(dlo[o + kHmStride])};
-                    mma_tf32_nv(gw[nt], alo, bhi);
-                    mma_tf32_nv(gw[nt], ahi, blo);
-                    mma_tf32_nv(gw[nt], ahi, bhi);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        mma_tf32_nv(gw[mt][nt], alo[mt], bhi);
+                        mma_tf32_nv(gw[mt][nt], ahi[mt], blo);
+                        mma_tf32_nv(gw[mt][nt], ahi[mt], bhi);
+                    }
                 }
             }
             }
@@ -834,33 +890,37 @@ __global__ void __launch_bounds__(kHmThreads, 1) hidden_bwd_mma_kernel(const flo
         if (r0 + kHmTile + 8 * kHmDepth <= nrows && r0 + kHmTile <= ncnt) run_tile(std::true_type{});
         else run_tile(std::false_type{});
 #pragma unroll
-        for (int nt = 0; nt < KS; ++nt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) gwm[nt][e] += gw[nt][e];
+            for (int nt = 0; nt < KS; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) gwm[mt][nt][e] += gw[mt][nt][e];
         if (tile + 1 < n_tiles) stage_split(tile + 1);   // (the last readers of that hi / lo buffer passed the previous barrier)
         __syncthreads();
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    // dW2 fragment  c0:(unit j0, class 8nt+2t) c1:(j0, 8nt+2t+1) c2:(unit j0+1, 8nt+2t) c3:(j0+1, 8nt+2t+1)
+    // dW2 fragment  c0:(unit j0 + 2 mt, class 8nt+2t) c1:(same unit, 8nt+2t+1) c2:(unit j0 + 2 mt + 1, 8nt+2t) c3:(.., 8nt+2t+1)
     float* out = partials + (int64_t)blockIdx.x * h * (c + 1);
     if (jok) {
 #pragma unroll
-        for (int nt = 0; nt < KS; ++nt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = j0 + (e >> 1), q = 8 * nt + 2 * t + (e & 1);
-                if (q < c) out[(int64_t)j * c + q] = gwm[nt][e];
-            }
+            for (int nt = 0; nt < KS; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = j0 + 2 * mt + (e >> 1), q = 8 * nt + 2 * t + (e & 1);
+                    if (q < c) out[(int64_t)j * c + q] = gwm[mt][nt][e];
+                }
     }
     // db1: the four lanes of a quad hold different rows of the same units
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NU; ++u) {
         gb[u] += __shfl_xor_sync(0xffffffffu, gb[u], 1);
         gb[u] += __shfl_xor_sync(0xffffffffu, gb[u], 2);
     }
     if (jok && t == 0) {
-        out[(int64_t)h * c + j0] = gb[0];
-        out[(int64_t)h * c + j0 + 1] = gb[1];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) out[(int64_t)h * c + j0 + u] = gb[u];
     }
 }
 
@@ -906,7 +966,28 @@ static bool mma_hidden_enabled() {   // TG_HIDDEN_MMA=0 selects the CUDA-core ke
     return on;
 }
 
-// tensor-core kernel: one CTA of sixteen warps per SM, every CTA a contiguous range of rows (a multiple of the 64-row tile)
+// tensor-core kernel: one CTA per SM, every CTA a contiguous range of rows (a multiple of the 128-row tile)
+template <int KS, int MT>
+static int launch_hidden_bwd_mma_t(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw, float scale,
+                                   float* dZ1, int64_t ldz, float* partials, int64_t n, int h, int c, int64_t rpb, int64_t n_count,
+                                   unsigned grid, cudaStream_t st) {
+    TG_CUDA(cudaFuncSetAttribute(hidden_bwd_mma_kernel<KS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HmCfg<MT>::kSmem));
+    hidden_bwd_mma_kernel<KS, MT><<<grid, HmCfg<MT>::kThreads, HmCfg<MT>::kSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h,
+                                                                                         c, rpb, n_count);
+    return TG_OK;
+}
+// m16 tiles per warp.  Two (8 warps x 32 units, 255 registers): the dS2 fragments of a group feed twice the MMAs and the
+// per-group bookkeeping is paid once per 32 units — 0.47 ms against 0.54 ms at C3; one (16 warps x 16 units) keeps more warps
+// busy when the hidden layer is narrow.  TG_HIDDEN_MMA_MT = 1 / 2 forces a variant (read once).
+static int hidden_mma_tiles(int h) {
+    static const int forced = [] {
+        const char* v = getenv("TG_HIDDEN_MMA_MT");
+        const int x = (v && *v) ? atoi(v) : 0;
+        return (x == 1 || x == 2) ? x : 0;
+    }();
+    if (forced) return forced;
+    return h > 128 ? 2 : 1;
+}
 static int launch_hidden_bwd_mma(const float* H1, int64_t ldh, const float* dS2, int64_t ldd, const float* W2, int64_t ldw,
                                  float scale, float* dZ1, int64_t ldz, float* dW2, float* db1, float* partials, int64_t n,
                                  int h, int c, int64_t n_count, cudaStream_t st) {
@@ -914,15 +995,18 @@ static int launch_hidden_bwd_mma(const float* H1, int64_t ldh, const float* dS2,
     int64_t rpb = ceil_div64(n > 0 ? n : 1, grid);
     rpb = ceil_div64(rpb, kHmTile) * kHmTile;
     grid = ceil_div64(n > 0 ? n : 1, rpb);
-    const int threads = kHmThreads;   // warps past the hidden width only help staging dS2
-    switch ((c + 7) / 8) {
-        case 1: TG_CUDA(cudaFuncSetAttribute(hidden_bwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHmSmem));
-                 hidden_bwd_mma_kernel<1><<<(unsigned)grid, threads, kHmSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count); break;
-        case 2: TG_CUDA(cudaFuncSetAttribute(hidden_bwd_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHmSmem));
-                 hidden_bwd_mma_kernel<2><<<(unsigned)grid, threads, kHmSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count); break;
-        default: TG_CUDA(cudaFuncSetAttribute(hidden_bwd_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHmSmem));
-                 hidden_bwd_mma_kernel<3><<<(unsigned)grid, threads, kHmSmem, st>>>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count); break;
+    const int ks = (c + 7) / 8;
+    int rc;
+    if (hidden_mma_tiles(h) == 2) {
+        rc = ks == 1 ? launch_hidden_bwd_mma_t<1, 2>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count, (unsigned)grid, st)
+           : ks == 2 ? launch_hidden_bwd_mma_t<2, 2>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count, (unsigned)grid, st)
+                     : launch_hidden_bwd_mma_t<3, 2>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count, (unsigned)grid, st);
+    } else {
+        rc = ks == 1 ? launch_hidden_bwd_mma_t<1, 1>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count, (unsigned)grid, st)
+           : ks == 2 ? launch_hidden_bwd_mma_t<2, 1>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count, (unsigned)grid, st)
+                     : launch_hidden_bwd_mma_t<3, 1>(H1, ldh, dS2, ldd, W2, ldw, scale, dZ1, ldz, partials, n, h, c, rpb, n_count, (unsigned)grid, st);
     }
+    if (rc != TG_OK) return rc;
     TG_LAUNCH_CHECK();
     const int64_t n_elem = (int64_t)h * (c + 1);
     sum_partials_kernel<<<(unsigned)ceil_div64(n_elem * 8, 256), 256, 0, st>>>(partials, grid, n_elem, dW2, (int64_t)h * c, db1, c, c);
