@@ -602,11 +602,11 @@ __global__ void __launch_bounds__(256, 2) hidden_bwd_dense_kernel(const float* _
 // (hi*hi + hi*lo + lo*hi in fp32):
 //   P1  dH1^T [j x rows] = W2 [j x c] * dS2^T [c x rows]      (M = hidden units, N = 8 rows, K = classes in steps of 8)
 //   P2  dW2   [j x c]   += H1^T [j x rows] * dS2 [rows x c]   (M = hidden units, N = classes in tiles of 8, K = 8 rows)
-// A warp owns 16 hidden units (one m16 tile) and walks the rows in groups of 8; the sixteen warps of a CTA share the rows,
-// so the dS2 tile is staged (already split into hi / lo) once per CTA.  Index choices that make every H1 element travel
-// exactly once, as one 64-bit load per lane and row, and every dZ1 element leave as one 64-bit store:
-//   * m-slot g is hidden unit j0, m-slot g + 8 unit j0 + 1 with j0 = 16 warp + 2 g — a lane's two units are adjacent in
-//     memory (the m index only names rows of W2 / dW2, any bijection works);
+// A warp owns 16 MT hidden units (MT = 1 or 2 m16 tiles) and walks the rows in groups of 8; the 16 / MT warps of a CTA share
+// the rows, so the dS2 tile is staged (already split into hi / lo) once per CTA.  Index choices that make every H1 element travel
+// exactly once and every dZ1 element leave as part of one 64- / 128-bit store per lane and row:
+//   * m-slot g + 8 hh of m-tile mt is hidden unit j0 + 2 mt + hh with j0 = 16 MT warp + 2 MT g — a lane's 2 MT units are
+//     adjacent in memory (the m index only names rows of W2 / dW2, any bijection works);
 //   * k-slot t of P2 is row 2t of the group, slot t + 4 row 2t + 1 (k is a summation index) — P2's A fragment
 //     {(g,t),(g+8,t),(g,t+4),(g+8,t+4)} is then the SAME set of elements as P1's C fragment {(g,2t),(g,2t+1),(g+8,2t),
 //     (g+8,2t+1)}: the H1 values a lane loaded for the mask of its dH1 outputs are its operand of P2.
