@@ -190,6 +190,23 @@ struct EpiLoss {
     template <int VEC, int G, int CPL>
     __device__ __forceinline__ void apply(int64_t row, int gl, unsigned gmask, int n_chunks,
                                           Chunk<VEC> (&acc)[CPL]) const {
+        const int y = __ldg(row_label + row);
+        if (y < 0 && !logits) {
+            // a row without a label (validation / test documents, topic rows) has no loss and a zero gradient: nothing to
+            // exponentiate (the whole group agrees on y: it is a property of the row)
+            if (gl == 0) row_loss[row] = 0.f;
+            if (dZ) {
+                Chunk<VEC> z;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) z.v[k] = 0.f;
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) {
+                    const int chunk = gl + i * G;
+                    if (chunk < n_chunks) chunk_st<VEC>(dZ + row * ldd + chunk * VEC, z);
+                }
+            }
+            return;
+        }
         float m = -INFINITY;
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
@@ -207,18 +224,21 @@ struct EpiLoss {
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(gmask, m, o, G));
+        // e = exp(z - max) is kept: the softmax of the gradient is e / sum(e), one exponential per element instead of two
+        Chunk<VEC> e[CPL];
         float se = 0.f;
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const int chunk = gl + i * G;
-            if (chunk >= n_chunks) continue;
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) se += expf(acc[i].v[k] - m);
+            for (int k = 0; k < VEC; ++k) {
+                e[i].v[k] = (chunk < n_chunks) ? expf(acc[i].v[k] - m) : 0.f;
+                se += e[i].v[k];
+            }
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) se += __shfl_xor_sync(gmask, se, o, G);
         const float lse = m + logf(se);
-        const int y = __ldg(row_label + row);
         // z_y lives in chunk y/VEC, owned by lane (y/VEC) % G, register (y/VEC) / G
         float zy = 0.f;
         if (y >= 0) {
@@ -233,6 +253,7 @@ struct EpiLoss {
         }
         if (gl == 0) row_loss[row] = (y >= 0) ? (lse - zy) * inv_count : 0.f;
         if (dZ) {
+            const float inv_se = 1.f / se;
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
                 const int chunk = gl + i * G;
@@ -241,7 +262,7 @@ struct EpiLoss {
                 Chunk<VEC> g;
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
-                    const float sm = expf(acc[i].v[k] - lse);
+                    const float sm = e[i].v[k] * inv_se;
                     g.v[k] = (y >= 0) ? (sm - ((col0 + k) == y ? 1.f : 0.f)) * inv_count : 0.f;
                 }
                 chunk_st<VEC>(dZ + row * ldd + col0, g);
