@@ -100,6 +100,29 @@ struct EpiStore {
             }
             return;
         }
+        if (!relu && drop_mode == 0) {
+            // linear epilogue (the class-sized products of layer 2: optional bias, optional upstream scale): decided once per
+            // row instead of testing every stage for every chunk
+            const float gsc = out_scale ? __ldg(out_scale) : 1.f;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int chunk = gl + i * G;
+                if (chunk >= n_chunks) continue;
+                const int col0 = chunk * VEC;
+                Chunk<VEC> y = acc[i];
+                if (bias) {
+                    const Chunk<VEC> bb = chunk_ldg<VEC>(bias + col0);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) y.v[k] += bb.v[k];
+                }
+                if (out_scale) {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) y.v[k] *= gsc;
+                }
+                chunk_st<VEC>(Y + row * ldy + col0, y);
+            }
+            return;
+        }
         Philox4 rnd = Philox4{0, 0, 0, 0};
         int rnd_cidx = -1;  // exact-half mode: the 128-column block `rnd` was drawn for
         const uint64_t offset = (drop_mode == 1 && offset_dev) ? this->offset + __ldg(offset_dev) : this->offset;
