@@ -55,6 +55,7 @@ constexpr int kNStages = 4;            // narrow kernels: hub stages
 constexpr int kNRing = 8;              // narrow kernels: document ring depth
 constexpr int kNPF = 6;                // ... jobs issued ahead
 constexpr size_t kSmemMax = 227 * 1024;
+constexpr double kDropDocWeight = 1.10;  // document-role weight of the dropout epilogue in the SM split (roles2_run_t)
 constexpr int32_t kNotShort = -1;      // rdesc.y of rows the document role does not produce (hub rows, padding)
 
 struct R2Args {
@@ -1918,6 +1919,12 @@ static int roles2_run_t(const tg_plan* pl, const StreamCall& c, const Epi& epi, 
     // the row-wise loss epilogue (exp / log / shuffles on 8 lanes per row) more than doubles the document role's work on a
     // class-sized operand (C4 shard, role-only runs: 2.46 ms against 1.08 ms on the same CTAs)
     if (!std::is_same<Epi, EpiStore>::value) doc_w *= 2.4;
+    // the dropout epilogue of the layer-1 forward (mask words, select, scale on 16 values per lane and row) makes the
+    // document role ~10 % heavier: at C3 the fused forward runs 0.857 ms with the plain product's 70 + 78 split and 0.823 ms
+    // with 64 + 84 (plain product: 0.770 / 0.808 ms) — the split follows the epilogue
+    if constexpr (std::is_same<Epi, EpiStore>::value) {
+        if (epi.drop_mode != 0) doc_w *= kDropDocWeight;
+    }
     split_sms(hub_w, doc_w, hslices * a.groups, dslices, a.n_chunks, (a.n_jobs + 4 / nq - 1) / (4 / nq), pl->r2_hub_pct, &a.hub_lanes,
               &a.doc_lanes);
     const size_t need = (size_t)a.hub_lanes * a.Kv * a.ldp * sizeof(float);
