@@ -1974,9 +1974,9 @@ static int roles2_narrow_run_t(const tg_plan* pl, const StreamCall& c, const Epi
     R2Args a;
     fill_common(a, pl, c);
     a.hub_slices = a.doc_slices = 1;
-    // measured balance points at C3, F = 20: 57 % hub CTAs for the plain product, 52 % when the document role also runs the
-    // log-softmax / cross-entropy epilogue
-    const int hub_pct = pl->r2_narrow_hub_pct >= 0 ? pl->r2_narrow_hub_pct : (std::is_same<Epi, EpiLoss>::value ? 52 : 57);
+    // measured balance points at C3, F = 20: 59 % hub CTAs for the plain product, 54 % when the document role also runs the
+    // log-softmax / cross-entropy epilogue (57 / 52 before the epilogues skipped unlabelled rows and per-chunk flag tests)
+    const int hub_pct = pl->r2_narrow_hub_pct >= 0 ? pl->r2_narrow_hub_pct : (std::is_same<Epi, EpiLoss>::value ? 54 : 59);
     int hub_lanes = (kNumSM * hub_pct / 100) / a.groups;
     if (hub_lanes < 1) hub_lanes = 1;
     if (hub_lanes > a.n_chunks) hub_lanes = a.n_chunks;
